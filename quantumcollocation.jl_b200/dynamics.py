@@ -1,0 +1,232 @@
+"""QuantumDynamics(integrators, traj): the reference's five-field dynamics object, evaluated on a B200.
+
+Reference surface (/root/reference/test/scripts/integrator_test_1qubit.jl:41-52):
+    dynamics = QuantumDynamics(f, Z)
+    dynamics.F(Z.datavec)
+    dynamics.∂F(Z.datavec), dynamics.∂F_structure
+    dynamics.μ∂²F(Z.datavec, μ), dynamics.μ∂²F_structure
+Python identifiers cannot contain ∂/²; the fields are spelled F, dF, dF_structure, mu_d2F, mu_d2F_structure.
+
+All arithmetic happens in libqcknot.so (hand-written sm_100a kernels) through the C-ABI in include/qcknot.h.
+There is no CPU path: construction fails without the library or without an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .integrators import AbstractIntegrator, DerivativeIntegrator, _QuantumIntegrator
+from .trajectory import NamedTrajectory
+
+
+class QcknotError(RuntimeError):
+    pass
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class QuantumDynamics:
+    """Stacks `integrators` over the knot points of `traj` (row order = integrator order, values knot-major).
+
+    knot_range=(t0, t1)       evaluate only the constraint blocks t0 <= t < t1 (0-based; one-knot halo is read);
+                              F/dF/mu_d2F then return that shard's contiguous segment of the global arrays.
+    integrator_range=(q0,q1)  ensemble sharding: evaluate only integrators q0 <= q < q1 (structures stay global).
+    """
+
+    def __init__(
+        self,
+        integrators: Sequence[AbstractIntegrator],
+        traj: NamedTrajectory,
+        eval_hessian: bool = True,
+        device: int = 0,
+        knot_range: Optional[Tuple[int, int]] = None,
+        integrator_range: Optional[Tuple[int, int]] = None,
+    ):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.integrators = list(integrators)
+        self.zdim = traj.dim
+        self.T_total = traj.T
+        t0, t1 = knot_range if knot_range is not None else (0, traj.T - 1)
+        if not (0 <= t0 < t1 <= traj.T - 1):
+            raise ValueError(f"knot_range {knot_range} outside [0, {traj.T - 1}]")
+        self.knot_range = (int(t0), int(t1))
+        self.T = t1 - t0 + 1  # knot points of this shard
+        self.eval_hessian = bool(eval_hessian)
+        self.free_time = traj.free_time
+        dt_off = traj.components[traj.timestep].start if traj.free_time else -1
+        dt_fixed = 0.0 if traj.free_time else float(traj.timestep)
+
+        descs = (_lib.IntegratorDesc * len(self.integrators))()
+        self._keep = []
+        for d, I in zip(descs, self.integrators):
+            d.kind, d.order = I.kind, getattr(I, "order", 0)
+            if isinstance(I, _QuantumIntegrator):
+                if I.freetime != traj.free_time:
+                    raise ValueError("integrator was built for a trajectory with a different timestep mode")
+                hd, hv = I.system.drift_reim(), I.system.drives_reim()
+                self._keep += [hd, hv]
+                d.levels, d.n_drives = I.system.levels, I.system.n_drives
+                d.state_off, d.state_len = I.state_components.start, len(I.state_components)
+                d.ctrl_off = I.drive_components.start
+                d.H_drift = hd.ctypes.data_as(C.POINTER(C.c_double))
+                d.H_drives = hv.ctypes.data_as(C.POINTER(C.c_double)) if hv.size else None
+            elif isinstance(I, DerivativeIntegrator):
+                d.state_off, d.state_len = I.x_components.start, len(I.x_components)
+                d.ctrl_off = I.dx_components.start
+            else:
+                raise TypeError(f"unsupported integrator {type(I).__name__}")
+        q0, q1 = integrator_range if integrator_range is not None else (0, 0)
+        self.integrator_range = (q0, q1) if integrator_range is not None else (0, len(self.integrators))
+        pd = _lib.ProblemDesc(self.T, self.zdim, dt_off, dt_fixed, len(self.integrators), int(self.eval_hessian),
+                              int(device), int(q0), int(q1), 0, descs)
+        rc = self._lib.qck_create(C.byref(pd), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.qck_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise QcknotError(f"qck_create failed ({rc}): {msg}")
+        dyn, nj, nh = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.qck_sizes(self._h, C.byref(dyn), C.byref(nj), C.byref(nh)))
+        self.dyn, self.nnzJ, self.nnzH = dyn.value, nj.value, nh.value
+        self.device = int(device)
+        self._J_struct = None
+        self._H_struct = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise QcknotError(f"libqcknot error {rc}: {self._lib.qck_last_error(self._h).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.qck_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_blocks(self) -> int:
+        return self.T - 1
+
+    def _Z(self, Z) -> np.ndarray:
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        t0, t1 = self.knot_range
+        if Z.size >= self.T_total * self.zdim and self.T != self.T_total:
+            Z = Z[t0 * self.zdim : (t1 + 1) * self.zdim]  # full datavec given to a shard
+        elif Z.size >= self.T * self.zdim:
+            Z = Z[: self.T * self.zdim]  # drop global (free-phase) variables: they never enter the dynamics
+        else:
+            raise ValueError(f"Z has {Z.size} entries, expected at least {self.T * self.zdim}")
+        return np.ascontiguousarray(Z)
+
+    def _mu(self, mu) -> np.ndarray:
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        t0, t1 = self.knot_range
+        if mu.size == (self.T_total - 1) * self.dyn and self.T != self.T_total:
+            mu = mu[t0 * self.dyn : t1 * self.dyn]
+        if mu.size != self.n_blocks * self.dyn:
+            raise ValueError(f"mu has {mu.size} entries, expected {self.n_blocks * self.dyn}")
+        return np.ascontiguousarray(mu)
+
+    # ---- the reference's five fields -------------------------------------------------------------------------------
+    def F(self, Z, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty(self.n_blocks * self.dyn) if out is None else out
+        self._check(self._lib.qck_eval_residual(self._h, _ptr(self._Z(Z)), _ptr(out)))
+        return out
+
+    def dF(self, Z, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty(self.n_blocks * self.nnzJ) if out is None else out
+        self._check(self._lib.qck_eval_jacobian(self._h, _ptr(self._Z(Z)), _ptr(out)))
+        return out
+
+    def mu_d2F(self, Z, mu, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty(self.n_blocks * self.nnzH) if out is None else out
+        self._check(self._lib.qck_eval_hessian(self._h, _ptr(self._Z(Z)), _ptr(self._mu(mu)), _ptr(out)))
+        return out
+
+    def eval_all(self, Z, mu=None, F=None, J=None, H=None):
+        """Fused residual + Jacobian + Hessian in one device pass (any output may be omitted with False)."""
+        F = np.empty(self.n_blocks * self.dyn) if F is None else (None if F is False else F)
+        J = np.empty(self.n_blocks * self.nnzJ) if J is None else (None if J is False else J)
+        want_h = self.eval_hessian and mu is not None and H is not False
+        H = (np.empty(self.n_blocks * self.nnzH) if H is None else H) if want_h else None
+        mu_ = self._mu(mu) if want_h else None
+        self._check(self._lib.qck_eval_all(self._h, _ptr(self._Z(Z)), _ptr(mu_), _ptr(F), _ptr(J), _ptr(H)))
+        return F, J, H
+
+    def _structure(self, fn, nnz) -> np.ndarray:
+        n = self.n_blocks * nnz
+        rows, cols = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        self._check(fn(self._h, self.knot_range[0], _ptr(rows), _ptr(cols)))
+        return np.stack([rows, cols], axis=1)
+
+    @property
+    def dF_structure(self) -> np.ndarray:
+        """(n, 2) int64 array of 1-based (row, col) pairs: the reference's Vector{Tuple{Int,Int}}."""
+        if self._J_struct is None:
+            self._J_struct = self._structure(self._lib.qck_jacobian_structure, self.nnzJ)
+        return self._J_struct
+
+    @property
+    def mu_d2F_structure(self) -> np.ndarray:
+        if self._H_struct is None:
+            self._H_struct = self._structure(self._lib.qck_hessian_structure, self.nnzH)
+        return self._H_struct
+
+    # ---- device-resident path (bench, multi-GPU) ----------------------------------------------------------------------
+    def eval_device(self, mask: int, dZ: int, dmu: int, dF: int, dJ: int, dH: int, stream: int = 0) -> None:
+        """Enqueue one pass on device pointers (ints, e.g. torch.Tensor.data_ptr()) on CUDA stream `stream`."""
+        self._check(self._lib.qck_eval_device(self._h, mask, dZ or None, dmu or None, dF or None, dJ or None,
+                                              dH or None, stream or None))
+
+    def device_buffers(self):
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self._check(self._lib.qck_device_buffers(self._h, *[C.byref(p) for p in ptrs]))
+        return tuple(p.value for p in ptrs)
+
+    def synchronize(self) -> None:
+        self._check(self._lib.qck_synchronize(self._h))
+
+    def shared_hessian_positions(self) -> np.ndarray:
+        n = C.c_int64()
+        self._check(self._lib.qck_shared_hessian_positions(self._h, C.byref(n), None))
+        pos = np.empty(n.value, dtype=np.int64)
+        if n.value:
+            self._check(self._lib.qck_shared_hessian_positions(self._h, C.byref(n), _ptr(pos)))
+        return pos
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.qck_launch_count(self._h, C.byref(n)))
+        return n.value
+
+
+def host_register(a: np.ndarray) -> None:
+    """Page-lock a numpy array (e.g. the solver's value buffer) for full-speed PCIe copies."""
+    rc = _lib.load().qck_host_register(_ptr(a), a.nbytes)
+    if rc != 0:
+        raise QcknotError(f"qck_host_register failed: {_lib.load().qck_last_error(None).decode()}")
+
+
+def host_unregister(a: np.ndarray) -> None:
+    _lib.load().qck_host_unregister(_ptr(a))
+
+
+def dense(vals, structure, shape) -> np.ndarray:
+    """test/test_utils.jl:14-27: matrix from (values, structure); duplicates sum; square => symmetric upper."""
+    M = np.zeros(shape)
+    s = np.asarray(structure)
+    np.add.at(M, (s[:, 0] - 1, s[:, 1] - 1), np.asarray(vals))
+    if shape[0] == shape[1]:
+        return np.triu(M) + np.triu(M, 1).T
+    return M

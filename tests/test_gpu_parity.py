@@ -1,0 +1,64 @@
+"""GPU parity: libqcknot.so (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerance: 1e-10 relative to the largest magnitude of the array (BASELINE.json north_star: "relative tolerance of
+1e-10 in FP64"); structures must be bit-exact."""
+import numpy as np
+import pytest
+
+import qcknot
+from qcknot import workloads as wl
+
+from helpers import oracle_dynamics, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def check(systems, traj, integrators, eval_hessian=True):
+    D = qcknot.QuantumDynamics(integrators, traj, eval_hessian=eval_hessian)
+    O = oracle_dynamics(integrators, traj, eval_hessian=eval_hessian)
+    assert (D.dyn, D.nnzJ, D.nnzH) == (O.dyn, O.nnzJ, O.nnzH)
+    assert np.array_equal(D.dF_structure, np.array(O.dF_structure))
+    Z = traj.datavec
+    mu = wl.random_multipliers(D.n_blocks * D.dyn)
+    F = D.F(Z)
+    J = D.dF(Z)
+    assert rel_err(F, O.F(Z)) < TOL
+    assert rel_err(J, O.dF(Z)) < TOL
+    if eval_hessian:
+        assert np.array_equal(D.mu_d2F_structure, np.array(O.mu_d2F_structure).reshape(-1, 2))
+        H = D.mu_d2F(Z, mu)
+        assert rel_err(H, O.mu_d2F(Z, mu)) < TOL
+        F2, J2, H2 = D.eval_all(Z, mu)  # fused pass must agree bitwise with the separate calls
+        assert np.array_equal(F, F2) and np.array_equal(J, J2) and np.array_equal(H, H2)
+    D.close()
+
+
+@pytest.mark.parametrize("free_time", [True, False])
+def test_hadamard_pade(free_time):
+    check(*wl.config("hadamard", T=12, free_time=free_time))
+
+
+def test_hadamard_no_hessian():
+    check(*wl.config("hadamard", T=6), eval_hessian=False)
+
+
+@pytest.mark.parametrize("free_time", [True, False])
+def test_cz_pade(free_time):
+    check(*wl.config("cz", T=6, free_time=free_time))
+
+
+@pytest.mark.parametrize("free_time", [True, False])
+def test_ket_pade(free_time):
+    check(*wl.config("ket", T=9, free_time=free_time))
+
+
+def test_sampling_pade():
+    check(*wl.config("sampling", T=4, n_systems=5))
+
+
+@pytest.mark.parametrize("levels,nd", [(3, 1), (4, 2), (5, 3), (6, 2)])
+def test_random_dense_systems(levels, nd):
+    sys_ = wl.random_hermitian_system(levels, nd, seed=levels * 10 + nd, scale=0.7)
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.3, seed=7)
+    check([sys_], traj, wl.build_integrators([sys_], traj))
