@@ -1,0 +1,37 @@
+"""Builds the oracle's view of a problem described with the product's host objects (same systems, same layout,
+same integrator order).  TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu-baseline legs.  Duck-typed on class names so that the oracle never imports the product package."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import knot_oracle as ko
+
+_CLS = {
+    "UnitaryPadeIntegrator": ko.UnitaryPadeIntegrator,
+    "UnitaryExponentialIntegrator": ko.UnitaryExponentialIntegrator,
+    "QuantumStatePadeIntegrator": ko.QuantumStatePadeIntegrator,
+    "QuantumStateExponentialIntegrator": ko.QuantumStateExponentialIntegrator,
+}
+
+
+def oracle_dynamics(integrators, traj, eval_hessian: bool = True) -> ko.QuantumDynamics:
+    comps = {n: (r.start, len(r)) for n, r in traj.components.items()}
+    layout = ko.Layout(comps, traj.T, traj.timestep if traj.free_time else None,
+                       0.0 if traj.free_time else traj.timestep, traj.global_dim)
+    out = []
+    for I in integrators:
+        name = type(I).__name__
+        if name == "DerivativeIntegrator":
+            out.append(ko.DerivativeIntegrator(I.x_name, I.dx_name, layout))
+        else:
+            sys_ = ko.QuantumSystem(I.system.H_drift, I.system.H_drives)
+            kw = {"order": I.order} if getattr(I, "order", 0) else {}
+            out.append(_CLS[name](I.state_name, I.control_name, sys_, layout, **kw))
+    return ko.QuantumDynamics(out, layout, eval_hessian=eval_hessian)
+
+
+def rel_err(a, b) -> float:
+    """max |a-b| relative to max(1, max|b|): the 1e-10 criterion of BASELINE.json's north_star."""
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if a.size else 0.0

@@ -1,0 +1,131 @@
+"""CPU tests of the host logic and the C-ABI: the library loads, exports every symbol include/qcknot.h declares,
+builds the reference's sparsity structures bit-exactly (structure-only handles need no GPU), and fails loudly --
+never falls back -- when asked to evaluate without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qcknot
+from qcknot import workloads as wl
+from oracle.bridge import oracle_dynamics
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "qcknot.h")).read()
+    return sorted(set(re.findall(r"\b(qck_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(qcknot.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"libqcknot.so does not export {s}"
+    assert sorted(qcknot._lib.EXPORTS) == syms
+    assert b"sm_100a" in qcknot._lib.load().qck_version()
+
+
+def test_no_reference_to_oracle_in_product():
+    """The product path must never import or link the oracle."""
+    pkg = os.path.join(ROOT, "quantumcollocation.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().lower(), f"{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("hadamard", {}), ("hadamard", {"free_time": False}), ("cz", {"T": 4}), ("ket", {"T": 7}),
+    ("ket", {"T": 4, "free_time": False}), ("sampling", {"T": 3, "n_systems": 5}),
+])
+def test_structures_bit_exact_vs_oracle(name, kw):
+    systems, traj, integrators = wl.config(name, **kw)
+    for eval_hessian in (True, False):
+        D = qcknot.QuantumDynamics(integrators, traj, eval_hessian=eval_hessian, device=-1)
+        O = oracle_dynamics(integrators, traj, eval_hessian=eval_hessian)
+        assert (D.dyn, D.nnzJ, D.nnzH) == (O.dyn, O.nnzJ, O.nnzH)
+        assert np.array_equal(D.dF_structure, np.array(O.dF_structure, dtype=np.int64).reshape(-1, 2))
+        assert np.array_equal(D.mu_d2F_structure, np.array(O.mu_d2F_structure, dtype=np.int64).reshape(-1, 2))
+        D.close()
+
+
+def test_survey_size_table():
+    # SURVEY.md section 8 size table (pade column): C1 104/58, C2 6674/1643 (zdim 175, dyn 170), C5 (S=256) 155,664/49,162
+    for name, kw, want in (("hadamard", {}, (12, 104, 58, 15)), ("cz", {"T": 3}, (170, 6674, 1643, 175)),
+                           ("sampling", {"T": 3, "n_systems": 256}, (8196, 155664, 49162, 8199))):
+        systems, traj, integrators = wl.config(name, **kw)
+        D = qcknot.QuantumDynamics(integrators, traj, device=-1)
+        assert (D.dyn, D.nnzJ, D.nnzH, D.zdim) == want
+        D.close()
+
+
+def test_knot_shard_structures_concatenate_to_global():
+    systems, traj, integrators = wl.config("hadamard", T=11)
+    full = qcknot.QuantumDynamics(integrators, traj, device=-1)
+    Js, Hs = [], []
+    for t0, t1 in qcknot.sharding.knot_shards(traj.T - 1, 3):
+        S = qcknot.QuantumDynamics(integrators, traj, device=-1, knot_range=(t0, t1))
+        assert S.n_blocks == t1 - t0
+        Js.append(S.dF_structure)
+        Hs.append(S.mu_d2F_structure)
+    assert np.array_equal(np.concatenate(Js), full.dF_structure)
+    assert np.array_equal(np.concatenate(Hs), full.mu_d2F_structure)
+
+
+def test_shared_hessian_positions_of_sampling_problem():
+    systems, traj, integrators = wl.config("sampling", T=3, n_systems=4)
+    D = qcknot.QuantumDynamics(integrators, traj, device=-1)
+    pos = D.shared_hessian_positions()
+    nd = systems[0].n_drives
+    assert len(pos) == nd * (nd + 1) // 2 + nd + 1  # a x a, a x dt, dt x dt
+    s = D.mu_d2F_structure[pos]  # first knot block
+    a = traj.components["a"]
+    dt = traj.components["Δt"].start
+    for r, c in s - 1:
+        assert (r in a or r == dt) and (c in a or c == dt)
+
+
+def test_evaluation_without_device_fails_loudly():
+    systems, traj, integrators = wl.config("hadamard", T=5)
+    D = qcknot.QuantumDynamics(integrators, traj, device=-1)
+    with pytest.raises(qcknot.QcknotError, match="no CPU evaluation path"):
+        D.F(traj.datavec)
+    with pytest.raises(qcknot.QcknotError, match="no CPU evaluation path"):
+        D.dF(traj.datavec)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(qcknot.QcknotError, match="no CPU fallback"):
+            qcknot.QuantumDynamics(integrators, traj, device=0)
+
+
+def test_bad_arguments_are_errors_not_crashes():
+    systems, traj, integrators = wl.config("hadamard", T=5)
+    with pytest.raises(ValueError):
+        qcknot.QuantumDynamics(integrators, traj, device=-1, knot_range=(3, 3))
+    with pytest.raises(KeyError):
+        qcknot.UnitaryPadeIntegrator("nope", "a", systems[0], traj)
+    with pytest.raises(ValueError):  # state length inconsistent with the system's levels
+        qcknot.UnitaryPadeIntegrator("a", "a", systems[0], traj)
+    bad = qcknot.UnitaryPadeIntegrator("Ũ⃗", "a", systems[0], traj, order=5)
+    with pytest.raises(qcknot.QcknotError, match="order"):
+        qcknot.QuantumDynamics([bad], traj, device=-1)
+    # raw ABI: NULL description
+    lib = qcknot._lib.load()
+    h = C.c_void_p()
+    assert lib.qck_create(None, C.byref(h)) != 0 and not h.value
+    assert b"empty" in lib.qck_last_error(None)
+
+
+def test_trajectory_layout_matches_reference_fixture():
+    # component order [state, a, da, dda, dt] and datavec = vec(data) column-major (test_utils.jl:52-118)
+    systems, traj, _ = wl.config("hadamard", T=5)
+    assert list(traj.names) == ["Ũ⃗", "a", "da", "dda", "Δt"]
+    assert traj.dim == 15 and traj.dims.states == 12  # integrator_test_1qubit.jl:44 uses Z.dims.states
+    z = traj.datavec
+    assert np.array_equal(z[15:30], traj.data[:, 1])
+    assert np.array_equal(qcknot.operator_to_iso_vec(np.eye(2)), [1, 0, 0, 0, 0, 1, 0, 0])
