@@ -103,6 +103,7 @@ struct HEntry {
     int cls, member;  // quantum class/member or -1
     uint16_t src;     // scratch slot (+sign) for quantum contributors
     int aux_op, aux_i0;  // for derivative contributors
+    int grp, period;     // output group of the integrator (segments never span groups) and its repeat period (0 = none)
 };
 struct JEntry {
     long long key;
@@ -110,7 +111,36 @@ struct JEntry {
     uint16_t src;
     int aux_op, aux_i0;
     double aux_c;
+    int grp, period;
 };
+struct MapEntry {
+    long long dst;
+    uint16_t src;
+    int grp, period;
+    bool operator<(const MapEntry& o) const { return dst < o.dst; }
+};
+
+// Cut one member's (destination-sorted) entries into segments and append the slot table.  Members of one class
+// must produce identical tables and segment shapes (only `dst` differs); returns false otherwise.
+bool make_segments(const std::vector<MapEntry>& e, long long split, std::vector<QckSeg>& segs, std::vector<uint16_t>& tab) {
+    size_t k = 0;
+    while (k < e.size()) {
+        size_t k2 = k + 1;
+        while (k2 < e.size() && e[k2].dst == e[k2 - 1].dst + 1 && e[k2].grp == e[k].grp && ((e[k2].dst < split) == (e[k].dst < split))) ++k2;
+        int len = (int)(k2 - k), period = len;
+        int p = e[k].period;
+        if (p > 0 && len % p == 0 && len / p >= 2) {
+            bool ok = true;
+            for (size_t u = k + p; u < k2 && ok; ++u) ok = e[u].src == e[u - p].src;
+            if (ok) period = p;
+        }
+        QckSeg sg{(int)e[k].dst, len, (int)tab.size(), period};
+        for (int u = 0; u < period; ++u) tab.push_back(e[k + u].src);
+        segs.push_back(sg);
+        k = k2;
+    }
+    return true;
+}
 
 // slot of iso-vec element i of state-type matrix `sidx`
 inline int slot_state(const QckClassDev& c, int sidx, int i) {
@@ -152,7 +182,7 @@ int build(qck_handle* h) {
             c.NP = ((I.N + QCK_TILE - 1) / QCK_TILE) * QCK_TILE;
             c.ncp = I.unitary() ? c.NP : 1;
             c.free_time = free_time; c.dt_off = h->dt_off; c.zdim = zdim; c.dyn = h->dyn; c.dt_fixed = h->dt_fixed;
-            qck_scratch_layout(c, h->eval_hessian);
+            qck_scratch_layout(c);
             if (c.scratch_doubles > 32768 || (size_t)c.scratch_doubles * 8 > 227 * 1024)
                 return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d scratch doubles per knot; this build supports at most %d",
                             I.N, I.nd, c.scratch_doubles, 227 * 1024 / 8);
@@ -186,51 +216,54 @@ int build(qck_handle* h) {
             const QckClassDev& c = h->classes[ci].dev;
             const int N = I.N, n2 = 2 * N;
             // Jacobian: state_t block (-F or -E), state_t+1 block (+B or identity), controls, timestep
+            const int blk = n2 * n2;  // one kron(I_N, .) block repeats every 2N columns of 2N rows
+            const int DRV = QS_FIXED;
             for (int cb = 0; cb < I.nc; ++cb)
                 for (int r = 0; r < n2; ++r)
                     for (int qq = 0; qq < n2; ++qq) {
-                        JE.push_back({jkey(R0 + cb * n2 + qq, I.state_off + cb * n2 + r), ci, mi, slot_iso(c, QA_F, qq, r, true), 0, 0, 0});
+                        JE.push_back({jkey(R0 + cb * n2 + qq, I.state_off + cb * n2 + r), ci, mi, slot_iso(c, QA_F, qq, r, true), 0, 0, 0, 0, blk});
                         if (I.pade())
-                            JE.push_back({jkey(R0 + cb * n2 + qq, zdim + I.state_off + cb * n2 + r), ci, mi, slot_iso(c, QA_B, qq, r, false), 0, 0, 0});
+                            JE.push_back({jkey(R0 + cb * n2 + qq, zdim + I.state_off + cb * n2 + r), ci, mi, slot_iso(c, QA_B, qq, r, false), 0, 0, 0, 1, blk});
                     }
             if (!I.pade())
                 for (int i = 0; i < I.dim; ++i)
-                    JE.push_back({jkey(R0 + i, zdim + I.state_off + i), ci, mi, (uint16_t)(c.off_X + QX_ONE), 0, 0, 0});
+                    JE.push_back({jkey(R0 + i, zdim + I.state_off + i), ci, mi, (uint16_t)(c.off_X + QX_ONE), 0, 0, 0, 1, 1});
             for (int j = 0; j < I.nd; ++j)
                 for (int i = 0; i < I.dim; ++i)
-                    JE.push_back({jkey(R0 + i, I.ctrl_off + j), ci, mi, (uint16_t)slot_state(c, QS_FIXED + QD_COUNT * j + QD_P, i), 0, 0, 0});
+                    JE.push_back({jkey(R0 + i, I.ctrl_off + j), ci, mi, (uint16_t)slot_state(c, DRV + QD_COUNT * j + QD_TA, i), 0, 0, 0, 2 + j, 0});
             if (free_time)
                 for (int i = 0; i < I.dim; ++i)
-                    JE.push_back({jkey(R0 + i, h->dt_off), ci, mi, (uint16_t)slot_state(c, QS_AS, i), 0, 0, 0});
+                    JE.push_back({jkey(R0 + i, h->dt_off), ci, mi, (uint16_t)slot_state(c, QS_AS, i), 0, 0, 0, 2 + I.nd, 0});
             if (h->eval_hessian) {
-                for (int j = 0; j < I.nd; ++j)
+                const int nd = I.nd;
+                for (int j = 0; j < nd; ++j)
                     for (int i = 0; i < I.dim; ++i) {
-                        HE.push_back({hkey(I.state_off + i, I.ctrl_off + j), q, ci, mi, (uint16_t)slot_state(c, QS_FIXED + QD_COUNT * j + QD_N2, i), 0, 0});
+                        HE.push_back({hkey(I.state_off + i, I.ctrl_off + j), q, ci, mi, (uint16_t)slot_state(c, DRV + QD_COUNT * j + QD_KA0, i), 0, 0, j, 0});
                         if (I.pade())
-                            HE.push_back({hkey(I.ctrl_off + j, zdim + I.state_off + i), q, ci, mi, (uint16_t)slot_state(c, QS_FIXED + QD_COUNT * j + QD_AHN1, i), 0, 0});
+                            HE.push_back({hkey(I.ctrl_off + j, zdim + I.state_off + i), q, ci, mi, (uint16_t)slot_state(c, DRV + QD_COUNT * j + QD_KA1, i), 0, 0, 2 * nd + 4, 0});
                     }
-                for (int i = 0; i < I.nd; ++i)
-                    for (int j = i; j < I.nd; ++j)
-                        HE.push_back({hkey(I.ctrl_off + i, I.ctrl_off + j), q, ci, mi, (uint16_t)(c.off_X + qx_haa(I.nd, i, j)), 0, 0});
+                for (int i = 0; i < nd; ++i)
+                    for (int j = i; j < nd; ++j)
+                        HE.push_back({hkey(I.ctrl_off + i, I.ctrl_off + j), q, ci, mi, (uint16_t)(c.off_X + qx_haa(nd, i, j)), 0, 0, nd + j, 0});
                 if (free_time) {
                     for (int i = 0; i < I.dim; ++i) {
-                        HE.push_back({hkey(I.state_off + i, h->dt_off), q, ci, mi, (uint16_t)slot_state(c, QS_AHM, i), 0, 0});
+                        HE.push_back({hkey(I.state_off + i, h->dt_off), q, ci, mi, (uint16_t)slot_state(c, QS_AHM, i), 0, 0, 2 * nd + 1, 0});
                         if (I.pade())
-                            HE.push_back({hkey(h->dt_off, zdim + I.state_off + i), q, ci, mi, (uint16_t)slot_state(c, QS_AHAHM, i), 0, 0});
+                            HE.push_back({hkey(h->dt_off, zdim + I.state_off + i), q, ci, mi, (uint16_t)slot_state(c, QS_AHAHM, i), 0, 0, 2 * nd + 4, 0});
                     }
-                    for (int j = 0; j < I.nd; ++j)
-                        HE.push_back({hkey(I.ctrl_off + j, h->dt_off), q, ci, mi, (uint16_t)(c.off_X + QX_HAH + j), 0, 0});
-                    HE.push_back({hkey(h->dt_off, h->dt_off), q, ci, mi, (uint16_t)(c.off_X + QX_HHH), 0, 0});
+                    for (int j = 0; j < nd; ++j)
+                        HE.push_back({hkey(I.ctrl_off + j, h->dt_off), q, ci, mi, (uint16_t)(c.off_X + QX_HAH + j), 0, 0, 2 * nd + 2, 0});
+                    HE.push_back({hkey(h->dt_off, h->dt_off), q, ci, mi, (uint16_t)(c.off_X + qx_hhh(nd)), 0, 0, 2 * nd + 2, 0});
                 }
             }
         } else {
             for (int i = 0; i < I.dim; ++i) {
-                JE.push_back({jkey(R0 + i, I.state_off + i), -1, q, 0, QAUX_CONST, 0, -1.0});
-                JE.push_back({jkey(R0 + i, zdim + I.state_off + i), -1, q, 0, QAUX_CONST, 0, 1.0});
-                JE.push_back({jkey(R0 + i, I.ctrl_off + i), -1, q, 0, QAUX_NEG_DT, 0, 0.0});
-                if (free_time) JE.push_back({jkey(R0 + i, h->dt_off), -1, q, 0, QAUX_NEG_Z, I.ctrl_off + i, 0.0});
+                JE.push_back({jkey(R0 + i, I.state_off + i), -1, q, 0, QAUX_CONST, 0, -1.0, 0, 0});
+                JE.push_back({jkey(R0 + i, zdim + I.state_off + i), -1, q, 0, QAUX_CONST, 0, 1.0, 0, 0});
+                JE.push_back({jkey(R0 + i, I.ctrl_off + i), -1, q, 0, QAUX_NEG_DT, 0, 0.0, 0, 0});
+                if (free_time) JE.push_back({jkey(R0 + i, h->dt_off), -1, q, 0, QAUX_NEG_Z, I.ctrl_off + i, 0.0, 0, 0});
                 if (free_time && h->eval_hessian)
-                    HE.push_back({hkey(I.ctrl_off + i, h->dt_off), q, -1, -1, 0, QAUX_NEG_MU, R0 + i});
+                    HE.push_back({hkey(I.ctrl_off + i, h->dt_off), q, -1, -1, 0, QAUX_NEG_MU, R0 + i, 0, 0});
             }
         }
     }
@@ -255,25 +288,27 @@ int build(qck_handle* h) {
     h->nnzH = (long long)h->Hr.size();
     std::vector<int> ncontrib((size_t)h->nnzH, 0);
     for (size_t k = 0; k < HE.size(); ++k) ++ncontrib[hpos[k]];
-    // shared positions get partial columns (active contributors only, ascending integrator order)
+    // shared positions get partial columns: one run of consecutive columns per active contributor (ascending
+    // integrator order), so that a contributor's shared entries stay contiguous; the reduce kernel sums the columns of
+    // a position in ascending integrator order.
     std::vector<long long> hdst(HE.size(), -1);  // destination: < nnzH direct, >= nnzH partial column
     h->npart = 0;
-    h->sh_ptr.push_back(0);
-    for (size_t k = 0; k < HE.size();) {
-        size_t k2 = k;
-        while (k2 < HE.size() && hpos[k2] == hpos[k]) ++k2;
-        if (ncontrib[hpos[k]] > 1) {
-            h->shared_positions.push_back(hpos[k]);
-            h->sh_pos.push_back(hpos[k]);
-            for (size_t u = k; u < k2; ++u) {
-                bool act = HE[u].contrib >= h->ib && HE[u].contrib < h->ie;
-                if (!act) continue;
-                hdst[u] = h->nnzH + h->npart;
-                h->sh_cols.push_back(h->npart++);
-            }
-            h->sh_ptr.push_back((int)h->sh_cols.size());
-        } else hdst[k] = hpos[k];
-        k = k2;
+    {
+        std::vector<size_t> shared_entries;
+        for (size_t k = 0; k < HE.size(); ++k) {
+            if (ncontrib[hpos[k]] > 1) {
+                if (k == 0 || hpos[k] != hpos[k - 1]) { h->shared_positions.push_back(hpos[k]); h->sh_pos.push_back(hpos[k]); }
+                if (HE[k].contrib >= h->ib && HE[k].contrib < h->ie) shared_entries.push_back(k);
+            } else hdst[k] = hpos[k];
+        }
+        std::stable_sort(shared_entries.begin(), shared_entries.end(), [&](size_t a, size_t b) { return HE[a].contrib < HE[b].contrib; });
+        for (size_t k : shared_entries) hdst[k] = h->nnzH + h->npart++;
+        std::map<int, int> slot_of_pos;
+        for (size_t i = 0; i < h->sh_pos.size(); ++i) slot_of_pos[h->sh_pos[i]] = (int)i;
+        std::vector<std::vector<int>> cols(h->sh_pos.size());
+        for (size_t k : shared_entries) cols[slot_of_pos[hpos[k]]].push_back((int)(hdst[k] - h->nnzH));
+        h->sh_ptr.push_back(0);
+        for (auto& v : cols) { for (int cidx : v) h->sh_cols.push_back(cidx); h->sh_ptr.push_back((int)h->sh_cols.size()); }
     }
 
     // ---- per-class maps ---------------------------------------------------------------------------------------------------------
@@ -281,27 +316,36 @@ int build(qck_handle* h) {
         ClassHost& C = h->classes[ci];
         QckClassDev& c = C.dev;
         const int nm = c.n_members;
-        std::vector<std::vector<std::pair<uint32_t, uint16_t>>> mj(nm), mh(nm);
+        std::vector<std::vector<MapEntry>> mj(nm), mh(nm);
         for (size_t k = 0; k < JE.size(); ++k)
-            if (JE[k].cls == (int)ci) mj[JE[k].member].push_back({(uint32_t)k, JE[k].src});
+            if (JE[k].cls == (int)ci) mj[JE[k].member].push_back({(long long)k, JE[k].src, JE[k].grp, JE[k].period});
         for (size_t k = 0; k < HE.size(); ++k)
-            if (HE[k].cls == (int)ci && hdst[k] >= 0) mh[HE[k].member].push_back({(uint32_t)hdst[k], HE[k].src});
-        // inactive members keep empty H maps (hdst = -1 for shared) but must be uniform: pad with their own direct entries
-        c.cntJ = nm ? (int)mj[0].size() : 0;
-        c.cntH = 0;
-        for (int m2 = C.member_begin; m2 < C.member_end; ++m2) c.cntH = std::max(c.cntH, (int)mh[m2].size());
-        std::vector<uint32_t> posJ((size_t)nm * c.cntJ), posH((size_t)nm * c.cntH);
-        std::vector<uint16_t> srcJ((size_t)nm * c.cntJ), srcH((size_t)nm * c.cntH);
-        for (int m2 = 0; m2 < nm; ++m2) {
-            if ((int)mj[m2].size() != c.cntJ) return fail(h, QCK_EINVAL, "internal: non-uniform Jacobian map in a class");
-            std::sort(mj[m2].begin(), mj[m2].end());
-            std::sort(mh[m2].begin(), mh[m2].end());
-            for (int k = 0; k < c.cntJ; ++k) { posJ[(size_t)m2 * c.cntJ + k] = mj[m2][k].first; srcJ[(size_t)m2 * c.cntJ + k] = mj[m2][k].second; }
-            if (m2 >= C.member_begin && m2 < C.member_end) {
-                if ((int)mh[m2].size() != c.cntH) return fail(h, QCK_EINVAL, "internal: non-uniform Hessian map in a class");
-                for (int k = 0; k < c.cntH; ++k) { posH[(size_t)m2 * c.cntH + k] = mh[m2][k].first; srcH[(size_t)m2 * c.cntH + k] = mh[m2][k].second; }
+            if (HE[k].cls == (int)ci && hdst[k] >= 0) mh[HE[k].member].push_back({hdst[k], HE[k].src, HE[k].grp, HE[k].period});
+        std::vector<uint16_t> tab;
+        std::vector<QckSeg> segs;
+        c.nsegJ = c.nsegH = 0;
+        {
+            std::vector<std::vector<QckSeg>> per_member(nm);
+            bool first = true;
+            for (int m2 = C.member_begin; m2 < C.member_end; ++m2) {  // only active members are ever launched
+                std::vector<uint16_t> t2;
+                std::vector<QckSeg> sj, sh;
+                std::sort(mj[m2].begin(), mj[m2].end());
+                std::sort(mh[m2].begin(), mh[m2].end());
+                make_segments(mj[m2], (long long)1 << 60, sj, t2);
+                make_segments(mh[m2], h->nnzH, sh, t2);
+                if (first) { tab = t2; c.nsegJ = (int)sj.size(); c.nsegH = (int)sh.size(); first = false; }
+                if (t2 != tab || (int)sj.size() != c.nsegJ || (int)sh.size() != c.nsegH)
+                    return fail(h, QCK_EINVAL, "integrators of one kind must see the same relative component order (state/control/timestep layout differs between members)");
+                per_member[m2] = sj;
+                per_member[m2].insert(per_member[m2].end(), sh.begin(), sh.end());
             }
+            const int ns = c.nsegJ + c.nsegH;
+            segs.assign((size_t)nm * std::max(ns, 1), QckSeg{0, 0, 0, 1});
+            for (int m2 = C.member_begin; m2 < C.member_end; ++m2)
+                for (int u = 0; u < ns; ++u) segs[(size_t)m2 * ns + u] = per_member[m2][u];
         }
+        c.tab_len = (int)tab.size();
         // constants: A0 = -i H_drift, A_j = -i H_j dense, and ELL forms of A_j and A_j^H
         const int N = c.N, nd = c.nd;
         int W = 1;
@@ -352,8 +396,10 @@ int build(qck_handle* h) {
                     }
         }
         cudaError_t e;
-        if ((e = upload(posJ, &c.posJ, C.allocs)) != cudaSuccess || (e = upload(srcJ, &c.srcJ, C.allocs)) != cudaSuccess ||
-            (e = upload(posH, &c.posH, C.allocs)) != cudaSuccess || (e = upload(srcH, &c.srcH, C.allocs)) != cudaSuccess ||
+        qck_smem_finalize(c);
+        if ((size_t)c.sm_bytes > 227 * 1024)
+            return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024);
+        if ((e = upload(tab, &c.tab, C.allocs)) != cudaSuccess || (e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||
             (e = upload(cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(ellc, &c.ell_col, C.allocs)) != cudaSuccess ||
             (e = upload(soff, &c.state_off, C.allocs)) != cudaSuccess || (e = upload(coff, &c.ctrl_off, C.allocs)) != cudaSuccess ||
             (e = upload(roff, &c.row_off, C.allocs)) != cudaSuccess)
@@ -392,12 +438,14 @@ int run(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, doubl
     L.Z = dZ; L.mu = dmu; L.F = dF; L.J = dJ; L.H = dH; L.partial = h->dpartial;
     L.n_knots = h->T - 1; L.nnzJ = h->nnzJ; L.nnzH = h->nnzH; L.npart = h->npart; L.mask = mask;
     bool aux_done = h->aux.empty();
+    const bool fuse_aux = (int)h->aux.size() <= qck_fused_aux_limit();
     int launches = 0;
     for (auto& C : h->classes) {
         if (C.member_end <= C.member_begin) continue;
         L.c = C.dev; L.member_begin = C.member_begin; L.member_end = C.member_end;
-        L.aux = aux_done ? nullptr : h->d_aux; L.n_aux = aux_done ? 0 : (int)h->aux.size();
-        aux_done = true;
+        const bool take_aux = !aux_done && fuse_aux;
+        L.aux = take_aux ? h->d_aux : nullptr; L.n_aux = take_aux ? (int)h->aux.size() : 0;
+        if (take_aux) aux_done = true;
         int rc = qck_launch_quantum(L, h->sm_count, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "quantum kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }

@@ -12,22 +12,25 @@
 
 // ---- scratch layout of the Pade-4 kernel (indices of matrices inside the CTA's shared-memory scratch) --------
 // "A-type" matrices are NP x NP complex, "state-type" are NP x ncp complex (ncp = NP for unitaries, 1 for kets).
-enum { QA_A = 0, QA_AH = 1, QA_A2 = 2, QA_F = 3, QA_B = 4, QA_COUNT = 5 };
-// state-type, fixed part.  Several slots are overwritten by the final outputs during assembly:
-//   D -> R (residual), AS -> Th (d/ddt), AhM -> Kh0 (state_t x dt), AhAhM -> Kh1 (dt x state_t+1)
+// Several slots are overwritten in place by the final outputs during assembly (the "->" notes).
+enum { QA_A = 0, QA_AH = 1 /* -> B */, QA_A2 = 2 /* -> F */, QA_COUNT = 3, QA_B = QA_AH, QA_F = QA_A2 };
+// state-type, fixed part:  D -> R (residual), AS -> Th (d/ddt), AhM -> Kh0 (state_t x dt), AhAhM -> Kh1 (dt x state_t+1)
 enum { QS_D = 0, QS_S = 1, QS_M = 2, QS_AD = 3, QS_AS = 4, QS_AHM = 5, QS_AAD = 6, QS_AHAHM = 7, QS_FIXED = 8 };
-// state-type, per drive j (index QS_FIXED + 7*j + k):
-//   P -> Ta (d/da_j), N2 -> Ka0 (state_t x a_j), AhN1 -> Ka1 (a_j x state_t+1)
-enum { QD_P = 0, QD_Q1 = 1, QD_N1 = 2, QD_Q2 = 3, QD_N2 = 4, QD_AQ1 = 5, QD_AHN1 = 6, QD_COUNT = 7 };
-// scalar slots (doubles) after the matrices
-enum { QX_ONE = 0, QX_HHH = 1, QX_HAH = 2 /* + j */ };
-static inline __host__ __device__ int qx_haa(int nd, int i, int j) { return QX_HAH + nd + i * nd + j; }
+// state-type, per drive j (index QS_FIXED + QD_COUNT*j + k):
+//   Q1 = A_j D,  N1 = A_j^H M -> Ka0 (state_t x a_j),  AQ1 = A (A_j D) -> Ta (d/da_j),  AhN1 = A^H (A_j^H M) -> Ka1 (a_j x state_t+1)
+enum { QD_Q1 = 0, QD_N1 = 1, QD_AQ1 = 2, QD_AHN1 = 3, QD_COUNT = 4, QD_KA0 = QD_N1, QD_TA = QD_AQ1, QD_KA1 = QD_AHN1 };
+// scalar slots (doubles) after the matrices: [ONE | Hah[0..nd) | Hhh | Haa column-wise (j*nd + i, i <= j)]
+enum { QX_ONE = 0, QX_HAH = 1 /* + j */ };
+static inline __host__ __device__ int qx_hhh(int nd) { return QX_HAH + nd; }
+static inline __host__ __device__ int qx_haa(int nd, int i, int j) { return QX_HAH + nd + 1 + j * nd + i; }
 
-// ---- scratch layout of the exponential kernel -----------------------------------------------------------------
-// All N x N ("A-type") unless noted; see qck_kernels.cu for the algorithm.
-struct QckExpLayout {
-    int n_a;  // number of A-type matrices
-    int n_s;  // number of state-type matrices
+// One contiguous run of output positions of one integrator: out[dst + k] = +-scratch[tab[src_off + k % period]].
+// period < len marks the kron(I_N, .) blocks: the same 2N x 2N values are stored len/period times.
+struct QckSeg {
+    int dst;      // first position inside the knot block (Hessian: >= nnzH means partial column dst - nnzH)
+    int len;
+    int src_off;  // into the class table of scratch slots (uint16, bit 15 = negate)
+    int period;
 };
 
 // One auxiliary (derivative-integrator) entry of a knot block; evaluated by a single thread.
@@ -59,12 +62,14 @@ struct QckClassDev {
     int cmat_stride;
     const int* ell_col;  // [member][nd*2*N*W]
     int ell_stride;
-    // output maps, per member, cnt entries each
-    int cntJ, cntH;
-    const uint32_t* posJ;
-    const uint16_t* srcJ;  // bit 15 = negate
-    const uint32_t* posH;
-    const uint16_t* srcH;
+    // output maps: class-level table of scratch slots + per-member segments [member][nsegJ + nsegH]
+    const uint16_t* tab;
+    int tab_len;
+    int nsegJ, nsegH;
+    const QckSeg* segs;
+    // shared-memory carve-up (byte offsets from the dynamic smem base; all 16-byte aligned)
+    int sm_tab, sm_seg, sm_ell, sm_stage, sm_bytes;
+    int seg_bytes, ell_bytes;  // size of ONE buffer of the double-buffered per-member tables
 };
 
 struct QckLaunch {
@@ -94,7 +99,9 @@ struct QckReduce {  // fixed-order reduction of shared Hessian positions
 // kernel launchers (qck_kernels.cu).  Return cudaError_t as int.
 int qck_launch_quantum(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches);
 int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches);
+int qck_fused_aux_limit(void);  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,
                       int npart, cudaStream_t stream, int* launches);
 // scratch sizing shared by host map builder and kernels
-void qck_scratch_layout(QckClassDev& c, int eval_hessian);
+void qck_scratch_layout(QckClassDev& c);   // phase 1: matrices + scalars (needed to compute slots)
+void qck_smem_finalize(QckClassDev& c);    // phase 2: tables + staging, after W / tab_len / nseg are known

@@ -13,8 +13,9 @@
 //    flops; the iso layout only appears in the load of z_t and in the output maps;
 //  * small dense complex products run on the FP64 pipe from shared memory with 3x3 complex register tiles;
 //    products with the constant drive matrices use a fixed-width sparse (ELL) form;
-//  * every structural nonzero of the knot block has a precomputed (position, scratch slot, sign) map entry, so
-//    the "scatter" is a gather from shared memory followed by position-ordered, coalesced 8-byte stores;
+//  * every structural nonzero of the knot block belongs to a precomputed output segment (first position, length,
+//    table of scratch slots + signs, repeat period) held in shared memory, so the "scatter" is a gather from
+//    shared memory followed by position-ordered, coalesced 8-byte stores with no global loads in the loop;
 //  * Hessian entries that several integrators contribute to (shared controls) go to a partial buffer that a
 //    second kernel reduces in fixed integrator order (bitwise run-to-run reproducible, no atomics).
 #include <cstdio>
@@ -44,6 +45,7 @@ __device__ __forceinline__ void tile_mm(const double2* __restrict__ A, const dou
         for (int j = 0; j < TC; ++j) acc[i][j] = make_double2(0.0, 0.0);
     const double2* a = A + r0;
     const double2* b = B + (size_t)ld * c0;
+#pragma unroll 9
     for (int k = 0; k < N; ++k) {
         double2 av[QCK_TILE], bv[TC];
 #pragma unroll
@@ -72,8 +74,8 @@ __device__ __forceinline__ double2 ell_row(const double2* __restrict__ val, cons
                                            const double2* __restrict__ X, int ld, int r, int c) {
     double2 acc = make_double2(0.0, 0.0);
     for (int w = 0; w < W; ++w) {
-        double2 v = __ldg(val + r * W + w);
-        int k = __ldg(col + r * W + w);
+        double2 v = val[r * W + w];
+        int k = col[r * W + w];
         cfma(acc, v, X[k + ld * c]);
     }
     return acc;
@@ -119,17 +121,93 @@ __device__ __forceinline__ void do_aux(const QckLaunch& p, long long t, int tid,
     }
 }
 
-// gather from scratch through the (position, slot, sign) map and store position-ordered
-__device__ __forceinline__ void write_map(const double* __restrict__ sm, const uint32_t* __restrict__ pos,
-                                          const uint16_t* __restrict__ src, int cnt, double* __restrict__ out,
-                                          long long limit, double* __restrict__ partial, int tid, int nthreads) {
-    for (int k = tid; k < cnt; k += nthreads) {
-        unsigned s = __ldg(src + k);
-        unsigned q = __ldg(pos + k);
-        double v = sm[s & 0x7fffu];
-        if (s & 0x8000u) v = -v;
-        if ((long long)q < limit) out[q] = v;
-        else partial[q - limit] = v;
+// same entries, operands already staged in shared memory by the prefetch (fused path: no global load latency)
+__device__ __forceinline__ void do_aux_staged(const QckLaunch& p, const QckAux* auxs, const double* auxv, double dt,
+                                              long long t, int tid, int nthreads) {
+    const QckClassDev& c = p.c;
+    for (int k = tid; k < p.n_aux; k += nthreads) {
+        const QckAux a = auxs[k];
+        if (!((p.mask >> a.out) & 1u)) continue;
+        double v;
+        switch (a.op) {
+            case QAUX_CONST: v = a.c; break;
+            case QAUX_NEG_DT: v = -dt; break;
+            case QAUX_NEG_Z: v = -auxv[3 * k]; break;
+            case QAUX_NEG_MU: v = -auxv[3 * k + 2]; break;
+            default: v = auxv[3 * k + 1] - auxv[3 * k] - dt * auxv[3 * k + 2]; break;
+        }
+        if (a.out == 0) p.F[t * c.dyn + a.pos] = v;
+        else if (a.out == 1) p.J[t * p.nnzJ + a.pos] = v;
+        else if (a.pos < p.nnzH) p.H[t * p.nnzH + a.pos] = v;
+        else p.partial[t * p.npart + (a.pos - p.nnzH)] = v;
+    }
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ double slot_val(const double* __restrict__ sm, unsigned s) {
+    double v = sm[s & 0x7fffu];
+    return (s & 0x8000u) ? -v : v;
+}
+
+// Output segments: out[dst + k] = +-scratch[tab[src_off + k % period]].  Everything the loop touches except the
+// destination is in shared memory; consecutive threads store consecutive positions (coalesced).  Stores are 16-byte
+// (two values) whenever the destination is 16-byte aligned, 8-byte otherwise.
+// A periodic segment (kron(I_N, .) block) gathers each value once and stores it len/period times.
+__device__ __forceinline__ void write_segments(const double* __restrict__ sm, const uint16_t* __restrict__ tab,
+                                               const QckSeg* __restrict__ segs, int nseg, double* __restrict__ out,
+                                               long long limit, double* __restrict__ partial, int tid, int nthreads) {
+    for (int s = 0; s < nseg; ++s) {
+        const QckSeg sg = segs[s];
+        double* dst = (long long)sg.dst < limit ? out + sg.dst : partial + (sg.dst - limit);
+        const uint16_t* tb = tab + sg.src_off;
+        const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
+        if (sg.period == sg.len) {
+            // head (one value if misaligned), 16-byte body, tail
+            const int head = odd ? 1 : 0;
+            const int pairs = (sg.len - head) >> 1;
+            if (tid == 0 && head) dst[0] = slot_val(sm, tb[0]);
+            double2* d2 = reinterpret_cast<double2*>(dst + head);
+            const uint16_t* t2 = tb + head;
+            int k = tid;
+            for (; k + nthreads < pairs; k += 2 * nthreads) {
+                double a0 = slot_val(sm, t2[2 * k]), a1 = slot_val(sm, t2[2 * k + 1]);
+                double b0 = slot_val(sm, t2[2 * (k + nthreads)]), b1 = slot_val(sm, t2[2 * (k + nthreads) + 1]);
+                d2[k] = make_double2(a0, a1);
+                d2[k + nthreads] = make_double2(b0, b1);
+            }
+            for (; k < pairs; k += nthreads) d2[k] = make_double2(slot_val(sm, t2[2 * k]), slot_val(sm, t2[2 * k + 1]));
+            if (tid == nthreads - 1 && head + 2 * pairs < sg.len) dst[sg.len - 1] = slot_val(sm, tb[sg.len - 1]);
+        } else {
+            const int nrep = sg.len / sg.period;
+            if (!odd && !(sg.period & 1)) {
+                const int hp = sg.period >> 1;
+                for (int k = tid; k < hp; k += nthreads) {
+                    const double2 v = make_double2(slot_val(sm, tb[2 * k]), slot_val(sm, tb[2 * k + 1]));
+                    double2* d = reinterpret_cast<double2*>(dst) + k;
+                    for (int r = 0; r < nrep; ++r) d[(size_t)r * hp] = v;
+                }
+            } else {
+                for (int k = tid; k < sg.period; k += nthreads) {
+                    const double v = slot_val(sm, tb[k]);
+                    double* d = dst + k;
+                    for (int r = 0; r < nrep; ++r) d[(size_t)r * sg.period] = v;
+                }
+            }
+        }
     }
 }
 
@@ -144,29 +222,47 @@ __device__ __forceinline__ void write_map(const double* __restrict__ sm, const u
 //   (dF/dh)^H M = 1/2 A^H M + h/6 A^H (A^H M),                         (dB/dh)^H M: first term negated
 //   d2/da_i da_j = h^2/12 Re(<A_i^H M, A_j D> + <A_j^H M, A_i D>)
 //   d2/da_j dh   = Re <M, -1/2 A_j S + h/6 (A_j (A D) + A (A_j D))>,   d2/dh2 = 1/6 Re <M, A (A D)>
-// 6 + 2 n_d dense N^3 products per knot (vs ~45 in the reference's real-iso formulation).
+// 6 + 2 n_d dense N^3 products per knot (vs ~45 in the reference's real-iso formulation); products with the
+// constant drive matrices A_j are sparse (ELL rows) and the cheap ones are recomputed on the fly instead of stored.
+//
+// Shared memory per CTA: [scratch matrices | slot table | per-member segments x2 | per-member ELL x2 | input staging].
+// The inputs (and, when the member changes, the tables) of the NEXT work item are prefetched with cp.async while
+// the current item computes, so no global-load latency sits on the per-item critical path.
 // ------------------------------------------------------------------------------------------------------------
-template <int TC>
-__global__ void qck_pade4_kernel(const QckLaunch p) {
-    extern __shared__ double sm[];
+template <int TC, int CN>
+__global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade4_kernel(const QckLaunch p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
     const QckClassDev& c = p.c;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    const int N = c.N, NP = c.NP, nc = c.nc, ncp = c.ncp, nd = c.nd, W = c.W;
+    // CN > 0: levels known at compile time (index arithmetic folds, k-loops unroll); CN == 0: generic fallback
+    const int N = CN > 0 ? CN : c.N;
+    const int NP = CN > 0 ? ((CN + QCK_TILE - 1) / QCK_TILE) * QCK_TILE : c.NP;
+    const int nc = TC == 1 ? 1 : N, ncp = TC == 1 ? 1 : NP;
+    const int nd = c.nd, W = c.W;
     const bool needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H, needF = p.mask & QCK_EVAL_F;
     const bool needT = needJ || needH;  // first-order drive terms
     const bool free_time = c.free_time;
+    const int dim = 2 * N * nc;
+    // auxiliary (derivative-integrator) entries live behind the class's shared-memory carve-up
+    QckAux* auxs = reinterpret_cast<QckAux*>(smem_raw + c.sm_bytes);
+    double* auxv = reinterpret_cast<double*>(smem_raw + c.sm_bytes + p.n_aux * (int)sizeof(QckAux));
 
     double2* SA = reinterpret_cast<double2*>(sm + c.off_A);
     double2* SS = reinterpret_cast<double2*>(sm + c.off_S);
     double* SX = sm + c.off_X;
+    uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + c.sm_tab);
+    double* stage = reinterpret_cast<double*>(smem_raw + c.sm_stage);  // [z_t state | z_t+1 state | mu | a | h]
+    const int nseg = c.nsegJ + c.nsegH;
+    const int elln = c.ell_stride;
     const int msa = NP * NP, mss = NP * ncp;  // complex elements per matrix
 #define MA(i) (SA + (i) * msa)
 #define MS(i) (SS + (i) * mss)
 #define MD(j, k) (SS + (QS_FIXED + QD_COUNT * (j) + (k)) * mss)
-
-    for (int i = tid; i < c.scratch_doubles; i += nthreads) sm[i] = 0.0;
-    if (tid == 0) SX[QX_ONE] = 1.0;
+#define SEGBUF(b) reinterpret_cast<QckSeg*>(smem_raw + c.sm_seg + (b) * c.seg_bytes)
+#define ELLV(b) reinterpret_cast<double2*>(smem_raw + c.sm_ell + (b) * c.ell_bytes)
+#define ELLC(b) reinterpret_cast<int*>(smem_raw + c.sm_ell + (b) * c.ell_bytes + elln * 16)
 
     const int nact = p.member_end - p.member_begin;
     const long long n_items = p.n_knots * nact;
@@ -174,39 +270,79 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
     const int tilesA = (NP / QCK_TILE) * (NP / QCK_TILE);
     const int tcols = ncp / TC;
 
+    // prefetch of one work item: inputs into `stage`, and the member's segment + ELL tables into buffer b if asked
+    auto prefetch = [&](long long item, int b, bool tables) {
+        const long long t = item / nact;
+        const int m = p.member_begin + (int)(item - t * nact);
+        const double* zt = p.Z + t * c.zdim;
+        const int soff = __ldg(c.state_off + m), coff = __ldg(c.ctrl_off + m), roff_n = __ldg(c.row_off + m);
+        for (int i = tid; i < dim; i += nthreads) {
+            cp_async8(stage + i, zt + soff + i);
+            cp_async8(stage + dim + i, zt + c.zdim + soff + i);
+            if (needH) cp_async8(stage + 2 * dim + i, p.mu + t * c.dyn + roff_n + i);
+        }
+        if (tid < nd) cp_async8(stage + 3 * dim + tid, zt + coff + tid);
+        if (tid == nd && free_time) cp_async8(stage + 3 * dim + nd, zt + c.dt_off);
+        if (p.n_aux && m == p.member_begin) {  // operands of the derivative-integrator entries this item also writes
+            for (int k = tid; k < p.n_aux; k += nthreads) {
+                const QckAux a = auxs[k];
+                if (a.op == QAUX_NEG_Z || a.op == QAUX_FROW) cp_async8(auxv + 3 * k, zt + a.i0);
+                if (a.op == QAUX_FROW) { cp_async8(auxv + 3 * k + 1, zt + c.zdim + a.i0); cp_async8(auxv + 3 * k + 2, zt + a.i1); }
+                if (a.op == QAUX_NEG_MU && needH) cp_async8(auxv + 3 * k + 2, p.mu + t * c.dyn + a.i0);
+            }
+        }
+        if (tables) {
+            const QckSeg* gs = c.segs + (size_t)m * nseg;
+            for (int i = tid; i < nseg; i += nthreads) cp_async16(SEGBUF(b) + i, gs + i);
+            const double2* gv = c.cmat + (size_t)m * c.cmat_stride + N * N * (1 + nd);
+            const int* gc = c.ell_col + (size_t)m * c.ell_stride;
+            for (int i = tid; i < elln; i += nthreads) { cp_async16(ELLV(b) + i, gv + i); cp_async4(ELLC(b) + i, gc + i); }
+        }
+        cp_async_commit();
+    };
+
+    for (int i = tid; i < c.scratch_doubles; i += nthreads) sm[i] = 0.0;
+    for (int i = tid; i < c.tab_len; i += nthreads) tab[i] = c.tab[i];
+    for (int i = tid; i < p.n_aux; i += nthreads) auxs[i] = p.aux[i];
+    __syncthreads();
+    int buf = 0, buf_member = -1;
+    if ((long long)blockIdx.x < n_items) {
+        buf_member = p.member_begin + (int)(blockIdx.x % nact);
+        prefetch(blockIdx.x, buf, true);
+    }
+
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const long long t = item / nact;
         const int mi = (int)(item - t * nact);
         const int m = p.member_begin + mi;
-        __syncthreads();  // previous item's write-out has finished reading scratch
-        const double* zt = p.Z + t * c.zdim;
-        const double* zt1 = zt + c.zdim;
-        const int soff = c.state_off[m], coff = c.ctrl_off[m], roff = c.row_off[m];
+        cp_async_wait_all();
+        __syncthreads();  // staged inputs visible; previous item's write-out has finished reading scratch
+        if (tid == 0) SX[QX_ONE] = 1.0;
+        const int roff = __ldg(c.row_off + m);
         const double2* cm = c.cmat + (size_t)m * c.cmat_stride;
         const double2* A0 = cm;
         const double2* Adr = cm + N * N;
-        const double2* ellv = Adr + nd * N * N;
-        const int* ellc = c.ell_col + (size_t)m * c.ell_stride;
-        const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
+        const double2* ellv = ELLV(buf);
+        const int* ellc = ELLC(buf);
+        const QckSeg* segs = SEGBUF(buf);
+        const double h = free_time ? stage[3 * dim + nd] : c.dt_fixed;
 
-        // ---- stage 0: load the knot pair, build A = -i H(a) and A^H ------------------------------------------
+        // ---- stage 0: unpack the staged knot pair, build A = -i H(a) and A^H ---------------------------------
         {
-            const int dim = 2 * N * nc;
-            const double* mut = needH ? p.mu + t * c.dyn + roff : nullptr;
             for (int idx = tid; idx < dim; idx += nthreads) {
                 int cc = idx / (2 * N), q = idx - cc * 2 * N;
                 int im = q >= N, r = q - im * N;
-                double u0 = zt[soff + idx], u1 = zt1[soff + idx];
+                double u0 = stage[idx], u1 = stage[dim + idx];
                 int o = 2 * (r + NP * cc) + im;
                 reinterpret_cast<double*>(MS(QS_D))[o] = u1 - u0;
                 reinterpret_cast<double*>(MS(QS_S))[o] = u1 + u0;
-                if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = mut[idx];
+                if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = stage[2 * dim + idx];
             }
             for (int e = tid; e < N * N; e += nthreads) {
                 int r = e % N, k = e / N;
                 double2 v = __ldg(A0 + e);
                 for (int j = 0; j < nd; ++j) {
-                    double aj = zt[coff + j];
+                    double aj = stage[3 * dim + j];
                     double2 d = __ldg(Adr + j * N * N + e);
                     v.x = fma(aj, d.x, v.x);
                     v.y = fma(aj, d.y, v.y);
@@ -216,8 +352,19 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
             }
         }
         __syncthreads();
+        // staging is free again: fetch the next item's inputs (and tables, if its member differs) behind the compute
+        int next_buf = buf, next_member = buf_member;
+        {
+            const long long nitem = item + gridDim.x;
+            if (nitem < n_items) {
+                const int nm = p.member_begin + (int)(nitem % nact);
+                const bool tables = nm != buf_member;
+                if (tables) { next_buf = buf ^ 1; next_member = nm; }  // several active members => two table buffers
+                prefetch(nitem, next_buf, tables);
+            }
+        }
 
-        // ---- stage 1: A2, A D, A S, A^H M (dense);  A_j S, A_j D, A_j^H M (sparse) ----------------------------
+        // ---- stage 1: A2, A D, A S, A^H M (dense);  Q1_j = A_j D, N1_j = A_j^H M (sparse) -----------------------
         {
             const int nA = needJ ? tilesA : 0;       // A2 only feeds F and B (Jacobian state blocks)
             const int nS = (needH ? 3 : 2) * tilesS;  // AD, AS, (AhM)
@@ -237,21 +384,20 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
             }
             if (needT) {
                 const int per = N * nc;
-                const int nsp = (needH ? 3 : 2) * nd * per;  // P_j = A_j S, Q1_j = A_j D, N1_j = A_j^H M
+                const int nsp = (needH ? 2 : 1) * nd * per;
                 for (int w = nthreads - 1 - tid; w < nsp; w += nthreads) {
                     int pj = w / per, e = w - pj * per;
-                    int kind = pj / nd, j = pj - kind * nd;
+                    int adj = pj / nd, j = pj - adj * nd;
                     int r = e % N, cc = e / N;
-                    int adj = kind == 2;
-                    const double2* X = kind == 0 ? MS(QS_S) : (kind == 1 ? MS(QS_D) : MS(QS_M));
+                    const double2* X = adj ? MS(QS_M) : MS(QS_D);
                     double2 v = ell_row(ellv + (j * 2 + adj) * N * W, ellc + (j * 2 + adj) * N * W, W, X, NP, r, cc);
-                    MD(j, kind == 0 ? QD_P : (kind == 1 ? QD_Q1 : QD_N1))[r + NP * cc] = v;
+                    MD(j, adj ? QD_N1 : QD_Q1)[r + NP * cc] = v;
                 }
             }
         }
         __syncthreads();
 
-        // ---- stage 2: A(AD), A^H(A^H M), A(A_j D), A^H(A_j^H M) (dense);  A_j(AD), A_j^H(A^H M) (sparse); F, B ----
+        // ---- stage 2: A(AD), A^H(A^H M), A(A_j D), A^H(A_j^H M) (dense) --------------------------------------------
         {
             const int nP = 1 + (needT ? nd : 0) + (needH ? 1 + nd : 0);
             for (int w = tid; w < nP * tilesS; w += nthreads) {
@@ -272,28 +418,6 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
                 }
                 tile_mm<TC>(Aop, Bop, Cop, N, NP, tr * QCK_TILE, tcc * TC);
             }
-            if (needT) {
-                const int per = N * nc;
-                const int nsp = (needH ? 2 : 1) * nd * per;  // Q2_j = A_j (A D), N2_j = A_j^H (A^H M)
-                for (int w = nthreads - 1 - tid; w < nsp; w += nthreads) {
-                    int pj = w / per, e = w - pj * per;
-                    int kind = pj / nd, j = pj - kind * nd;
-                    int r = e % N, cc = e / N;
-                    const double2* X = kind == 0 ? MS(QS_AD) : MS(QS_AHM);
-                    double2 v = ell_row(ellv + (j * 2 + kind) * N * W, ellc + (j * 2 + kind) * N * W, W, X, NP, r, cc);
-                    MD(j, kind == 0 ? QD_Q2 : QD_N2)[r + NP * cc] = v;
-                }
-            }
-            if (needJ) {
-                const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0);
-                for (int e = tid; e < N * N; e += nthreads) {
-                    int r = e % N, k = e / N;
-                    double2 a = MA(QA_A)[r + NP * k], a2 = MA(QA_A2)[r + NP * k];
-                    double id = r == k ? 1.0 : 0.0;
-                    MA(QA_F)[r + NP * k] = make_double2(id + c1h * a.x + c2h2 * a2.x, c1h * a.y + c2h2 * a2.y);
-                    MA(QA_B)[r + NP * k] = make_double2(id - c1h * a.x + c2h2 * a2.x, -c1h * a.y + c2h2 * a2.y);
-                }
-            }
         }
         __syncthreads();
 
@@ -313,14 +437,23 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
                                 re_dot(MD(j, QD_N1), MD(i, QD_Q1), N, nc, NP, lane));
                     slot = qx_haa(nd, i, j);
                 } else if (task < npair + nd) {
+                    // Re <M, -1/2 A_j S + h/6 (A_j (A D) + A (A_j D))>, the two sparse products recomputed on the fly
                     int j = task - npair;
-                    s = -0.5 * re_dot(MS(QS_M), MD(j, QD_P), N, nc, NP, lane) +
-                        c2h * (re_dot(MS(QS_M), MD(j, QD_Q2), N, nc, NP, lane) +
-                               re_dot(MS(QS_M), MD(j, QD_AQ1), N, nc, NP, lane));
+                    s = 0.0;
+                    for (int e = lane; e < N * nc; e += 32) {
+                        int r = e % N, cc = e / N;
+                        double2 mm = MS(QS_M)[r + NP * cc];
+                        double2 pj = ell_row(ellv + (j * 2) * N * W, ellc + (j * 2) * N * W, W, MS(QS_S), NP, r, cc);
+                        double2 q2 = ell_row(ellv + (j * 2) * N * W, ellc + (j * 2) * N * W, W, MS(QS_AD), NP, r, cc);
+                        double2 aq = MD(j, QD_AQ1)[r + NP * cc];
+                        double vr = -0.5 * pj.x + c2h * (q2.x + aq.x), vi = -0.5 * pj.y + c2h * (q2.y + aq.y);
+                        s = fma(mm.x, vr, s);
+                        s = fma(mm.y, vi, s);
+                    }
                     slot = QX_HAH + j;
                 } else {
                     s = (1.0 / 6.0) * re_dot(MS(QS_M), MS(QS_AAD), N, nc, NP, lane);
-                    slot = QX_HHH;
+                    slot = qx_hhh(nd);
                 }
                 s = warp_sum(s);
                 if (lane == 0) SX[slot] = s;
@@ -328,7 +461,43 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
             __syncthreads();
         }
 
-        // ---- stage 3b: assemble the outputs in place ------------------------------------------------------------
+        // ---- stage 3b-1: per-drive outputs (read S, AD, AhM; overwrite only their own element) and F, B ----------
+        {
+            const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0);
+            const int per = N * nc;
+            if (needT) {
+                for (int w = tid; w < nd * per; w += nthreads) {
+                    int j = w / per, e = w - j * per;
+                    int r = e % N, cc = e / N;
+                    int o = r + NP * cc;
+                    const double2* ev = ellv + (j * 2) * N * W;
+                    const int* ec = ellc + (j * 2) * N * W;
+                    double2 pj = ell_row(ev, ec, W, MS(QS_S), NP, r, cc);
+                    double2 q2 = ell_row(ev, ec, W, MS(QS_AD), NP, r, cc);
+                    double2 aq1 = MD(j, QD_AQ1)[o];
+                    MD(j, QD_TA)[o] = make_double2(-c1h * pj.x + c2h2 * (q2.x + aq1.x), -c1h * pj.y + c2h2 * (q2.y + aq1.y));
+                    if (needH) {
+                        double2 n1 = MD(j, QD_N1)[o], ahn1 = MD(j, QD_AHN1)[o];
+                        double2 n2 = ell_row(ev + N * W, ec + N * W, W, MS(QS_AHM), NP, r, cc);
+                        double xr = n2.x + ahn1.x, xi = n2.y + ahn1.y;
+                        MD(j, QD_KA0)[o] = make_double2(-(c1h * n1.x + c2h2 * xr), -(c1h * n1.y + c2h2 * xi));
+                        MD(j, QD_KA1)[o] = make_double2(-c1h * n1.x + c2h2 * xr, -c1h * n1.y + c2h2 * xi);
+                    }
+                }
+            }
+            if (needJ) {
+                for (int e = nthreads - 1 - tid; e < N * N; e += nthreads) {
+                    int r = e % N, k = e / N;
+                    double2 a = MA(QA_A)[r + NP * k], a2 = MA(QA_A2)[r + NP * k];
+                    double id = r == k ? 1.0 : 0.0;
+                    MA(QA_F)[r + NP * k] = make_double2(id + c1h * a.x + c2h2 * a2.x, c1h * a.y + c2h2 * a2.y);
+                    MA(QA_B)[r + NP * k] = make_double2(id - c1h * a.x + c2h2 * a2.x, -c1h * a.y + c2h2 * a2.y);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- stage 3b-2: fixed outputs in place: R, dR/dh, and the dt Hessian blocks -----------------------------------
         {
             const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
             const int per = N * nc;
@@ -344,27 +513,11 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
                     MS(QS_AHAHM)[o] = make_double2(-0.5 * ahm.x + c2h * ahahm.x, -0.5 * ahm.y + c2h * ahahm.y);
                 }
             }
-            if (needT) {
-                for (int w = tid; w < nd * per; w += nthreads) {
-                    int j = w / per, e = w - j * per;
-                    int r = e % N, cc = e / N;
-                    int o = r + NP * cc;
-                    double2 pj = MD(j, QD_P)[o], q2 = MD(j, QD_Q2)[o], aq1 = MD(j, QD_AQ1)[o];
-                    MD(j, QD_P)[o] = make_double2(-c1h * pj.x + c2h2 * (q2.x + aq1.x), -c1h * pj.y + c2h2 * (q2.y + aq1.y));
-                    if (needH) {
-                        double2 n1 = MD(j, QD_N1)[o], n2 = MD(j, QD_N2)[o], ahn1 = MD(j, QD_AHN1)[o];
-                        double xr = n2.x + ahn1.x, xi = n2.y + ahn1.y;
-                        MD(j, QD_N2)[o] = make_double2(-(c1h * n1.x + c2h2 * xr), -(c1h * n1.y + c2h2 * xi));
-                        MD(j, QD_AHN1)[o] = make_double2(-c1h * n1.x + c2h2 * xr, -c1h * n1.y + c2h2 * xi);
-                    }
-                }
-            }
         }
         __syncthreads();
 
         // ---- stage 4: write-out ------------------------------------------------------------------------------------
         if (needF) {
-            const int dim = 2 * N * nc;
             double* Fo = p.F + t * c.dyn + roff;
             const double* R = reinterpret_cast<const double*>(MS(QS_D));
             for (int idx = tid; idx < dim; idx += nthreads) {
@@ -373,17 +526,20 @@ __global__ void qck_pade4_kernel(const QckLaunch p) {
                 Fo[idx] = R[2 * (r + NP * cc) + im];
             }
         }
-        if (needJ)
-            write_map(sm, c.posJ + (size_t)m * c.cntJ, c.srcJ + (size_t)m * c.cntJ, c.cntJ, p.J + t * p.nnzJ, p.nnzJ,
-                      nullptr, tid, nthreads);
+        if (needJ) write_segments(sm, tab, segs, c.nsegJ, p.J + t * p.nnzJ, (long long)1 << 60, nullptr, tid, nthreads);
         if (needH)
-            write_map(sm, c.posH + (size_t)m * c.cntH, c.srcH + (size_t)m * c.cntH, c.cntH, p.H + t * p.nnzH, p.nnzH,
-                      p.partial + t * p.npart, tid, nthreads);
-        if (mi == 0 && p.n_aux) do_aux(p, t, tid, nthreads);
+            write_segments(sm, tab, segs + c.nsegJ, c.nsegH, p.H + t * p.nnzH, p.nnzH, p.partial + t * p.npart, tid, nthreads);
+        if (mi == 0 && p.n_aux) do_aux_staged(p, auxs, auxv, h, t, tid, nthreads);
+        buf = next_buf;
+        buf_member = next_member;
     }
+    cp_async_wait_all();
 #undef MA
 #undef MS
 #undef MD
+#undef SEGBUF
+#undef ELLV
+#undef ELLC
 }
 
 __global__ void qck_aux_kernel(const QckLaunch p) {
@@ -405,16 +561,27 @@ __global__ void qck_reduce_kernel(const QckReduce r, double* __restrict__ H, con
 }  // namespace
 
 // shared by the host map builder: where each output lives inside the CTA scratch
-void qck_scratch_layout(QckClassDev& c, int eval_hessian) {
-    (void)eval_hessian;
+void qck_scratch_layout(QckClassDev& c) {
     c.msa = 2 * c.NP * c.NP;
     c.mss = 2 * c.NP * c.ncp;
     c.off_A = 0;
     int n_s = QS_FIXED + QD_COUNT * c.nd;
     c.off_S = c.off_A + QA_COUNT * c.msa;
     c.off_X = c.off_S + n_s * c.mss;
-    c.scratch_doubles = c.off_X + QX_HAH + c.nd + c.nd * c.nd;
+    c.scratch_doubles = c.off_X + qx_haa(c.nd, 0, 0) + c.nd * c.nd;
     c.scratch_doubles = (c.scratch_doubles + 1) & ~1;
+}
+
+void qck_smem_finalize(QckClassDev& c) {
+    auto al = [](int b) { return (b + 15) & ~15; };
+    const int dim = 2 * c.N * c.nc;
+    c.sm_tab = al(c.scratch_doubles * 8);
+    c.sm_seg = al(c.sm_tab + c.tab_len * 2);
+    c.seg_bytes = al((c.nsegJ + c.nsegH) * (int)sizeof(QckSeg));
+    c.sm_ell = c.sm_seg + 2 * c.seg_bytes;
+    c.ell_bytes = al(c.ell_stride * 16 + c.ell_stride * 4);
+    c.sm_stage = c.sm_ell + 2 * c.ell_bytes;
+    c.sm_bytes = al(c.sm_stage + (3 * dim + c.nd + 1) * 8);
 }
 
 static int pick_threads(const QckClassDev& c, int tc) {
@@ -423,20 +590,39 @@ static int pick_threads(const QckClassDev& c, int tc) {
     int th = ((items + 31) / 32) * 32;
     if (th < 64) th = 64;
     if (th > 256) th = 256;
+    if (c.N >= 8 && th < 128) th = 128;  // the write-out and assembly phases want the extra warp
     return th;
 }
 
-int qck_launch_quantum(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches) {
+typedef void (*qck_kernel_t)(const QckLaunch);
+template <int TC>
+static qck_kernel_t pade4_for(int N) {
+    switch (N) {
+        case 2: return qck_pade4_kernel<TC, 2>;
+        case 3: return qck_pade4_kernel<TC, 3>;
+        case 4: return qck_pade4_kernel<TC, 4>;
+        case 5: return qck_pade4_kernel<TC, 5>;
+        case 6: return qck_pade4_kernel<TC, 6>;
+        case 8: return qck_pade4_kernel<TC, 8>;
+        case 9: return qck_pade4_kernel<TC, 9>;
+        default: return qck_pade4_kernel<TC, 0>;
+    }
+}
+
+#define QCK_MAX_FUSED_AUX 256
+
+int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, int* launches) {
+    QckLaunch L = L0;
     const QckClassDev& c = L.c;
-    size_t smem = (size_t)c.scratch_doubles * sizeof(double);
     long long n_items = L.n_knots * (long long)(L.member_end - L.member_begin);
     if (n_items <= 0) return 0;
     const bool unitary = c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP;
-    void (*kern)(const QckLaunch) = nullptr;
+    qck_kernel_t kern = nullptr;
     int tc = unitary ? QCK_TILE : 1;
-    if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = qck_pade4_kernel<QCK_TILE>;
-    else if (c.kind == QCK_KET_PADE && c.order == 4) kern = qck_pade4_kernel<1>;
+    if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = pade4_for<QCK_TILE>(c.N);
+    else if (c.kind == QCK_KET_PADE && c.order == 4) kern = pade4_for<1>(c.N);
     else return (int)cudaErrorNotSupported;
+    size_t smem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double));
     int threads = pick_threads(c, tc);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -450,6 +636,8 @@ int qck_launch_quantum(const QckLaunch& L, int sm_count, cudaStream_t stream, in
     if (launches) ++*launches;
     return (int)cudaGetLastError();
 }
+
+int qck_fused_aux_limit(void) { return QCK_MAX_FUSED_AUX; }
 
 int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches) {
     if (L.n_aux == 0 || L.n_knots <= 0) return 0;
