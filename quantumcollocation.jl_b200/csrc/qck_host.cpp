@@ -97,66 +97,135 @@ int fail(qck_handle* h, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, QCK_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-struct HEntry {
-    long long key;  // col * (2*zdim) + row  (CSC order)
-    int contrib;    // integrator index
-    int cls, member;  // quantum class/member or -1
-    uint16_t src;     // scratch slot (+sign) for quantum contributors
-    int aux_op, aux_i0;  // for derivative contributors
-    int grp, period;     // output group of the integrator (segments never span groups) and its repeat period (0 = none)
-};
-struct JEntry {
-    long long key;
-    int cls, member;
-    uint16_t src;
+// One structural nonzero of the per-knot Jacobian / Hessian block.
+struct Ent {
+    long long key;     // col * nrows + row  (CSC order)
+    int contrib;       // integrator index
+    int cls, member;   // quantum class / member, or cls = -1 for a derivative integrator (member = integrator index)
+    int qid, idx;      // output quantity and element index inside it (quantum)
+    int period;        // repeat period of the quantity (kron(I_N, .) blocks), 0 = none
     int aux_op, aux_i0;
     double aux_c;
-    int grp, period;
 };
-struct MapEntry {
+struct MapEnt {
     long long dst;
-    uint16_t src;
-    int grp, period;
-    bool operator<(const MapEntry& o) const { return dst < o.dst; }
+    int qid, idx, period;
+    bool operator<(const MapEnt& o) const { return dst < o.dst; }
 };
 
-// Cut one member's (destination-sorted) entries into segments and append the slot table.  Members of one class
-// must produce identical tables and segment shapes (only `dst` differs); returns false otherwise.
-bool make_segments(const std::vector<MapEntry>& e, long long split, std::vector<QckSeg>& segs, std::vector<uint16_t>& tab) {
+// Image placement of one member's output quantities of one value array + its segments.
+// Groups (one per quantity) must be affine in the element index: dst(i) = d0 + i * stride.  Stride-1 groups get
+// their own contiguous image range, allocated in destination order so that destination-adjacent groups are also
+// image-adjacent (they merge into one segment); groups with a common stride > 1 that interleave share one range.
+struct Run { int dst, len, img, period; };
+bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* base, short* stride, std::vector<Run>& segs,
+                 std::string& why) {
+    if (e.empty()) return true;
+    struct Group { int qid; long long d0; int s, n, period; };
+    std::map<int, std::vector<MapEnt>> by_q;
+    for (auto& x : e) by_q[x.qid].push_back(x);
+    std::vector<Group> groups;
+    for (auto& kv : by_q) {
+        auto& v = kv.second;
+        std::sort(v.begin(), v.end(), [](const MapEnt& a, const MapEnt& b) { return a.idx < b.idx; });
+        Group g{kv.first, v[0].dst, 1, (int)v.size(), v[0].period};
+        if (v.size() > 1) g.s = (int)(v[1].dst - v[0].dst);
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].idx != (int)i || v[i].dst != g.d0 + (long long)i * g.s || g.s < 1) { why = "an output quantity is not laid out affinely in the structure"; return false; }
+        if (g.period > 0 && (g.s != 1 || g.n % g.period)) { why = "a repeated block is not contiguous in the structure"; return false; }
+        groups.push_back(g);
+    }
+    std::sort(groups.begin(), groups.end(), [](const Group& a, const Group& b) { return a.d0 < b.d0; });
+    struct Family { long long d0; int s; int base; };
+    std::vector<Family> fams;
+    long long run_end = -2;      // destination just past the previous stride-1, non-periodic group
+    for (auto& g : groups) {
+        int b;
+        if (g.s == 1) {
+            const bool periodic = g.period > 0 && g.period < g.n;
+            const bool glue = !periodic && run_end == g.d0 && ((g.d0 < split) == (g.d0 - 1 < split));
+            b = glue ? cursor : ((cursor + 1) & ~1);
+            cursor = b + (periodic ? g.period : g.n);
+            run_end = periodic ? -2 : g.d0 + g.n;
+        } else {
+            b = -1;
+            for (auto& f : fams)
+                if (f.s == g.s && g.d0 >= f.d0 && g.d0 < f.d0 + f.s) b = f.base + (int)(g.d0 - f.d0);
+            if (b < 0) {
+                b = (cursor + 1) & ~1;
+                fams.push_back({g.d0, g.s, b});
+                cursor = b + g.n * g.s;
+            }
+            run_end = -2;
+        }
+        if (cursor > 32000) { why = "output image too large"; return false; }
+        base[g.qid] = (short)b;
+        stride[g.qid] = (short)g.s;
+    }
+    // segments: maximal runs contiguous in both destination and image
+    std::sort(e.begin(), e.end());
+    auto img_of = [&](const MapEnt& x) { return base[x.qid] + (x.period > 0 ? x.idx % x.period : x.idx) * stride[x.qid]; };
     size_t k = 0;
     while (k < e.size()) {
+        const bool periodic = e[k].period > 0;
         size_t k2 = k + 1;
-        while (k2 < e.size() && e[k2].dst == e[k2 - 1].dst + 1 && e[k2].grp == e[k].grp && ((e[k2].dst < split) == (e[k].dst < split))) ++k2;
-        int len = (int)(k2 - k), period = len;
-        int p = e[k].period;
-        if (p > 0 && len % p == 0 && len / p >= 2) {
-            bool ok = true;
-            for (size_t u = k + p; u < k2 && ok; ++u) ok = e[u].src == e[u - p].src;
-            if (ok) period = p;
+        if (periodic) {
+            while (k2 < e.size() && e[k2].qid == e[k].qid && e[k2].dst == e[k2 - 1].dst + 1) ++k2;
+            segs.push_back(Run{(int)e[k].dst, (int)(k2 - k), img_of(e[k]), e[k].period});
+        } else {
+            while (k2 < e.size() && e[k2].period == 0 && e[k2].dst == e[k2 - 1].dst + 1 && img_of(e[k2]) == img_of(e[k2 - 1]) + 1 &&
+                   ((e[k2].dst < split) == (e[k].dst < split)))
+                ++k2;
+            segs.push_back(Run{(int)e[k].dst, (int)(k2 - k), img_of(e[k]), (int)(k2 - k)});
         }
-        QckSeg sg{(int)e[k].dst, len, (int)tab.size(), period};
-        for (int u = 0; u < period; ++u) tab.push_back(e[k + u].src);
-        segs.push_back(sg);
+        if (segs.back().img & 1) { why = "internal: odd segment image offset"; return false; }
         k = k2;
     }
     return true;
 }
 
-// slot of iso-vec element i of state-type matrix `sidx`
-inline int slot_state(const QckClassDev& c, int sidx, int i) {
-    int cc = i / (2 * c.N), q = i - cc * 2 * c.N;
-    int im = q >= c.N, r = q - im * c.N;
-    return c.off_S + sidx * c.mss + 2 * (r + c.NP * cc) + im;
-}
-// slot and sign of iso(X)[q, r] for A-type matrix `aidx`:  iso(X) = [Re X, -Im X; Im X, Re X]
-inline uint16_t slot_iso(const QckClassDev& c, int aidx, int q, int r, bool negate) {
-    int N = c.N;
-    int qi = q >= N, ri = r >= N;
-    int qq = q - qi * N, rr = r - ri * N;
-    int im = qi != ri;                 // off-diagonal quadrants hold Im
-    bool neg = (!qi && ri) != negate;  // upper-right quadrant is -Im
-    int s = c.off_A + aidx * c.msa + 2 * (qq + c.NP * rr) + im;
-    return (uint16_t)(s | (neg ? 0x8000 : 0));
+// Cut runs into write-out units and balance them over the CTA's warps (longest-processing-time first).
+std::vector<QckSeg> balance_units(const std::vector<Run> (&runs)[3], int nwarps, int* hdr /* QCK_SEG_HDR */) {
+    struct Unit { QckSeg s; long long cost; };
+    std::vector<Unit> units;
+    long long total = 0;
+    for (int arr = 0; arr < 3; ++arr) for (auto& r : runs[arr]) total += r.len;
+    const long long target = std::max<long long>(64, total / (2 * nwarps));
+    for (int arr = 0; arr < 3; ++arr)
+        for (auto& r : runs[arr]) {
+            if (r.period < r.len) {  // repeated block: split by whole repetitions
+                const int nrep = r.len / r.period;
+                int per = (int)std::max<long long>(1, target / r.period);
+                for (int r0 = 0; r0 < nrep; r0 += per) {
+                    const int k = std::min(per, nrep - r0);
+                    units.push_back({{r.dst + r0 * r.period, r.period, r.img | (k << 16), arr}, (long long)k * r.period});
+                }
+            } else {  // plain run: split into even-length pieces (keeps the 16-byte alignment parity of every piece)
+                int piece = (int)((target + 1) & ~1LL);
+                for (int o = 0; o < r.len; o += piece) {
+                    const int k = std::min(piece, r.len - o);
+                    units.push_back({{r.dst + o, k, (r.img + o) | (1 << 16), arr}, (long long)k});
+                }
+            }
+        }
+    std::vector<size_t> order(units.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return units[a].cost > units[b].cost; });
+    std::vector<long long> load(nwarps, 0);
+    std::vector<std::vector<size_t>> mine(nwarps);
+    for (size_t i : order) {
+        int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[w] += units[i].cost + 24;  // per-unit set-up cost
+        mine[w].push_back(i);
+    }
+    std::vector<QckSeg> out;
+    for (int w = 0; w < nwarps; ++w) {
+        hdr[w] = (int)out.size();
+        std::sort(mine[w].begin(), mine[w].end());
+        for (size_t i : mine[w]) out.push_back(units[i].s);
+    }
+    for (int w = nwarps; w < QCK_SEG_HDR; ++w) hdr[w] = (int)out.size();
+    return out;
 }
 
 int build(qck_handle* h) {
@@ -183,9 +252,6 @@ int build(qck_handle* h) {
             c.ncp = I.unitary() ? c.NP : 1;
             c.free_time = free_time; c.dt_off = h->dt_off; c.zdim = zdim; c.dyn = h->dyn; c.dt_fixed = h->dt_fixed;
             qck_scratch_layout(c);
-            if (c.scratch_doubles > 32768 || (size_t)c.scratch_doubles * 8 > 227 * 1024)
-                return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d scratch doubles per knot; this build supports at most %d",
-                            I.N, I.nd, c.scratch_doubles, 227 * 1024 / 8);
         } else ci = it->second;
         cls_idx[q] = ci;
         mem_idx[q] = (int)h->classes[ci].members.size();
@@ -204,8 +270,7 @@ int build(qck_handle* h) {
     }
 
     // ---- entries -----------------------------------------------------------------------------------------------
-    std::vector<JEntry> JE;
-    std::vector<HEntry> HE;
+    std::vector<Ent> JE, HE;
     auto jkey = [&](int row, int col) { return (long long)col * h->dyn + row; };
     auto hkey = [&](int r, int c) { if (r > c) std::swap(r, c); return (long long)c * (2 * zdim) + r; };
     for (int q = 0; q < nI; ++q) {
@@ -213,62 +278,52 @@ int build(qck_handle* h) {
         const int R0 = I.row_off;
         if (I.quantum()) {
             const int ci = cls_idx[q], mi = mem_idx[q];
-            const QckClassDev& c = h->classes[ci].dev;
-            const int N = I.N, n2 = 2 * N;
+            const int N = I.N, n2 = 2 * N, blk = n2 * n2, nd = I.nd;
+            auto J = [&](int row, int col, int qid, int idx, int period) { JE.push_back({jkey(row, col), q, ci, mi, qid, idx, period, 0, 0, 0.0}); };
+            auto Hh = [&](int r, int c2, int qid, int idx) { HE.push_back({hkey(r, c2), q, ci, mi, qid, idx, 0, 0, 0, 0.0}); };
             // Jacobian: state_t block (-F or -E), state_t+1 block (+B or identity), controls, timestep
-            const int blk = n2 * n2;  // one kron(I_N, .) block repeats every 2N columns of 2N rows
-            const int DRV = QS_FIXED;
             for (int cb = 0; cb < I.nc; ++cb)
                 for (int r = 0; r < n2; ++r)
                     for (int qq = 0; qq < n2; ++qq) {
-                        JE.push_back({jkey(R0 + cb * n2 + qq, I.state_off + cb * n2 + r), ci, mi, slot_iso(c, QA_F, qq, r, true), 0, 0, 0, 0, blk});
-                        if (I.pade())
-                            JE.push_back({jkey(R0 + cb * n2 + qq, zdim + I.state_off + cb * n2 + r), ci, mi, slot_iso(c, QA_B, qq, r, false), 0, 0, 0, 1, blk});
+                        J(R0 + cb * n2 + qq, I.state_off + cb * n2 + r, QO_ISOF, cb * blk + r * n2 + qq, blk);
+                        if (I.pade()) J(R0 + cb * n2 + qq, zdim + I.state_off + cb * n2 + r, QO_ISOB, cb * blk + r * n2 + qq, blk);
                     }
             if (!I.pade())
-                for (int i = 0; i < I.dim; ++i)
-                    JE.push_back({jkey(R0 + i, zdim + I.state_off + i), ci, mi, (uint16_t)(c.off_X + QX_ONE), 0, 0, 0, 1, 1});
-            for (int j = 0; j < I.nd; ++j)
-                for (int i = 0; i < I.dim; ++i)
-                    JE.push_back({jkey(R0 + i, I.ctrl_off + j), ci, mi, (uint16_t)slot_state(c, DRV + QD_COUNT * j + QD_TA, i), 0, 0, 0, 2 + j, 0});
+                for (int i = 0; i < I.dim; ++i) J(R0 + i, zdim + I.state_off + i, QO_ONE, i, 1);
+            for (int j = 0; j < nd; ++j)
+                for (int i = 0; i < I.dim; ++i) J(R0 + i, I.ctrl_off + j, QO_TA + j, i, 0);
             if (free_time)
-                for (int i = 0; i < I.dim; ++i)
-                    JE.push_back({jkey(R0 + i, h->dt_off), ci, mi, (uint16_t)slot_state(c, QS_AS, i), 0, 0, 0, 2 + I.nd, 0});
+                for (int i = 0; i < I.dim; ++i) J(R0 + i, h->dt_off, QO_TH, i, 0);
             if (h->eval_hessian) {
-                const int nd = I.nd;
                 for (int j = 0; j < nd; ++j)
                     for (int i = 0; i < I.dim; ++i) {
-                        HE.push_back({hkey(I.state_off + i, I.ctrl_off + j), q, ci, mi, (uint16_t)slot_state(c, DRV + QD_COUNT * j + QD_KA0, i), 0, 0, j, 0});
-                        if (I.pade())
-                            HE.push_back({hkey(I.ctrl_off + j, zdim + I.state_off + i), q, ci, mi, (uint16_t)slot_state(c, DRV + QD_COUNT * j + QD_KA1, i), 0, 0, 2 * nd + 4, 0});
+                        Hh(I.state_off + i, I.ctrl_off + j, QO_KA0 + j, i);
+                        if (I.pade()) Hh(I.ctrl_off + j, zdim + I.state_off + i, QO_KA1 + j, i);
                     }
                 for (int i = 0; i < nd; ++i)
-                    for (int j = i; j < nd; ++j)
-                        HE.push_back({hkey(I.ctrl_off + i, I.ctrl_off + j), q, ci, mi, (uint16_t)(c.off_X + qx_haa(nd, i, j)), 0, 0, nd + j, 0});
+                    for (int j = i; j < nd; ++j) Hh(I.ctrl_off + i, I.ctrl_off + j, qo_haa(i, j), 0);
                 if (free_time) {
                     for (int i = 0; i < I.dim; ++i) {
-                        HE.push_back({hkey(I.state_off + i, h->dt_off), q, ci, mi, (uint16_t)slot_state(c, QS_AHM, i), 0, 0, 2 * nd + 1, 0});
-                        if (I.pade())
-                            HE.push_back({hkey(h->dt_off, zdim + I.state_off + i), q, ci, mi, (uint16_t)slot_state(c, QS_AHAHM, i), 0, 0, 2 * nd + 4, 0});
+                        Hh(I.state_off + i, h->dt_off, QO_KH0, i);
+                        if (I.pade()) Hh(h->dt_off, zdim + I.state_off + i, QO_KH1, i);
                     }
-                    for (int j = 0; j < nd; ++j)
-                        HE.push_back({hkey(I.ctrl_off + j, h->dt_off), q, ci, mi, (uint16_t)(c.off_X + QX_HAH + j), 0, 0, 2 * nd + 2, 0});
-                    HE.push_back({hkey(h->dt_off, h->dt_off), q, ci, mi, (uint16_t)(c.off_X + qx_hhh(nd)), 0, 0, 2 * nd + 2, 0});
+                    for (int j = 0; j < nd; ++j) Hh(I.ctrl_off + j, h->dt_off, QO_HAH + j, 0);
+                    Hh(h->dt_off, h->dt_off, QO_HHH, 0);
                 }
             }
         } else {
             for (int i = 0; i < I.dim; ++i) {
-                JE.push_back({jkey(R0 + i, I.state_off + i), -1, q, 0, QAUX_CONST, 0, -1.0, 0, 0});
-                JE.push_back({jkey(R0 + i, zdim + I.state_off + i), -1, q, 0, QAUX_CONST, 0, 1.0, 0, 0});
-                JE.push_back({jkey(R0 + i, I.ctrl_off + i), -1, q, 0, QAUX_NEG_DT, 0, 0.0, 0, 0});
-                if (free_time) JE.push_back({jkey(R0 + i, h->dt_off), -1, q, 0, QAUX_NEG_Z, I.ctrl_off + i, 0.0, 0, 0});
+                JE.push_back({jkey(R0 + i, I.state_off + i), q, -1, q, 0, 0, 0, QAUX_CONST, 0, -1.0});
+                JE.push_back({jkey(R0 + i, zdim + I.state_off + i), q, -1, q, 0, 0, 0, QAUX_CONST, 0, 1.0});
+                JE.push_back({jkey(R0 + i, I.ctrl_off + i), q, -1, q, 0, 0, 0, QAUX_NEG_DT, 0, 0.0});
+                if (free_time) JE.push_back({jkey(R0 + i, h->dt_off), q, -1, q, 0, 0, 0, QAUX_NEG_Z, I.ctrl_off + i, 0.0});
                 if (free_time && h->eval_hessian)
-                    HE.push_back({hkey(I.ctrl_off + i, h->dt_off), q, -1, -1, 0, QAUX_NEG_MU, R0 + i, 0, 0});
+                    HE.push_back({hkey(I.ctrl_off + i, h->dt_off), q, -1, q, 0, 0, 0, QAUX_NEG_MU, R0 + i, 0.0});
             }
         }
     }
-    // ---- Jacobian structure (CSC order) and maps ---------------------------------------------------------------------
-    std::sort(JE.begin(), JE.end(), [](const JEntry& a, const JEntry& b) { return a.key < b.key; });
+    // ---- Jacobian structure (CSC order) ---------------------------------------------------------------------------------------
+    std::sort(JE.begin(), JE.end(), [](const Ent& a, const Ent& b) { return a.key < b.key; });
     for (size_t k = 1; k < JE.size(); ++k)
         if (JE[k].key == JE[k - 1].key) return fail(h, QCK_EINVAL, "two integrators write the same Jacobian entry (overlapping rows?)");
     h->nnzJ = (long long)JE.size();
@@ -276,7 +331,7 @@ int build(qck_handle* h) {
     for (size_t k = 0; k < JE.size(); ++k) { h->Jc[k] = (int32_t)(JE[k].key / h->dyn); h->Jr[k] = (int32_t)(JE[k].key % h->dyn); }
 
     // ---- Hessian structure: unique keys, contributor lists ----------------------------------------------------------------
-    std::stable_sort(HE.begin(), HE.end(), [](const HEntry& a, const HEntry& b) { return a.key != b.key ? a.key < b.key : a.contrib < b.contrib; });
+    std::stable_sort(HE.begin(), HE.end(), [](const Ent& a, const Ent& b) { return a.key != b.key ? a.key < b.key : a.contrib < b.contrib; });
     std::vector<int> hpos(HE.size());
     {
         long long last = -1; int pos = -1;
@@ -311,47 +366,68 @@ int build(qck_handle* h) {
         for (auto& v : cols) { for (int cidx : v) h->sh_cols.push_back(cidx); h->sh_ptr.push_back((int)h->sh_cols.size()); }
     }
 
-    // ---- per-class maps ---------------------------------------------------------------------------------------------------------
+    // ---- per-class image placement, segments and constants ---------------------------------------------------------------------
     for (size_t ci = 0; ci < h->classes.size(); ++ci) {
         ClassHost& C = h->classes[ci];
         QckClassDev& c = C.dev;
         const int nm = c.n_members;
-        std::vector<std::vector<MapEntry>> mj(nm), mh(nm);
+        std::vector<std::vector<MapEnt>> mj(nm), mh(nm);
         for (size_t k = 0; k < JE.size(); ++k)
-            if (JE[k].cls == (int)ci) mj[JE[k].member].push_back({(long long)k, JE[k].src, JE[k].grp, JE[k].period});
+            if (JE[k].cls == (int)ci) mj[JE[k].member].push_back({(long long)k, JE[k].qid, JE[k].idx, JE[k].period});
         for (size_t k = 0; k < HE.size(); ++k)
-            if (HE[k].cls == (int)ci && hdst[k] >= 0) mh[HE[k].member].push_back({hdst[k], HE[k].src, HE[k].grp, HE[k].period});
-        std::vector<uint16_t> tab;
+            if (HE[k].cls == (int)ci && hdst[k] >= 0) mh[HE[k].member].push_back({hdst[k], HE[k].qid, HE[k].idx, 0});
         std::vector<QckSeg> segs;
-        c.nsegJ = c.nsegH = 0;
+        c.nseg = 0;
+        c.n_tbuf = C.member_end - C.member_begin > 1 ? 2 : 1;
+        c.threads = qck_pick_threads(c);
+        const int nwarps = c.threads / 32;
+        for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
         {
             std::vector<std::vector<QckSeg>> per_member(nm);
+            std::vector<std::vector<int>> hdrs(nm, std::vector<int>(QCK_SEG_HDR, 0));
             bool first = true;
             for (int m2 = C.member_begin; m2 < C.member_end; ++m2) {  // only active members are ever launched
-                std::vector<uint16_t> t2;
-                std::vector<QckSeg> sj, sh;
-                std::sort(mj[m2].begin(), mj[m2].end());
-                std::sort(mh[m2].begin(), mh[m2].end());
-                make_segments(mj[m2], (long long)1 << 60, sj, t2);
-                make_segments(mh[m2], h->nnzH, sh, t2);
-                if (first) { tab = t2; c.nsegJ = (int)sj.size(); c.nsegH = (int)sh.size(); first = false; }
-                if (t2 != tab || (int)sj.size() != c.nsegJ || (int)sh.size() != c.nsegH)
+                const Integ& I = h->integ[C.members[m2]];
+                short base[QO_COUNT], stride[QO_COUNT];
+                for (int q2 = 0; q2 < QO_COUNT; ++q2) { base[q2] = -1; stride[q2] = 0; }
+                std::vector<Run> runs[3];
+                std::vector<MapEnt> mf;
+                for (int i = 0; i < I.dim; ++i) mf.push_back({(long long)I.row_off + i, QO_R, i, 0});
+                int cursor = 0;
+                std::string why;
+                if (!place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why) ||
+                    !place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why) ||
+                    !place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why))
+                    return fail(h, QCK_EINVAL, "unsupported trajectory layout: %s", why.c_str());
+                per_member[m2] = balance_units(runs, nwarps, hdrs[m2].data());
+                if (first) {
+                    memcpy(c.pl_base, base, sizeof base); memcpy(c.pl_stride, stride, sizeof stride);
+                    c.img_doubles = cursor; c.nseg = (int)per_member[m2].size();
+                    first = false;
+                }
+                bool same = !memcmp(c.pl_base, base, sizeof base) && !memcmp(c.pl_stride, stride, sizeof stride) && c.img_doubles == cursor &&
+                            (int)per_member[m2].size() == c.nseg && hdrs[m2] == hdrs[C.member_begin];
+                if (same && m2 > C.member_begin)
+                    for (size_t u = 0; u < per_member[m2].size(); ++u) {
+                        const QckSeg &a = per_member[m2][u], &b = per_member[C.member_begin][u];
+                        same = same && a.n == b.n && a.img_nrep == b.img_nrep && a.arr == b.arr;
+                    }
+                if (!same)
                     return fail(h, QCK_EINVAL, "integrators of one kind must see the same relative component order (state/control/timestep layout differs between members)");
-                per_member[m2] = sj;
-                per_member[m2].insert(per_member[m2].end(), sh.begin(), sh.end());
             }
-            const int ns = c.nsegJ + c.nsegH;
-            segs.assign((size_t)nm * std::max(ns, 1), QckSeg{0, 0, 0, 1});
-            for (int m2 = C.member_begin; m2 < C.member_end; ++m2)
-                for (int u = 0; u < ns; ++u) segs[(size_t)m2 * ns + u] = per_member[m2][u];
+            const int rec = QCK_SEG_HDR / 4 + c.nseg;  // records of 16 bytes per member
+            segs.assign((size_t)nm * rec, QckSeg{0, 0, 0, 0});
+            for (int m2 = C.member_begin; m2 < C.member_end; ++m2) {
+                memcpy(&segs[(size_t)m2 * rec], hdrs[m2].data(), QCK_SEG_HDR * sizeof(int));
+                for (int u = 0; u < c.nseg; ++u) segs[(size_t)m2 * rec + QCK_SEG_HDR / 4 + u] = per_member[m2][u];
+            }
         }
-        c.tab_len = (int)tab.size();
-        // constants: A0 = -i H_drift, A_j = -i H_j dense, and ELL forms of A_j and A_j^H
-        const int N = c.N, nd = c.nd;
+        // constants: A0 = -i H_drift, A_j = -i H_j dense, ELL forms of A_j and A_j^H, sparse anticommutators {A_i, A_j}
+        const int N = c.N, nd = c.nd, npair = nd * (nd + 1) / 2;
         int W = 1;
         for (int q : C.members) {
             const Integ& I = h->integ[q];
-            for (int j = 0; j < nd; ++j) {
+            for (int j = 0; j < nd; ++j)
                 for (int r = 0; r < N; ++r) {
                     int cnt = 0, cnta = 0;
                     for (int k = 0; k < N; ++k) {
@@ -360,13 +436,37 @@ int build(qck_handle* h) {
                     }
                     W = std::max(W, std::max(cnt, cnta));
                 }
-            }
         }
         c.W = W;
-        c.cmat_stride = N * N * (1 + nd) + nd * 2 * N * W;
         c.ell_stride = nd * 2 * N * W;
+        // {A_i, A_j} = -(H_i H_j + H_j H_i) for A = -iH, pairs ordered by (j, i <= j)
+        std::vector<std::vector<std::vector<std::pair<int, std::complex<double>>>>> kk(nm);
+        int kk_cap = 0;
+        for (int m2 = 0; m2 < nm; ++m2) {
+            const Integ& I = h->integ[C.members[m2]];
+            kk[m2].resize(npair);
+            int tot = 0;
+            for (int j = 0, pidx = 0; j < nd; ++j)
+                for (int i = 0; i <= j; ++i, ++pidx) {
+                    const std::complex<double>* Hi = I.Hdrives.data() + (size_t)i * N * N;
+                    const std::complex<double>* Hj = I.Hdrives.data() + (size_t)j * N * N;
+                    for (int r = 0; r < N; ++r)
+                        for (int k = 0; k < N; ++k) {
+                            std::complex<double> v = 0.0;
+                            for (int u = 0; u < N; ++u) v += Hi[r + (size_t)N * u] * Hj[u + (size_t)N * k] + Hj[r + (size_t)N * u] * Hi[u + (size_t)N * k];
+                            if (v != 0.0) { kk[m2][pidx].push_back({(r << 8) | k, -v}); ++tot; }
+                        }
+                }
+            kk_cap = std::max(kk_cap, tot);
+        }
+        if (N > 255) return fail(h, QCK_EINVAL, "levels > 255 unsupported");
+        c.kk_cap = kk_cap;
+        qck_smem_finalize(c);
+        if ((size_t)c.sm_bytes > 227 * 1024 - 4096)
+            return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024 - 4096);
+        c.cmat_stride = N * N * (1 + nd) + c.ell_stride + kk_cap;
         std::vector<double2> cmat((size_t)nm * c.cmat_stride, make_double2(0.0, 0.0));
-        std::vector<int> ellc((size_t)nm * std::max(c.ell_stride, 1), 0);
+        std::vector<int> icon((size_t)nm * c.icon_stride, 0);
         std::vector<int> soff(nm), coff(nm), roff(nm);
         for (int m2 = 0; m2 < nm; ++m2) {
             const Integ& I = h->integ[C.members[m2]];
@@ -377,7 +477,7 @@ int build(qck_handle* h) {
             for (int j = 0; j < nd; ++j)
                 for (int e = 0; e < N * N; ++e) base[N * N + j * N * N + e] = minus_i(I.Hdrives[(size_t)j * N * N + e]);
             double2* ev = base + N * N * (1 + nd);
-            int* ec = ellc.data() + (size_t)m2 * c.ell_stride;
+            int* ec = icon.data() + (size_t)m2 * c.icon_stride;
             for (int j = 0; j < nd; ++j)
                 for (int adj = 0; adj < 2; ++adj)
                     for (int r = 0; r < N; ++r) {
@@ -394,13 +494,19 @@ int build(qck_handle* h) {
                             ++w;
                         }
                     }
+            double2* kv = ev + c.ell_stride;
+            int* kptr = ec + c.ell_stride;
+            int* krc = kptr + npair + 1;
+            int u = 0;
+            for (int pidx = 0; pidx < npair; ++pidx) {
+                kptr[pidx] = u;
+                for (auto& t : kk[m2][pidx]) { krc[u] = t.first; kv[u] = make_double2(t.second.real(), t.second.imag()); ++u; }
+            }
+            kptr[npair] = u;
         }
         cudaError_t e;
-        qck_smem_finalize(c);
-        if ((size_t)c.sm_bytes > 227 * 1024)
-            return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024);
-        if ((e = upload(tab, &c.tab, C.allocs)) != cudaSuccess || (e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||
-            (e = upload(cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(ellc, &c.ell_col, C.allocs)) != cudaSuccess ||
+        if ((e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||
+            (e = upload(cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(icon, &c.ell_col, C.allocs)) != cudaSuccess ||
             (e = upload(soff, &c.state_off, C.allocs)) != cudaSuccess || (e = upload(coff, &c.ctrl_off, C.allocs)) != cudaSuccess ||
             (e = upload(roff, &c.row_off, C.allocs)) != cudaSuccess)
             return fail(h, QCK_ECUDA, "uploading class constants: %s", cudaGetErrorString(e));
@@ -528,7 +634,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
         I.state_off = s.state_off; I.state_len = s.state_len; I.ctrl_off = s.ctrl_off;
         if (I.kind < 0 || I.kind > QCK_DERIVATIVE) { fail(h, QCK_EINVAL, "integrator %d: unknown kind %d", q, I.kind); return bail(QCK_EINVAL); }
         if (I.quantum()) {
-            if (I.N < 1 || I.nd < 0 || I.nd > QCK_MAX_DRIVES) { fail(h, QCK_EINVAL, "integrator %d: levels=%d n_drives=%d unsupported (max %d drives)", q, I.N, I.nd, QCK_MAX_DRIVES); return bail(QCK_EINVAL); }
+            if (I.N < 1 || I.nd < 1 || I.nd > QCK_MAX_DRIVES) { fail(h, QCK_EINVAL, "integrator %d: levels=%d n_drives=%d unsupported (max %d drives)", q, I.N, I.nd, QCK_MAX_DRIVES); return bail(QCK_EINVAL); }
             I.nc = I.unitary() ? I.N : 1;
             I.dim = 2 * I.N * I.nc;
             if (I.state_len != I.dim) { fail(h, QCK_EINVAL, "integrator %d: state_len %d != %d", q, I.state_len, I.dim); return bail(QCK_EINVAL); }

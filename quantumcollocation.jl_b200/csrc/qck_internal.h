@@ -7,31 +7,43 @@
 #include "../../include/qcknot.h"
 
 #define QCK_TILE 3          // register tile edge of the small complex products (3x3 complex per thread)
-#define QCK_MAX_DRIVES 8
+#define QCK_MAX_DRIVES 6
 #define QCK_MAX_PADE_M 5    // Pade order <= 10
 
-// ---- scratch layout of the Pade-4 kernel (indices of matrices inside the CTA's shared-memory scratch) --------
-// "A-type" matrices are NP x NP complex, "state-type" are NP x ncp complex (ncp = NP for unitaries, 1 for kets).
-// Several slots are overwritten in place by the final outputs during assembly (the "->" notes).
-enum { QA_A = 0, QA_AH = 1 /* -> B */, QA_A2 = 2 /* -> F */, QA_COUNT = 3, QA_B = QA_AH, QA_F = QA_A2 };
-// state-type, fixed part:  D -> R (residual), AS -> Th (d/ddt), AhM -> Kh0 (state_t x dt), AhAhM -> Kh1 (dt x state_t+1)
-enum { QS_D = 0, QS_S = 1, QS_M = 2, QS_AD = 3, QS_AS = 4, QS_AHM = 5, QS_AAD = 6, QS_AHAHM = 7, QS_FIXED = 8 };
-// state-type, per drive j (index QS_FIXED + QD_COUNT*j + k):
-//   Q1 = A_j D,  N1 = A_j^H M -> Ka0 (state_t x a_j),  AQ1 = A (A_j D) -> Ta (d/da_j),  AhN1 = A^H (A_j^H M) -> Ka1 (a_j x state_t+1)
-enum { QD_Q1 = 0, QD_N1 = 1, QD_AQ1 = 2, QD_AHN1 = 3, QD_COUNT = 4, QD_KA0 = QD_N1, QD_TA = QD_AQ1, QD_KA1 = QD_AHN1 };
-// scalar slots (doubles) after the matrices: [ONE | Hah[0..nd) | Hhh | Haa column-wise (j*nd + i, i <= j)]
-enum { QX_ONE = 0, QX_HAH = 1 /* + j */ };
-static inline __host__ __device__ int qx_hhh(int nd) { return QX_HAH + nd; }
-static inline __host__ __device__ int qx_haa(int nd, int i, int j) { return QX_HAH + nd + 1 + j * nd + i; }
+// ---- shared-memory scratch of the quantum kernels -----------------------------------------------------------------
+// "A-type" matrices are NP x NP complex, "state-type" are NP x ncp complex (ncp = NP for unitaries, 1 for kets),
+// both column-major with leading dimension NP (NP = N rounded up to the register tile).
+// Pade-4 kernel: A, A2, G = D M^H, G2 = S M^H, C_j = {A_j, A}  |  D, S, M, AS, AhM
+enum { QA_A = 0, QA_A2 = 1, QA_G = 2, QA_G2 = 3, QA_C = 4 /* + j */ };
+enum { QS_D = 0, QS_S = 1, QS_M = 2, QS_AS = 3, QS_AHM = 4, QS_COUNT = 5 };
 
-// One contiguous run of output positions of one integrator: out[dst + k] = +-scratch[tab[src_off + k % period]].
-// period < len marks the kron(I_N, .) blocks: the same 2N x 2N values are stored len/period times.
-struct QckSeg {
-    int dst;      // first position inside the knot block (Hessian: >= nnzH means partial column dst - nnzH)
-    int len;
-    int src_off;  // into the class table of scratch slots (uint16, bit 15 = negate)
-    int period;
+// ---- output quantities ---------------------------------------------------------------------------------------------------
+// Every value a quantum integrator writes belongs to one of these quantities.  The host decides where each quantity
+// lives inside the CTA's shared-memory OUTPUT IMAGE (base + element * stride) such that the image is laid out in the
+// solver's structure order; the kernel's epilogues write values there and the write-out is a plain contiguous copy.
+//   iso blocks  (2N x 2N real, column-major; stored once, written N times: kron(I_N, .)):  ISOF = -iso(F|E), ISOB = +iso(B)
+//   iso-vectors (element i of vec_iso(X), i = cc*2N + q):  R residual, TH d/ddt, TA_j d/da_j,
+//                KH0 (state_t x dt), KH1 (dt x state_t+1), KA0_j (state_t x a_j), KA1_j (a_j x state_t+1)
+//   scalars:     HHH (dt x dt), HAH_j (a_j x dt), HAA_ij (a_i x a_j, i <= j), ONE (constant 1: identity Jacobian block)
+enum {
+    QO_ISOF = 0, QO_ISOB = 1, QO_R = 2, QO_TH = 3, QO_KH0 = 4, QO_KH1 = 5,
+    QO_TA = 6, QO_KA0 = QO_TA + QCK_MAX_DRIVES, QO_KA1 = QO_KA0 + QCK_MAX_DRIVES,
+    QO_HHH = QO_KA1 + QCK_MAX_DRIVES, QO_HAH = QO_HHH + 1, QO_HAA = QO_HAH + QCK_MAX_DRIVES,
+    QO_ONE = QO_HAA + QCK_MAX_DRIVES * QCK_MAX_DRIVES, QO_COUNT = QO_ONE + 1
 };
+static inline __host__ __device__ int qo_haa(int i, int j) { return QO_HAA + j * QCK_MAX_DRIVES + i; }
+
+// One unit of write-out work, owned by one warp: nrep back-to-back copies of n doubles,
+//   out_arr[dst + r*n + k] = image[img + k],  0 <= k < n, 0 <= r < nrep.
+// nrep > 1 marks a kron(I_N, .) block: the same 2N x 2N values are stored N times.  The host cuts the per-integrator
+// runs into units and balances them over the CTA's warps (per-member table: int hdr[QCK_SEG_HDR] = first unit of each warp).
+struct QckSeg {
+    int dst;       // first position inside the knot block (Hessian: >= nnzH means partial column dst - nnzH)
+    int n;
+    int img_nrep;  // image offset (doubles, always even) | nrep << 16
+    int arr;       // 0 F, 1 J, 2 H
+};
+#define QCK_SEG_HDR 16  // ints (warp w owns units [hdr[w], hdr[w+1]))
 
 // One auxiliary (derivative-integrator) entry of a knot block; evaluated by a single thread.
 enum { QAUX_CONST = 0, QAUX_NEG_DT = 1, QAUX_NEG_Z = 2, QAUX_NEG_MU = 3, QAUX_FROW = 4 };
@@ -53,23 +65,27 @@ struct QckClassDev {
     double dt_fixed;
     int n_members;
     // scratch (offsets in doubles)
-    int off_A, msa, off_S, mss, off_X, scratch_doubles;
+    int off_A, msa, off_S, mss, off_img, img_doubles, scratch_doubles;
+    // placement of every output quantity inside the image: element i lives at off_img + pl_base[q] + i * pl_stride[q]
+    short pl_base[QO_COUNT];
+    short pl_stride[QO_COUNT];
     // per member
     const int* state_off;
     const int* ctrl_off;
     const int* row_off;
-    const double2* cmat;  // [member][A0: N*N | Adr: nd*N*N | ell_val: nd*2*N*W]
+    const double2* cmat;  // [member][A0: N*N | Adr: nd*N*N | ell_val: nd*2*N*W | kk_val: kk_cap]
     int cmat_stride;
-    const int* ell_col;  // [member][nd*2*N*W]
-    int ell_stride;
-    // output maps: class-level table of scratch slots + per-member segments [member][nsegJ + nsegH]
-    const uint16_t* tab;
-    int tab_len;
-    int nsegJ, nsegH;
-    const QckSeg* segs;
+    const int* ell_col;   // [member][ell_col: nd*2*N*W | kk_ptr: npair+1 | kk_rc: kk_cap]   (kk = sparse {A_i, A_j})
+    int ell_stride;       // nd*2*N*W
+    int icon_stride;      // ints per member in ell_col
+    int kk_cap;
+    // write-out units per member: [member][QCK_SEG_HDR ints | nseg units], balanced over `threads`/32 warps
+    int nseg, threads;
+    const QckSeg* segs;  // (QCK_SEG_HDR/4 + nseg) QckSeg-sized records per member
     // shared-memory carve-up (byte offsets from the dynamic smem base; all 16-byte aligned)
-    int sm_tab, sm_seg, sm_ell, sm_stage, sm_bytes;
-    int seg_bytes, ell_bytes;  // size of ONE buffer of the double-buffered per-member tables
+    int sm_seg, sm_con, sm_stage, sm_bytes;
+    int seg_bytes, con_bytes;  // size of ONE buffer of the double-buffered per-member tables
+    int n_tbuf;                // 1 when a single member is active (tables never change), else 2
 };
 
 struct QckLaunch {
@@ -99,7 +115,8 @@ struct QckReduce {  // fixed-order reduction of shared Hessian positions
 // kernel launchers (qck_kernels.cu).  Return cudaError_t as int.
 int qck_launch_quantum(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches);
 int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches);
-int qck_fused_aux_limit(void);  // more aux entries than this go through the stand-alone aux kernel
+int qck_fused_aux_limit(void);
+int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,
                       int npart, cudaStream_t stream, int* launches);
 // scratch sizing shared by host map builder and kernels

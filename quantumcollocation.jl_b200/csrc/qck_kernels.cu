@@ -34,40 +34,40 @@ __device__ __forceinline__ void cfma(double2& c, double2 a, double2 b) {
     c.y = fma(a.y, b.x, c.y);
 }
 
-// C[r0:r0+3, c0:c0+TC] = A[r0:r0+3, 0:N] * B[0:N, c0:c0+TC]; column-major, leading dimension ld (complex elements).
+// acc[i][j] = sum_k opA(A)[r0+i, k] * opB(B)[k, c0+j],  k < K, 3 x TC complex register tile.
+// Operands are column-major with leading dimension ld.  opX = conj-transpose when tX is set, expressed through
+// runtime strides + a sign on the imaginary part so that every product of a stage runs the same instruction stream.
 template <int TC>
-__device__ __forceinline__ void tile_mm(const double2* __restrict__ A, const double2* __restrict__ B,
-                                        double2* __restrict__ C, int N, int ld, int r0, int c0) {
-    double2 acc[QCK_TILE][TC];
+__device__ __forceinline__ void tile_mm(const double2* __restrict__ A, bool tA, const double2* __restrict__ B, bool tB,
+                                        int K, int ld, int r0, int c0, double2 (&acc)[QCK_TILE][TC]) {
 #pragma unroll
     for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
         for (int j = 0; j < TC; ++j) acc[i][j] = make_double2(0.0, 0.0);
-    const double2* a = A + r0;
-    const double2* b = B + (size_t)ld * c0;
+    const int ar = tA ? ld : 1, ak = tA ? 1 : ld;  // A[(r0+i)*ar + k*ak]
+    const int bc = tB ? 1 : ld, bk = tB ? ld : 1;  // B[(c0+j)*bc + k*bk]
+    const double sa = tA ? -1.0 : 1.0, sb = tB ? -1.0 : 1.0;  // conjugation = sign of the imaginary part
+    const double2* a = A + r0 * ar;
+    const double2* b = B + c0 * bc;
 #pragma unroll 9
-    for (int k = 0; k < N; ++k) {
+    for (int k = 0; k < K; ++k) {
         double2 av[QCK_TILE], bv[TC];
 #pragma unroll
-        for (int i = 0; i < QCK_TILE; ++i) av[i] = a[i + ld * k];
+        for (int i = 0; i < QCK_TILE; ++i) {
+            av[i] = a[i * ar + k * ak];
+            av[i].y *= sa;
+        }
 #pragma unroll
-        for (int j = 0; j < TC; ++j) bv[j] = b[k + ld * j];
+        for (int j = 0; j < TC; ++j) {
+            bv[j] = b[j * bc + k * bk];
+            bv[j].y *= sb;
+        }
 #pragma unroll
         for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
             for (int j = 0; j < TC; ++j) cfma(acc[i][j], av[i], bv[j]);
     }
-#pragma unroll
-    for (int i = 0; i < QCK_TILE; ++i)
-#pragma unroll
-        for (int j = 0; j < TC; ++j) C[r0 + i + ld * (c0 + j)] = acc[i][j];
 }
-
-struct Prod {
-    const double2* A;
-    const double2* B;
-    double2* C;
-};
 
 // out[r, c] = sum_w val[r][w] * X[col[r][w], c]   (fixed-width sparse row format of a constant drive matrix)
 __device__ __forceinline__ double2 ell_row(const double2* __restrict__ val, const int* __restrict__ col, int W,
@@ -81,18 +81,6 @@ __device__ __forceinline__ double2 ell_row(const double2* __restrict__ val, cons
     return acc;
 }
 
-__device__ __forceinline__ double re_dot(const double2* X, const double2* Y, int N, int nc, int ld, int lane) {
-    // sum over real elements of Re(conj(X) Y), strided over the 32 lanes of a warp (not yet reduced)
-    double s = 0.0;
-    int n = N * nc;
-    for (int e = lane; e < n; e += 32) {
-        int r = e % N, c = e / N;
-        double2 x = X[r + ld * c], y = Y[r + ld * c];
-        s = fma(x.x, y.x, s);
-        s = fma(x.y, y.y, s);
-    }
-    return s;
-}
 __device__ __forceinline__ double warp_sum(double s) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -158,54 +146,50 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-__device__ __forceinline__ double slot_val(const double* __restrict__ sm, unsigned s) {
-    double v = sm[s & 0x7fffu];
-    return (s & 0x8000u) ? -v : v;
-}
-
-// Output segments: out[dst + k] = +-scratch[tab[src_off + k % period]].  Everything the loop touches except the
-// destination is in shared memory; consecutive threads store consecutive positions (coalesced).  Stores are 16-byte
-// (two values) whenever the destination is 16-byte aligned, 8-byte otherwise.
-// A periodic segment (kron(I_N, .) block) gathers each value once and stores it len/period times.
-__device__ __forceinline__ void write_segments(const double* __restrict__ sm, const uint16_t* __restrict__ tab,
-                                               const QckSeg* __restrict__ segs, int nseg, double* __restrict__ out,
-                                               long long limit, double* __restrict__ partial, int tid, int nthreads) {
-    for (int s = 0; s < nseg; ++s) {
+// Write-out: every unit is nrep back-to-back contiguous copies image -> value array, owned by ONE warp (the host
+// balanced the units over the warps).  Consecutive lanes store consecutive positions; 16-byte loads/stores whenever
+// the destination is 16-byte aligned (unit image offsets are always even), 8-byte otherwise.
+__device__ __forceinline__ void write_units(const double* __restrict__ image, const QckSeg* __restrict__ segs, int s0, int s1,
+                                            const QckLaunch& p, long long t, int lane) {
+    for (int s = s0; s < s1; ++s) {
         const QckSeg sg = segs[s];
-        double* dst = (long long)sg.dst < limit ? out + sg.dst : partial + (sg.dst - limit);
-        const uint16_t* tb = tab + sg.src_off;
+        if (!((p.mask >> sg.arr) & 1u)) continue;
+        double* dst;
+        if (sg.arr == 0) dst = p.F + t * p.c.dyn + sg.dst;
+        else if (sg.arr == 1) dst = p.J + t * p.nnzJ + sg.dst;
+        else dst = (long long)sg.dst < p.nnzH ? p.H + t * p.nnzH + sg.dst : p.partial + t * p.npart + (sg.dst - p.nnzH);
+        const double* src = image + (sg.img_nrep & 0xffff);
+        const int nrep = sg.img_nrep >> 16, n = sg.n;
         const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
-        if (sg.period == sg.len) {
-            // head (one value if misaligned), 16-byte body, tail
-            const int head = odd ? 1 : 0;
-            const int pairs = (sg.len - head) >> 1;
-            if (tid == 0 && head) dst[0] = slot_val(sm, tb[0]);
-            double2* d2 = reinterpret_cast<double2*>(dst + head);
-            const uint16_t* t2 = tb + head;
-            int k = tid;
-            for (; k + nthreads < pairs; k += 2 * nthreads) {
-                double a0 = slot_val(sm, t2[2 * k]), a1 = slot_val(sm, t2[2 * k + 1]);
-                double b0 = slot_val(sm, t2[2 * (k + nthreads)]), b1 = slot_val(sm, t2[2 * (k + nthreads) + 1]);
-                d2[k] = make_double2(a0, a1);
-                d2[k + nthreads] = make_double2(b0, b1);
-            }
-            for (; k < pairs; k += nthreads) d2[k] = make_double2(slot_val(sm, t2[2 * k]), slot_val(sm, t2[2 * k + 1]));
-            if (tid == nthreads - 1 && head + 2 * pairs < sg.len) dst[sg.len - 1] = slot_val(sm, tb[sg.len - 1]);
-        } else {
-            const int nrep = sg.len / sg.period;
-            if (!odd && !(sg.period & 1)) {
-                const int hp = sg.period >> 1;
-                for (int k = tid; k < hp; k += nthreads) {
-                    const double2 v = make_double2(slot_val(sm, tb[2 * k]), slot_val(sm, tb[2 * k + 1]));
-                    double2* d = reinterpret_cast<double2*>(dst) + k;
+        if (!odd && !(n & 1)) {
+            const int hp = n >> 1;
+            const double2* s2 = reinterpret_cast<const double2*>(src);
+            double2* d2 = reinterpret_cast<double2*>(dst);
+            if (nrep == 1) {
+                for (int k = lane; k < hp; k += 32) d2[k] = s2[k];
+            } else {
+                for (int k = lane; k < hp; k += 32) {
+                    const double2 v = s2[k];
+                    double2* d = d2 + k;
                     for (int r = 0; r < nrep; ++r) d[(size_t)r * hp] = v;
                 }
-            } else {
-                for (int k = tid; k < sg.period; k += nthreads) {
-                    const double v = slot_val(sm, tb[k]);
-                    double* d = dst + k;
-                    for (int r = 0; r < nrep; ++r) d[(size_t)r * sg.period] = v;
-                }
+            }
+        } else if (nrep == 1) {
+            // misaligned and/or odd length: scalar head / tail, 16-byte body
+            const int head = odd ? 1 : 0;
+            const int pairs = (n - head) >> 1;
+            double2* d2 = reinterpret_cast<double2*>(dst + head);
+            const double* sh = src + head;
+            if (lane == 31) {
+                if (head) dst[0] = src[0];
+                if (head + 2 * pairs < n) dst[n - 1] = src[n - 1];
+            }
+            for (int k = lane; k < pairs; k += 32) d2[k] = make_double2(sh[2 * k], sh[2 * k + 1]);
+        } else {
+            for (int k = lane; k < n; k += 32) {
+                const double v = src[k];
+                double* d = dst + k;
+                for (int r = 0; r < nrep; ++r) d[(size_t)r * n] = v;
             }
         }
     }
@@ -213,21 +197,22 @@ __device__ __forceinline__ void write_segments(const double* __restrict__ sm, co
 
 // ------------------------------------------------------------------------------------------------------------
 // Pade-4 integrators (UnitaryPadeIntegrator / QuantumStatePadeIntegrator, order 4).
-//   F = I + h/2 A + h^2/12 A^2,  B = I - h/2 A + h^2/12 A^2,  residual R = B U1 - F U0,  A = -i H(a), h = dt
-// with D = U1-U0, S = U1+U0, M = multipliers as a complex matrix (mu^T vec_iso(R) = Re <M, R>):
-//   R       = D - h/2 A S + h^2/12 A (A D)
-//   dR/da_j = -h/2 A_j S + h^2/12 (A_j (A D) + A (A_j D))
-//   dR/dh   = -1/2 A S + h/6 A (A D)
-//   (dF_j)^H M = h/2 A_j^H M + h^2/12 (A^H (A_j^H M) + A_j^H (A^H M)),  (dB_j)^H M: first term negated
-//   (dF/dh)^H M = 1/2 A^H M + h/6 A^H (A^H M),                         (dB/dh)^H M: first term negated
-//   d2/da_i da_j = h^2/12 Re(<A_i^H M, A_j D> + <A_j^H M, A_i D>)
-//   d2/da_j dh   = Re <M, -1/2 A_j S + h/6 (A_j (A D) + A (A_j D))>,   d2/dh2 = 1/6 Re <M, A (A D)>
-// 6 + 2 n_d dense N^3 products per knot (vs ~45 in the reference's real-iso formulation); products with the
-// constant drive matrices A_j are sparse (ELL rows) and the cheap ones are recomputed on the fly instead of stored.
+//   F = I + h/2 A + h^2/12 A^2,  B = I - h/2 A + h^2/12 A^2,  residual R = B U1 - F U0,  A = -i H(a), h = dt.
+// With D = U1-U0, S = U1+U0, M = multipliers as a complex matrix (mu^T vec_iso(R) = Re <M, R>), C_j = A_j A + A A_j,
+// G = D M^H, G2 = S M^H (so that Re <M, K D> = Re tr(K G) for any N x N matrix K):
+//   R       = D - h/2 A S + h^2/12 A^2 D                     dR/dh = -1/2 A S + h/6 A^2 D
+//   dR/da_j = -h/2 A_j S + h^2/12 C_j D
+//   state_t x a_j:   -(h/2 A_j^H M + h^2/12 C_j^H M)         a_j x state_t+1:  -h/2 A_j^H M + h^2/12 C_j^H M
+//   state_t x dt:    -(1/2 A^H M + h/6 (A^2)^H M)            dt x state_t+1:   -1/2 A^H M + h/6 (A^2)^H M
+//   a_i x a_j = h^2/12 Re tr({A_i, A_j} G)     a_j x dt = -1/2 Re tr(A_j G2) + h/6 Re tr(C_j G)     dt x dt = 1/6 Re tr(A^2 G)
+// Dense N^3-type products per knot: stage 1: A^2, A S, A^H M, D M^H, S M^H;  stage 2: A^2 D, (A^2)^H M, C_j D, C_j^H M
+// (5 + 2 + 2 n_d; the reference's real-iso formulation needs ~45 of twice the size).  {A_i, A_j} is a constant sparse
+// matrix (host-precomputed), A_j is sparse (ELL rows): every product with them is O(nnz).
 //
-// Shared memory per CTA: [scratch matrices | slot table | per-member segments x2 | per-member ELL x2 | input staging].
-// The inputs (and, when the member changes, the tables) of the NEXT work item are prefetched with cp.async while
-// the current item computes, so no global-load latency sits on the per-item critical path.
+// Every product's epilogue writes final values straight into the CTA's OUTPUT IMAGE, a shared-memory buffer laid out
+// in the solver's structure order (host-computed placement), so the write-out is a contiguous smem -> HBM copy.
+// Shared memory per CTA: [matrices | image | per-member segments + constants (x2 if several members) | input staging | aux].
+// The inputs (and tables, when the member changes) of the NEXT work item are prefetched with cp.async during compute.
 // ------------------------------------------------------------------------------------------------------------
 template <int TC, int CN>
 __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade4_kernel(const QckLaunch p) {
@@ -235,42 +220,41 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
     double* sm = reinterpret_cast<double*>(smem_raw);
     const QckClassDev& c = p.c;
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     // CN > 0: levels known at compile time (index arithmetic folds, k-loops unroll); CN == 0: generic fallback
     const int N = CN > 0 ? CN : c.N;
     const int NP = CN > 0 ? ((CN + QCK_TILE - 1) / QCK_TILE) * QCK_TILE : c.NP;
     const int nc = TC == 1 ? 1 : N, ncp = TC == 1 ? 1 : NP;
     const int nd = c.nd, W = c.W;
     const bool needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H, needF = p.mask & QCK_EVAL_F;
-    const bool needT = needJ || needH;  // first-order drive terms
+    const bool needT = needJ || needH;  // drive terms
     const bool free_time = c.free_time;
-    const int dim = 2 * N * nc;
-    // auxiliary (derivative-integrator) entries live behind the class's shared-memory carve-up
-    QckAux* auxs = reinterpret_cast<QckAux*>(smem_raw + c.sm_bytes);
-    double* auxv = reinterpret_cast<double*>(smem_raw + c.sm_bytes + p.n_aux * (int)sizeof(QckAux));
+    const int dim = 2 * N * nc, n2 = 2 * N;
+    const int npair = nd * (nd + 1) / 2;
 
     double2* SA = reinterpret_cast<double2*>(sm + c.off_A);
     double2* SS = reinterpret_cast<double2*>(sm + c.off_S);
-    double* SX = sm + c.off_X;
-    uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + c.sm_tab);
+    double* image = sm + c.off_img;
     double* stage = reinterpret_cast<double*>(smem_raw + c.sm_stage);  // [z_t state | z_t+1 state | mu | a | h]
-    const int nseg = c.nsegJ + c.nsegH;
-    const int elln = c.ell_stride;
+    QckAux* auxs = reinterpret_cast<QckAux*>(smem_raw + c.sm_bytes);
+    double* auxv = reinterpret_cast<double*>(smem_raw + c.sm_bytes + p.n_aux * (int)sizeof(QckAux));
+    const int nrec = QCK_SEG_HDR / 4 + c.nseg;  // 16-byte records of the per-member write-out table
+    const int lane = tid & 31, warp = tid >> 5;
+    const int elln = c.ell_stride, kkc = c.kk_cap;
     const int msa = NP * NP, mss = NP * ncp;  // complex elements per matrix
 #define MA(i) (SA + (i) * msa)
 #define MS(i) (SS + (i) * mss)
-#define MD(j, k) (SS + (QS_FIXED + QD_COUNT * (j) + (k)) * mss)
 #define SEGBUF(b) reinterpret_cast<QckSeg*>(smem_raw + c.sm_seg + (b) * c.seg_bytes)
-#define ELLV(b) reinterpret_cast<double2*>(smem_raw + c.sm_ell + (b) * c.ell_bytes)
-#define ELLC(b) reinterpret_cast<int*>(smem_raw + c.sm_ell + (b) * c.ell_bytes + elln * 16)
+#define CONV(b) reinterpret_cast<double2*>(smem_raw + c.sm_con + (b) * c.con_bytes)
+#define CONI(b) reinterpret_cast<int*>(smem_raw + c.sm_con + (b) * c.con_bytes + (elln + kkc) * 16)
+#define PUT(q, i, v) image[c.pl_base[q] + (i) * c.pl_stride[q]] = (v)
 
     const int nact = p.member_end - p.member_begin;
     const long long n_items = p.n_knots * nact;
     const int tilesS = (NP / QCK_TILE) * (ncp / TC);
     const int tilesA = (NP / QCK_TILE) * (NP / QCK_TILE);
-    const int tcols = ncp / TC;
+    const int tcols = ncp / TC, tcolsA = NP / QCK_TILE;
 
-    // prefetch of one work item: inputs into `stage`, and the member's segment + ELL tables into buffer b if asked
+    // prefetch of one work item: inputs into `stage`, and the member's tables into buffer b if asked
     auto prefetch = [&](long long item, int b, bool tables) {
         const long long t = item / nact;
         const int m = p.member_begin + (int)(item - t * nact);
@@ -292,19 +276,20 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
             }
         }
         if (tables) {
-            const QckSeg* gs = c.segs + (size_t)m * nseg;
-            for (int i = tid; i < nseg; i += nthreads) cp_async16(SEGBUF(b) + i, gs + i);
+            const QckSeg* gs = c.segs + (size_t)m * nrec;
+            for (int i = tid; i < nrec; i += nthreads) cp_async16(SEGBUF(b) + i, gs + i);
             const double2* gv = c.cmat + (size_t)m * c.cmat_stride + N * N * (1 + nd);
-            const int* gc = c.ell_col + (size_t)m * c.ell_stride;
-            for (int i = tid; i < elln; i += nthreads) { cp_async16(ELLV(b) + i, gv + i); cp_async4(ELLC(b) + i, gc + i); }
+            const int* gc = c.ell_col + (size_t)m * c.icon_stride;
+            for (int i = tid; i < elln + kkc; i += nthreads) cp_async16(CONV(b) + i, gv + i);
+            for (int i = tid; i < c.icon_stride; i += nthreads) cp_async4(CONI(b) + i, gc + i);
         }
         cp_async_commit();
     };
 
     for (int i = tid; i < c.scratch_doubles; i += nthreads) sm[i] = 0.0;
-    for (int i = tid; i < c.tab_len; i += nthreads) tab[i] = c.tab[i];
     for (int i = tid; i < p.n_aux; i += nthreads) auxs[i] = p.aux[i];
     __syncthreads();
+    if (tid == 0 && c.pl_base[QO_ONE] >= 0) image[c.pl_base[QO_ONE]] = 1.0;
     int buf = 0, buf_member = -1;
     if ((long long)blockIdx.x < n_items) {
         buf_member = p.member_begin + (int)(blockIdx.x % nact);
@@ -316,21 +301,24 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
         const int mi = (int)(item - t * nact);
         const int m = p.member_begin + mi;
         cp_async_wait_all();
-        __syncthreads();  // staged inputs visible; previous item's write-out has finished reading scratch
-        if (tid == 0) SX[QX_ONE] = 1.0;
-        const int roff = __ldg(c.row_off + m);
+        __syncthreads();  // staged inputs visible; previous item's write-out has finished reading the image
         const double2* cm = c.cmat + (size_t)m * c.cmat_stride;
         const double2* A0 = cm;
         const double2* Adr = cm + N * N;
-        const double2* ellv = ELLV(buf);
-        const int* ellc = ELLC(buf);
-        const QckSeg* segs = SEGBUF(buf);
+        const double2* ellv = CONV(buf);
+        const double2* kkv = CONV(buf) + elln;
+        const int* ellc = CONI(buf);
+        const int* kkptr = CONI(buf) + elln;
+        const int* kkrc = kkptr + npair + 1;
+        const int* seghdr = reinterpret_cast<const int*>(SEGBUF(buf));
+        const QckSeg* segs = SEGBUF(buf) + QCK_SEG_HDR / 4;
         const double h = free_time ? stage[3 * dim + nd] : c.dt_fixed;
+        const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
 
-        // ---- stage 0: unpack the staged knot pair, build A = -i H(a) and A^H ---------------------------------
+        // ---- stage 0: unpack the staged knot pair into D, S, M; build A = -i H(a) -----------------------------
         {
             for (int idx = tid; idx < dim; idx += nthreads) {
-                int cc = idx / (2 * N), q = idx - cc * 2 * N;
+                int cc = idx / n2, q = idx - cc * n2;
                 int im = q >= N, r = q - im * N;
                 double u0 = stage[idx], u1 = stage[dim + idx];
                 int o = 2 * (r + NP * cc) + im;
@@ -338,7 +326,7 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
                 reinterpret_cast<double*>(MS(QS_S))[o] = u1 + u0;
                 if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = stage[2 * dim + idx];
             }
-            for (int e = tid; e < N * N; e += nthreads) {
+            for (int e = nthreads - 1 - tid; e < N * N; e += nthreads) {
                 int r = e % N, k = e / N;
                 double2 v = __ldg(A0 + e);
                 for (int j = 0; j < nd; ++j) {
@@ -348,7 +336,6 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
                     v.y = fma(aj, d.y, v.y);
                 }
                 MA(QA_A)[r + NP * k] = v;
-                MA(QA_AH)[k + NP * r] = make_double2(v.x, -v.y);
             }
         }
         __syncthreads();
@@ -364,171 +351,209 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
             }
         }
 
-        // ---- stage 1: A2, A D, A S, A^H M (dense);  Q1_j = A_j D, N1_j = A_j^H M (sparse) -----------------------
+        // ---- stage 1: A2 = A A (+ F, B blocks), AS = A S, AhM = A^H M, G = D M^H, G2 = S M^H;  C_j = A_j A + A A_j ----
         {
-            const int nA = needJ ? tilesA : 0;       // A2 only feeds F and B (Jacobian state blocks)
-            const int nS = (needH ? 3 : 2) * tilesS;  // AD, AS, (AhM)
-            for (int w = tid; w < nA + nS; w += nthreads) {
+            const int nG = needH ? (free_time ? 2 : 1) : 0;
+            const int nA = (1 + nG) * tilesA;
+            const int nS = (needH && free_time ? 2 : 1) * tilesS;
+            const int nDense = nA + nS;
+            for (int w = tid; w < nDense; w += nthreads) {
                 if (w < nA) {
-                    int tr = w / (NP / QCK_TILE), tcc = w - tr * (NP / QCK_TILE);
-                    tile_mm<QCK_TILE>(MA(QA_A), MA(QA_A), MA(QA_A2), N, NP, tr * QCK_TILE, tcc * QCK_TILE);
+                    const int pi = w / tilesA, tl = w - pi * tilesA;
+                    const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
+                    double2 acc[QCK_TILE][QCK_TILE];
+                    // pi 0: A A (K = N);  pi 1: D M^H;  pi 2: S M^H  (K = nc, B operand conj-transposed)
+                    const double2* Aop = pi == 0 ? MA(QA_A) : (pi == 1 ? MS(QS_D) : MS(QS_S));
+                    const double2* Bop = pi == 0 ? MA(QA_A) : MS(QS_M);
+                    tile_mm<QCK_TILE>(Aop, false, Bop, pi != 0, pi == 0 ? N : nc, NP, r0, c0, acc);
+                    double2* Cop = MA(pi == 0 ? QA_A2 : (pi == 1 ? QA_G : QA_G2));
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int j = 0; j < QCK_TILE; ++j) {
+                            const int r = r0 + i, cc = c0 + j;
+                            Cop[r + NP * cc] = acc[i][j];
+                            if (pi == 0 && needJ && r < N && cc < N) {
+                                const double2 a = MA(QA_A)[r + NP * cc];
+                                const double id = r == cc ? 1.0 : 0.0;
+                                const double fr = id + c1h * a.x + c2h2 * acc[i][j].x, fi = c1h * a.y + c2h2 * acc[i][j].y;
+                                const double br = id - c1h * a.x + c2h2 * acc[i][j].x, bi = -c1h * a.y + c2h2 * acc[i][j].y;
+                                const int k00 = r + n2 * cc, k01 = r + n2 * (cc + N);
+                                PUT(QO_ISOF, k00, -fr); PUT(QO_ISOF, k00 + N, -fi); PUT(QO_ISOF, k01, fi); PUT(QO_ISOF, k01 + N, -fr);
+                                PUT(QO_ISOB, k00, br);  PUT(QO_ISOB, k00 + N, bi);  PUT(QO_ISOB, k01, -bi); PUT(QO_ISOB, k01 + N, br);
+                            }
+                        }
                 } else {
-                    int w2 = w - nA;
-                    int pi = w2 / tilesS, tl = w2 - pi * tilesS;
-                    int tr = tl / tcols, tcc = tl - tr * tcols;
-                    const double2* Aop = pi == 2 ? MA(QA_AH) : MA(QA_A);
-                    const double2* Bop = pi == 0 ? MS(QS_D) : (pi == 1 ? MS(QS_S) : MS(QS_M));
-                    double2* Cop = pi == 0 ? MS(QS_AD) : (pi == 1 ? MS(QS_AS) : MS(QS_AHM));
-                    tile_mm<TC>(Aop, Bop, Cop, N, NP, tr * QCK_TILE, tcc * TC);
+                    const int w2 = w - nA;
+                    const int pi = w2 / tilesS, tl = w2 - pi * tilesS;
+                    const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
+                    double2 acc[QCK_TILE][TC];
+                    // pi 0: A S;  pi 1: A^H M
+                    tile_mm<TC>(MA(QA_A), pi == 1, pi == 0 ? MS(QS_S) : MS(QS_M), false, N, NP, r0, c0, acc);
+                    double2* Cop = MS(pi == 0 ? QS_AS : QS_AHM);
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int j = 0; j < TC; ++j) Cop[r0 + i + NP * (c0 + j)] = acc[i][j];
                 }
             }
             if (needT) {
-                const int per = N * nc;
-                const int nsp = (needH ? 2 : 1) * nd * per;
-                for (int w = nthreads - 1 - tid; w < nsp; w += nthreads) {
-                    int pj = w / per, e = w - pj * per;
-                    int adj = pj / nd, j = pj - adj * nd;
-                    int r = e % N, cc = e / N;
-                    const double2* X = adj ? MS(QS_M) : MS(QS_D);
-                    double2 v = ell_row(ellv + (j * 2 + adj) * N * W, ellc + (j * 2 + adj) * N * W, W, X, NP, r, cc);
-                    MD(j, adj ? QD_N1 : QD_Q1)[r + NP * cc] = v;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- stage 2: A(AD), A^H(A^H M), A(A_j D), A^H(A_j^H M) (dense) --------------------------------------------
-        {
-            const int nP = 1 + (needT ? nd : 0) + (needH ? 1 + nd : 0);
-            for (int w = tid; w < nP * tilesS; w += nthreads) {
-                int pi = w / tilesS, tl = w - pi * tilesS;
-                int tr = tl / tcols, tcc = tl - tr * tcols;
-                const double2 *Aop, *Bop;
-                double2* Cop;
-                if (pi == 0) {
-                    Aop = MA(QA_A); Bop = MS(QS_AD); Cop = MS(QS_AAD);
-                } else if (pi <= nd && needT) {
-                    int j = pi - 1;
-                    Aop = MA(QA_A); Bop = MD(j, QD_Q1); Cop = MD(j, QD_AQ1);
-                } else if (pi == 1 + nd) {
-                    Aop = MA(QA_AH); Bop = MS(QS_AHM); Cop = MS(QS_AHAHM);
-                } else {
-                    int j = pi - 2 - nd;
-                    Aop = MA(QA_AH); Bop = MD(j, QD_N1); Cop = MD(j, QD_AHN1);
-                }
-                tile_mm<TC>(Aop, Bop, Cop, N, NP, tr * QCK_TILE, tcc * TC);
-            }
-        }
-        __syncthreads();
-
-        // ---- stage 3a: Lagrangian-weighted scalar second derivatives (one warp per dot product) ---------------
-        if (needH) {
-            const double c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
-            const int npair = nd * (nd + 1) / 2;
-            const int ntask = npair + (free_time ? nd + 1 : 0);
-            for (int task = warp; task < ntask; task += nwarps) {
-                double s;
-                int slot;
-                if (task < npair) {
-                    int i = 0, rem = task;
-                    while (rem >= nd - i) { rem -= nd - i; ++i; }
-                    int j = i + rem;
-                    s = c2h2 * (re_dot(MD(i, QD_N1), MD(j, QD_Q1), N, nc, NP, lane) +
-                                re_dot(MD(j, QD_N1), MD(i, QD_Q1), N, nc, NP, lane));
-                    slot = qx_haa(nd, i, j);
-                } else if (task < npair + nd) {
-                    // Re <M, -1/2 A_j S + h/6 (A_j (A D) + A (A_j D))>, the two sparse products recomputed on the fly
-                    int j = task - npair;
-                    s = 0.0;
-                    for (int e = lane; e < N * nc; e += 32) {
-                        int r = e % N, cc = e / N;
-                        double2 mm = MS(QS_M)[r + NP * cc];
-                        double2 pj = ell_row(ellv + (j * 2) * N * W, ellc + (j * 2) * N * W, W, MS(QS_S), NP, r, cc);
-                        double2 q2 = ell_row(ellv + (j * 2) * N * W, ellc + (j * 2) * N * W, W, MS(QS_AD), NP, r, cc);
-                        double2 aq = MD(j, QD_AQ1)[r + NP * cc];
-                        double vr = -0.5 * pj.x + c2h * (q2.x + aq.x), vi = -0.5 * pj.y + c2h * (q2.y + aq.y);
-                        s = fma(mm.x, vr, s);
-                        s = fma(mm.y, vi, s);
+                // C_j[r, c] = sum_w A_j[r, k_w] A[k_w, c] + sum_w A[r, k_w] A_j[k_w, c]; the second sum walks row c of A_j^H
+                // (A_j[k, c] = conj(A_j^H[c, k])).  Runs on the warps the dense tiles left free.
+                int first = ((nDense + 31) >> 5) << 5;
+                if (first >= nthreads) first = 0;
+                const int nsp = nd * N * N, stride = nthreads - first;
+                for (int w = tid - first; w >= 0 && w < nsp; w += stride) {
+                    const int j = w / (N * N), e = w - j * N * N;
+                    const int r = e % N, cc = e / N;
+                    const int o0 = ((j * 2) * N + r) * W, o1 = ((j * 2 + 1) * N + cc) * W;
+                    const double2* Acol = MA(QA_A) + NP * cc;
+                    const double2* Arow = MA(QA_A) + r;
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int u = 0; u < W; ++u) {
+                        cfma(acc, ellv[o0 + u], Acol[ellc[o0 + u]]);
+                        double2 ah = ellv[o1 + u];
+                        ah.y = -ah.y;
+                        cfma(acc, Arow[NP * ellc[o1 + u]], ah);
                     }
-                    slot = QX_HAH + j;
-                } else {
-                    s = (1.0 / 6.0) * re_dot(MS(QS_M), MS(QS_AAD), N, nc, NP, lane);
-                    slot = qx_hhh(nd);
+                    MA(QA_C + j)[r + NP * cc] = acc;
                 }
-                s = warp_sum(s);
-                if (lane == 0) SX[slot] = s;
             }
-            __syncthreads();
         }
+        __syncthreads();
 
-        // ---- stage 3b-1: per-drive outputs (read S, AD, AhM; overwrite only their own element) and F, B ----------
+        // ---- stage 2: A2 D, (A2)^H M, C_j D, C_j^H M with fused epilogues into the image;  scalar traces ------------
         {
-            const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0);
-            const int per = N * nc;
-            if (needT) {
-                for (int w = tid; w < nd * per; w += nthreads) {
-                    int j = w / per, e = w - j * per;
-                    int r = e % N, cc = e / N;
-                    int o = r + NP * cc;
-                    const double2* ev = ellv + (j * 2) * N * W;
-                    const int* ec = ellc + (j * 2) * N * W;
-                    double2 pj = ell_row(ev, ec, W, MS(QS_S), NP, r, cc);
-                    double2 q2 = ell_row(ev, ec, W, MS(QS_AD), NP, r, cc);
-                    double2 aq1 = MD(j, QD_AQ1)[o];
-                    MD(j, QD_TA)[o] = make_double2(-c1h * pj.x + c2h2 * (q2.x + aq1.x), -c1h * pj.y + c2h2 * (q2.y + aq1.y));
-                    if (needH) {
-                        double2 n1 = MD(j, QD_N1)[o], ahn1 = MD(j, QD_AHN1)[o];
-                        double2 n2 = ell_row(ev + N * W, ec + N * W, W, MS(QS_AHM), NP, r, cc);
-                        double xr = n2.x + ahn1.x, xi = n2.y + ahn1.y;
-                        MD(j, QD_KA0)[o] = make_double2(-(c1h * n1.x + c2h2 * xr), -(c1h * n1.y + c2h2 * xi));
-                        MD(j, QD_KA1)[o] = make_double2(-c1h * n1.x + c2h2 * xr, -c1h * n1.y + c2h2 * xi);
+            const bool hdt = needH && free_time;  // timestep Hessian blocks exist
+            const int nP = 1 + (needT ? nd : 0) + (hdt ? 1 : 0) + (needH ? nd : 0);
+            const int nDense = nP * tilesS;
+            for (int w = tid; w < nDense; w += nthreads) {
+                const int pi = w / tilesS, tl = w - pi * tilesS;
+                const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
+                // product list: [A2 D -> R, TH] [C_j D -> TA_j]*nd [A2^H M -> KH0, KH1] [C_j^H M -> KA0_j, KA1_j]*nd
+                bool adj = false;
+                int j = -1, rest = pi - 1;
+                if (pi > 0) {
+                    if (needT && rest < nd) j = rest;
+                    else {
+                        if (needT) rest -= nd;
+                        adj = true;
+                        if (hdt && rest == 0) j = -1;
+                        else j = rest - (hdt ? 1 : 0);
                     }
                 }
-            }
-            if (needJ) {
-                for (int e = nthreads - 1 - tid; e < N * N; e += nthreads) {
-                    int r = e % N, k = e / N;
-                    double2 a = MA(QA_A)[r + NP * k], a2 = MA(QA_A2)[r + NP * k];
-                    double id = r == k ? 1.0 : 0.0;
-                    MA(QA_F)[r + NP * k] = make_double2(id + c1h * a.x + c2h2 * a2.x, c1h * a.y + c2h2 * a2.y);
-                    MA(QA_B)[r + NP * k] = make_double2(id - c1h * a.x + c2h2 * a2.x, -c1h * a.y + c2h2 * a2.y);
+                const double2* Aop = j < 0 ? MA(QA_A2) : MA(QA_C + j);
+                double2 acc[QCK_TILE][TC];
+                tile_mm<TC>(Aop, adj, adj ? MS(QS_M) : MS(QS_D), false, N, NP, r0, c0, acc);
+                // epilogue: out1 = extra + e1 E + x1 X,  out2 = e2 E + x2 X   (X = tile result, E = AS | AhM | A_j S | A_j^H M)
+                double e1, x1, e2, x2;
+                int q1, q2;
+                const double2* Esrc;
+                if (j < 0 && !adj) { e1 = -c1h; x1 = c2h2; e2 = -0.5; x2 = c2h; q1 = QO_R; q2 = QO_TH; Esrc = MS(QS_AS); }
+                else if (j < 0) { e1 = -0.5; x1 = -c2h; e2 = -0.5; x2 = c2h; q1 = QO_KH0; q2 = QO_KH1; Esrc = MS(QS_AHM); }
+                else if (!adj) { e1 = -c1h; x1 = c2h2; e2 = 0.0; x2 = 0.0; q1 = QO_TA + j; q2 = -1; Esrc = MS(QS_S); }
+                else { e1 = -c1h; x1 = -c2h2; e2 = -c1h; x2 = c2h2; q1 = QO_KA0 + j; q2 = QO_KA1 + j; Esrc = MS(QS_M); }
+                const bool want2 = q2 >= 0 && c.pl_base[q2] >= 0;
+                const int b1 = c.pl_base[q1], s1 = c.pl_stride[q1];
+                const int b2 = q2 >= 0 ? c.pl_base[q2] : 0, s2 = q2 >= 0 ? c.pl_stride[q2] : 0;
+                // E tile: stored matrix (A2 products) or sparse product with the constant drive matrix, row data shared by the tile's columns
+                double2 E[QCK_TILE][TC];
+                if (j < 0) {
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < TC; ++jj) E[i][jj] = Esrc[r0 + i + NP * (c0 + jj)];
+                } else {
+                    const int eo = (j * 2 + (adj ? 1 : 0)) * N * W;
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i) {
+#pragma unroll
+                        for (int jj = 0; jj < TC; ++jj) E[i][jj] = make_double2(0.0, 0.0);
+                        if (r0 + i < N)
+                            for (int u = 0; u < W; ++u) {
+                                const double2 v = ellv[eo + (r0 + i) * W + u];
+                                const double2* xr = Esrc + ellc[eo + (r0 + i) * W + u] + NP * c0;
+#pragma unroll
+                                for (int jj = 0; jj < TC; ++jj) cfma(E[i][jj], v, xr[NP * jj]);
+                            }
+                    }
                 }
+#pragma unroll
+                for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < TC; ++jj) {
+                        const int r = r0 + i, cc = c0 + jj;
+                        if (r < N && cc < nc) {
+                            const double2 X = acc[i][jj];
+                            double o1r = e1 * E[i][jj].x + x1 * X.x, o1i = e1 * E[i][jj].y + x1 * X.y;
+                            if (q1 == QO_R) { const double2 d = MS(QS_D)[r + NP * cc]; o1r += d.x; o1i += d.y; }
+                            const int ire = cc * n2 + r;
+                            if (b1 >= 0) {
+                                image[b1 + ire * s1] = o1r;
+                                image[b1 + (ire + N) * s1] = o1i;
+                            }
+                            if (want2) {
+                                image[b2 + ire * s2] = e2 * E[i][jj].x + x2 * X.x;
+                                image[b2 + (ire + N) * s2] = e2 * E[i][jj].y + x2 * X.y;
+                            }
+                        }
+                    }
+            }
+            if (needH) {
+                // scalar second derivatives as traces against G = D M^H and G2 = S M^H, on the warps the dense tiles left
+                // free: the N^2-term traces (dt x dt, a_j x dt) take 4 lanes each, the sparse a_i x a_j traces one lane each
+                int first = ((nDense + 31) >> 5) << 5;
+                if (first >= nthreads) first = 0;
+                const int fw = first >> 5, nfw = (nthreads >> 5) - fw;
+                const int n4 = free_time ? 1 + nd : 0, nv = 4 * n4 + npair;
+                if (warp >= fw)
+                    for (int vb = (warp - fw) * 32; vb < nv; vb += nfw * 32) {
+                        const int v = vb + lane;
+                        double val = 0.0;
+                        int q = -1;
+                        if (v < 4 * n4) {
+                            const int task = v >> 2, part = v & 3, j = task - 1;
+                            const double2* X = task == 0 ? MA(QA_A2) : MA(QA_C + j);
+                            double s1 = 0.0, s2 = 0.0;
+                            for (int e = part; e < N * N; e += 4) {  // Re tr(X G)
+                                const int r = e % N, k = e / N;
+                                const double2 xv = X[r + NP * k], g = MA(QA_G)[k + NP * r];
+                                s2 = fma(xv.x, g.x, s2);
+                                s2 = fma(-xv.y, g.y, s2);
+                            }
+                            if (task > 0)
+                                for (int e = part; e < N * W; e += 4) {  // Re tr(A_j G2), A_j sparse
+                                    const int r = e / W;
+                                    const double2 av = ellv[(j * 2) * N * W + e], g = MA(QA_G2)[ellc[(j * 2) * N * W + e] + NP * r];
+                                    s1 = fma(av.x, g.x, s1);
+                                    s1 = fma(-av.y, g.y, s1);
+                                }
+                            val = task == 0 ? s2 * (1.0 / 6.0) : -0.5 * s1 + c2h * s2;  // dt x dt | a_j x dt
+                            q = part == 0 ? (task == 0 ? QO_HHH : QO_HAH + j) : -1;
+                        } else if (v < nv) {  // a_i x a_j = h^2/12 Re tr({A_i, A_j} G); tasks in (j, i <= j) order
+                            const int task = v - 4 * n4;
+                            int j = 0, rem = task;
+                            while (rem > j) { rem -= j + 1; ++j; }
+                            for (int u = kkptr[task]; u < kkptr[task + 1]; ++u) {
+                                const int rc = kkrc[u];
+                                const double2 kv = kkv[u], g = MA(QA_G)[(rc & 255) + NP * (rc >> 8)];  // K[r, k] G[k, r]
+                                val = fma(kv.x, g.x, val);
+                                val = fma(-kv.y, g.y, val);
+                            }
+                            val *= c2h2;
+                            q = qo_haa(rem, j);
+                        }
+                        double red = val + __shfl_xor_sync(0xffffffffu, val, 1);
+                        red += __shfl_xor_sync(0xffffffffu, red, 2);
+                        if (v < 4 * n4) val = red;
+                        if (q >= 0 && c.pl_base[q] >= 0) image[c.pl_base[q]] = val;
+                    }
             }
         }
         __syncthreads();
 
-        // ---- stage 3b-2: fixed outputs in place: R, dR/dh, and the dt Hessian blocks -----------------------------------
-        {
-            const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
-            const int per = N * nc;
-            for (int e = tid; e < per; e += nthreads) {
-                int r = e % N, cc = e / N;
-                int o = r + NP * cc;
-                double2 d = MS(QS_D)[o], as = MS(QS_AS)[o], aad = MS(QS_AAD)[o];
-                MS(QS_D)[o] = make_double2(d.x - c1h * as.x + c2h2 * aad.x, d.y - c1h * as.y + c2h2 * aad.y);
-                MS(QS_AS)[o] = make_double2(-0.5 * as.x + c2h * aad.x, -0.5 * as.y + c2h * aad.y);
-                if (needH) {
-                    double2 ahm = MS(QS_AHM)[o], ahahm = MS(QS_AHAHM)[o];
-                    MS(QS_AHM)[o] = make_double2(-(0.5 * ahm.x + c2h * ahahm.x), -(0.5 * ahm.y + c2h * ahahm.y));
-                    MS(QS_AHAHM)[o] = make_double2(-0.5 * ahm.x + c2h * ahahm.x, -0.5 * ahm.y + c2h * ahahm.y);
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- stage 4: write-out ------------------------------------------------------------------------------------
-        if (needF) {
-            double* Fo = p.F + t * c.dyn + roff;
-            const double* R = reinterpret_cast<const double*>(MS(QS_D));
-            for (int idx = tid; idx < dim; idx += nthreads) {
-                int cc = idx / (2 * N), q = idx - cc * 2 * N;
-                int im = q >= N, r = q - im * N;
-                Fo[idx] = R[2 * (r + NP * cc) + im];
-            }
-        }
-        if (needJ) write_segments(sm, tab, segs, c.nsegJ, p.J + t * p.nnzJ, (long long)1 << 60, nullptr, tid, nthreads);
-        if (needH)
-            write_segments(sm, tab, segs + c.nsegJ, c.nsegH, p.H + t * p.nnzH, p.nnzH, p.partial + t * p.npart, tid, nthreads);
+        // ---- stage 3: write-out: contiguous copies image -> value arrays ---------------------------------------------
+        write_units(image, segs, seghdr[warp], seghdr[warp + 1], p, t, lane);
         if (mi == 0 && p.n_aux) do_aux_staged(p, auxs, auxv, h, t, tid, nthreads);
         buf = next_buf;
         buf_member = next_member;
@@ -536,10 +561,10 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
     cp_async_wait_all();
 #undef MA
 #undef MS
-#undef MD
 #undef SEGBUF
-#undef ELLV
-#undef ELLC
+#undef CONV
+#undef CONI
+#undef PUT
 }
 
 __global__ void qck_aux_kernel(const QckLaunch p) {
@@ -560,38 +585,39 @@ __global__ void qck_reduce_kernel(const QckReduce r, double* __restrict__ H, con
 
 }  // namespace
 
-// shared by the host map builder: where each output lives inside the CTA scratch
+// phase 1: matrices (the image is sized by the host's placement pass)
 void qck_scratch_layout(QckClassDev& c) {
     c.msa = 2 * c.NP * c.NP;
     c.mss = 2 * c.NP * c.ncp;
     c.off_A = 0;
-    int n_s = QS_FIXED + QD_COUNT * c.nd;
-    c.off_S = c.off_A + QA_COUNT * c.msa;
-    c.off_X = c.off_S + n_s * c.mss;
-    c.scratch_doubles = c.off_X + qx_haa(c.nd, 0, 0) + c.nd * c.nd;
-    c.scratch_doubles = (c.scratch_doubles + 1) & ~1;
+    c.off_S = c.off_A + (QA_C + c.nd) * c.msa;
+    c.off_img = c.off_S + QS_COUNT * c.mss;
 }
 
+// phase 2: image + per-member tables + staging, after img_doubles / W / kk_cap / nseg are known
 void qck_smem_finalize(QckClassDev& c) {
     auto al = [](int b) { return (b + 15) & ~15; };
     const int dim = 2 * c.N * c.nc;
-    c.sm_tab = al(c.scratch_doubles * 8);
-    c.sm_seg = al(c.sm_tab + c.tab_len * 2);
-    c.seg_bytes = al((c.nsegJ + c.nsegH) * (int)sizeof(QckSeg));
-    c.sm_ell = c.sm_seg + 2 * c.seg_bytes;
-    c.ell_bytes = al(c.ell_stride * 16 + c.ell_stride * 4);
-    c.sm_stage = c.sm_ell + 2 * c.ell_bytes;
+    const int npair = c.nd * (c.nd + 1) / 2;
+    c.scratch_doubles = (c.off_img + c.img_doubles + 1) & ~1;
+    c.icon_stride = c.ell_stride + npair + 1 + c.kk_cap;
+    c.sm_seg = al(c.scratch_doubles * 8);
+    c.seg_bytes = al((QCK_SEG_HDR / 4 + c.nseg) * (int)sizeof(QckSeg));
+    c.sm_con = c.sm_seg + c.n_tbuf * c.seg_bytes;
+    c.con_bytes = al((c.ell_stride + c.kk_cap) * 16 + c.icon_stride * 4);
+    c.sm_stage = c.sm_con + c.n_tbuf * c.con_bytes;
     c.sm_bytes = al(c.sm_stage + (3 * dim + c.nd + 1) * 8);
 }
 
-static int pick_threads(const QckClassDev& c, int tc) {
+int qck_pick_threads(const QckClassDev& c) {
+    const int tc = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP) ? QCK_TILE : 1;
     int tilesS = (c.NP / QCK_TILE) * (c.ncp / tc);
     int items = (2 + 2 * c.nd) * tilesS;
-    int th = ((items + 31) / 32) * 32;
+    int th = ((items + 31) / 32) * 32 + 32;  // one extra warp for the sparse products / scalar traces
     if (th < 64) th = 64;
     if (th > 256) th = 256;
-    if (c.N >= 8 && th < 128) th = 128;  // the write-out and assembly phases want the extra warp
-    return th;
+    if (c.N != 2 && c.N != 3 && c.N != 4 && c.N != 5 && c.N != 6 && c.N != 8 && c.N != 9) return th;  // generic kernel: up to 256
+    return th > 128 ? 128 : th;
 }
 
 typedef void (*qck_kernel_t)(const QckLaunch);
@@ -623,7 +649,8 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     else if (c.kind == QCK_KET_PADE && c.order == 4) kern = pade4_for<1>(c.N);
     else return (int)cudaErrorNotSupported;
     size_t smem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double));
-    int threads = pick_threads(c, tc);
+    int threads = c.threads;
+    (void)tc;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
