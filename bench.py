@@ -61,8 +61,9 @@ def algorithmic_bytes(zdim, dyn, nnzJ, nnzH):
 
 
 def flops_per_eval(N, nd, nc):
-    """Dense complex products of the implemented Pade-4 algorithm: A^2 (N^3) + (5 + 2 nd) N^2 nc products, 8 flops/cMAC."""
-    return 8 * (N ** 3 + (5 + 2 * nd) * N * N * nc)
+    """Dense complex products of the implemented Pade-4 algorithm: stage 1: A^2 (N^3), A S, A^H M (N^2 nc each),
+    D M^H, S M^H (N^2 nc each); stage 2: A^2 D, (A^2)^H M, C_j D, C_j^H M ((2 + 2 nd) N^2 nc).  8 flops per complex MAC."""
+    return 8 * (N ** 3 + (6 + 2 * nd) * N * N * nc)
 
 
 class ClockSampler(threading.Thread):

@@ -464,19 +464,17 @@ int build(qck_handle* h) {
         qck_smem_finalize(c);
         if ((size_t)c.sm_bytes > 227 * 1024 - 4096)
             return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024 - 4096);
-        c.cmat_stride = N * N * (1 + nd) + c.ell_stride + kk_cap;
+        c.cmat_stride = N * N + c.ell_stride + kk_cap;
         std::vector<double2> cmat((size_t)nm * c.cmat_stride, make_double2(0.0, 0.0));
         std::vector<int> icon((size_t)nm * c.icon_stride, 0);
-        std::vector<int> soff(nm), coff(nm), roff(nm);
+        std::vector<int> moff(3 * (size_t)nm);
         for (int m2 = 0; m2 < nm; ++m2) {
             const Integ& I = h->integ[C.members[m2]];
-            soff[m2] = I.state_off; coff[m2] = I.ctrl_off; roff[m2] = I.row_off;
+            moff[3 * m2] = I.state_off; moff[3 * m2 + 1] = I.ctrl_off; moff[3 * m2 + 2] = I.row_off;
             double2* base = cmat.data() + (size_t)m2 * c.cmat_stride;
             auto minus_i = [](std::complex<double> z) { return make_double2(z.imag(), -z.real()); };
             for (int e = 0; e < N * N; ++e) base[e] = minus_i(I.Hdrift[e]);
-            for (int j = 0; j < nd; ++j)
-                for (int e = 0; e < N * N; ++e) base[N * N + j * N * N + e] = minus_i(I.Hdrives[(size_t)j * N * N + e]);
-            double2* ev = base + N * N * (1 + nd);
+            double2* ev = base + N * N;
             int* ec = icon.data() + (size_t)m2 * c.icon_stride;
             for (int j = 0; j < nd; ++j)
                 for (int adj = 0; adj < 2; ++adj)
@@ -507,8 +505,7 @@ int build(qck_handle* h) {
         cudaError_t e;
         if ((e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||
             (e = upload(cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(icon, &c.ell_col, C.allocs)) != cudaSuccess ||
-            (e = upload(soff, &c.state_off, C.allocs)) != cudaSuccess || (e = upload(coff, &c.ctrl_off, C.allocs)) != cudaSuccess ||
-            (e = upload(roff, &c.row_off, C.allocs)) != cudaSuccess)
+            (e = upload(moff, &c.moff, C.allocs)) != cudaSuccess)
             return fail(h, QCK_ECUDA, "uploading class constants: %s", cudaGetErrorString(e));
     }
 
@@ -549,6 +546,7 @@ int run(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, doubl
     for (auto& C : h->classes) {
         if (C.member_end <= C.member_begin) continue;
         L.c = C.dev; L.member_begin = C.member_begin; L.member_end = C.member_end;
+        L.moff_global = C.dev.moff ? C.dev.moff + 3 * C.member_begin : nullptr;
         const bool take_aux = !aux_done && fuse_aux;
         L.aux = take_aux ? h->d_aux : nullptr; L.n_aux = take_aux ? (int)h->aux.size() : 0;
         if (take_aux) aux_done = true;

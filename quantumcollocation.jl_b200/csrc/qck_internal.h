@@ -70,10 +70,8 @@ struct QckClassDev {
     short pl_base[QO_COUNT];
     short pl_stride[QO_COUNT];
     // per member
-    const int* state_off;
-    const int* ctrl_off;
-    const int* row_off;
-    const double2* cmat;  // [member][A0: N*N | Adr: nd*N*N | ell_val: nd*2*N*W | kk_val: kk_cap]
+    const int* moff;      // [member][state_off, ctrl_off, row_off]
+    const double2* cmat;  // [member][A0: N*N | ell_val: nd*2*N*W | kk_val: kk_cap]
     int cmat_stride;
     const int* ell_col;   // [member][ell_col: nd*2*N*W | kk_ptr: npair+1 | kk_rc: kk_cap]   (kk = sparse {A_i, A_j})
     int ell_stride;       // nd*2*N*W
@@ -103,6 +101,10 @@ struct QckLaunch {
     int member_begin, member_end;
     const QckAux* aux;  // processed by the first active member's CTA of class 0 (or by the aux kernel)
     int n_aux;
+    const int* moff_global;  // [active member][state_off, ctrl_off, row_off]
+    int moff_smem;           // copy them to shared memory at kernel start (set by the launcher)
+    int sm_count;
+    long long* timing;       // optional per-stage cycle counters (debug)
 };
 
 struct QckReduce {  // fixed-order reduction of shared Hessian positions

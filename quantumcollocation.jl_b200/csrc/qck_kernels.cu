@@ -19,6 +19,7 @@
 //  * Hessian entries that several integrators contribute to (shared controls) go to a partial buffer that a
 //    second kernel reduces in fixed integrator order (bitwise run-to-run reproducible, no atomics).
 #include <cstdio>
+#include <cstdlib>
 
 #include "qck_internal.h"
 
@@ -162,17 +163,17 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
         const int nrep = sg.img_nrep >> 16, n = sg.n;
         const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
         if (!odd && !(n & 1)) {
-            const int hp = n >> 1;
+            // 16-byte path: the destination is walked linearly (nrep * n/2 pairs), the source index wraps every n/2 pairs
+            const int hp = n >> 1, total = hp * nrep, step = 32 % hp;
             const double2* s2 = reinterpret_cast<const double2*>(src);
-            double2* d2 = reinterpret_cast<double2*>(dst);
-            if (nrep == 1) {
-                for (int k = lane; k < hp; k += 32) d2[k] = s2[k];
-            } else {
-                for (int k = lane; k < hp; k += 32) {
-                    const double2 v = s2[k];
-                    double2* d = d2 + k;
-                    for (int r = 0; r < nrep; ++r) d[(size_t)r * hp] = v;
-                }
+            double2* d2 = reinterpret_cast<double2*>(dst) + lane;
+            int k = lane % hp;
+#pragma unroll 2
+            for (int idx = lane; idx < total; idx += 32) {
+                *d2 = s2[k];
+                d2 += 32;
+                k += step;
+                if (k >= hp) k -= hp;
             }
         } else if (nrep == 1) {
             // misaligned and/or odd length: scalar head / tail, 16-byte body
@@ -186,10 +187,12 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
             }
             for (int k = lane; k < pairs; k += 32) d2[k] = make_double2(sh[2 * k], sh[2 * k + 1]);
         } else {
-            for (int k = lane; k < n; k += 32) {
-                const double v = src[k];
-                double* d = dst + k;
-                for (int r = 0; r < nrep; ++r) d[(size_t)r * n] = v;
+            const int total = n * nrep, step = 32 % n;
+            int k = lane % n;
+            for (int idx = lane; idx < total; idx += 32) {
+                dst[idx] = src[k];
+                k += step;
+                if (k >= n) k -= n;
             }
         }
     }
@@ -214,6 +217,14 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
 // Shared memory per CTA: [matrices | image | per-member segments + constants (x2 if several members) | input staging | aux].
 // The inputs (and tables, when the member changes) of the NEXT work item are prefetched with cp.async during compute.
 // ------------------------------------------------------------------------------------------------------------
+// optional per-stage cycle accounting (QCK_DEBUG_TIMING=1): thread 0 of every CTA accumulates clock64() deltas
+#define QCK_TICK(k)                                                                  \
+    if (p.timing && tid == 0) {                                                      \
+        long long now_ = clock64();                                                  \
+        atomicAdd((unsigned long long*)p.timing + (k), (unsigned long long)(now_ - tick_)); \
+        tick_ = now_;                                                                \
+    }
+
 template <int TC, int CN>
 __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade4_kernel(const QckLaunch p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -237,33 +248,40 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
     double* stage = reinterpret_cast<double*>(smem_raw + c.sm_stage);  // [z_t state | z_t+1 state | mu | a | h]
     QckAux* auxs = reinterpret_cast<QckAux*>(smem_raw + c.sm_bytes);
     double* auxv = reinterpret_cast<double*>(smem_raw + c.sm_bytes + p.n_aux * (int)sizeof(QckAux));
+    const int nact = p.member_end - p.member_begin;
+    // per-member offsets (state, drive, row) of the active members: in shared memory when they fit, else global
+    const int* moff = p.moff_smem ? reinterpret_cast<const int*>(auxv + 3 * p.n_aux) : p.moff_global;
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;  // 16-byte records of the per-member write-out table
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nwarps_ = nthreads >> 5;
     const int elln = c.ell_stride, kkc = c.kk_cap;
     const int msa = NP * NP, mss = NP * ncp;  // complex elements per matrix
 #define MA(i) (SA + (i) * msa)
 #define MS(i) (SS + (i) * mss)
 #define SEGBUF(b) reinterpret_cast<QckSeg*>(smem_raw + c.sm_seg + (b) * c.seg_bytes)
 #define CONV(b) reinterpret_cast<double2*>(smem_raw + c.sm_con + (b) * c.con_bytes)
-#define CONI(b) reinterpret_cast<int*>(smem_raw + c.sm_con + (b) * c.con_bytes + (elln + kkc) * 16)
+#define CONI(b) reinterpret_cast<int*>(smem_raw + c.sm_con + (b) * c.con_bytes + (N * N + elln + kkc) * 16)
 #define PUT(q, i, v) image[c.pl_base[q] + (i) * c.pl_stride[q]] = (v)
 
-    const int nact = p.member_end - p.member_begin;
     const long long n_items = p.n_knots * nact;
+    long long tick_ = clock64();
     const int tilesS = (NP / QCK_TILE) * (ncp / TC);
     const int tilesA = (NP / QCK_TILE) * (NP / QCK_TILE);
     const int tcols = ncp / TC, tcolsA = NP / QCK_TILE;
 
     // prefetch of one work item: inputs into `stage`, and the member's tables into buffer b if asked
-    auto prefetch = [&](long long item, int b, bool tables) {
-        const long long t = item / nact;
-        const int m = p.member_begin + (int)(item - t * nact);
+    auto prefetch = [&](long long t, int m, int b, bool tables) {
         const double* zt = p.Z + t * c.zdim;
-        const int soff = __ldg(c.state_off + m), coff = __ldg(c.ctrl_off + m), roff_n = __ldg(c.row_off + m);
-        for (int i = tid; i < dim; i += nthreads) {
-            cp_async8(stage + i, zt + soff + i);
-            cp_async8(stage + dim + i, zt + c.zdim + soff + i);
-            if (needH) cp_async8(stage + 2 * dim + i, p.mu + t * c.dyn + roff_n + i);
+        const int soff = moff[3 * (m - p.member_begin)], coff = moff[3 * (m - p.member_begin) + 1], roff_n = moff[3 * (m - p.member_begin) + 2];
+        {
+            const double* g0 = zt + soff + tid;
+            const double* g1 = g0 + c.zdim;
+            const double* g2 = p.mu + t * c.dyn + roff_n + tid;
+            double* d0 = stage + tid;
+            for (int i = tid; i < dim; i += nthreads, g0 += nthreads, g1 += nthreads, g2 += nthreads, d0 += nthreads) {
+                cp_async8(d0, g0);
+                cp_async8(d0 + dim, g1);
+                if (needH) cp_async8(d0 + 2 * dim, g2);
+            }
         }
         if (tid < nd) cp_async8(stage + 3 * dim + tid, zt + coff + tid);
         if (tid == nd && free_time) cp_async8(stage + 3 * dim + nd, zt + c.dt_off);
@@ -278,9 +296,9 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
         if (tables) {
             const QckSeg* gs = c.segs + (size_t)m * nrec;
             for (int i = tid; i < nrec; i += nthreads) cp_async16(SEGBUF(b) + i, gs + i);
-            const double2* gv = c.cmat + (size_t)m * c.cmat_stride + N * N * (1 + nd);
+            const double2* gv = c.cmat + (size_t)m * c.cmat_stride;  // [A0 | ell_val | kk_val]
             const int* gc = c.ell_col + (size_t)m * c.icon_stride;
-            for (int i = tid; i < elln + kkc; i += nthreads) cp_async16(CONV(b) + i, gv + i);
+            for (int i = tid; i < N * N + elln + kkc; i += nthreads) cp_async16(CONV(b) + i, gv + i);
             for (int i = tid; i < c.icon_stride; i += nthreads) cp_async4(CONI(b) + i, gc + i);
         }
         cp_async_commit();
@@ -288,25 +306,30 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
 
     for (int i = tid; i < c.scratch_doubles; i += nthreads) sm[i] = 0.0;
     for (int i = tid; i < p.n_aux; i += nthreads) auxs[i] = p.aux[i];
+    if (p.moff_smem)
+        for (int i = tid; i < 3 * nact; i += nthreads) const_cast<int*>(moff)[i] = p.moff_global[i];
     __syncthreads();
     if (tid == 0 && c.pl_base[QO_ONE] >= 0) image[c.pl_base[QO_ONE]] = 1.0;
     int buf = 0, buf_member = -1;
     if ((long long)blockIdx.x < n_items) {
         buf_member = p.member_begin + (int)(blockIdx.x % nact);
-        prefetch(blockIdx.x, buf, true);
+        prefetch(blockIdx.x / nact, buf_member, buf, true);
     }
 
+    // (t, mi) of the current item are advanced incrementally: a 64-bit division per item is not free
+    const int step_t = (int)(gridDim.x / nact), step_m = (int)(gridDim.x % nact);
+    long long t = blockIdx.x / nact;
+    int mi = (int)(blockIdx.x % nact);
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const long long t = item / nact;
-        const int mi = (int)(item - t * nact);
+        const int vwarp = warp, vtid = tid;
         const int m = p.member_begin + mi;
+        QCK_TICK(0);
         cp_async_wait_all();
         __syncthreads();  // staged inputs visible; previous item's write-out has finished reading the image
-        const double2* cm = c.cmat + (size_t)m * c.cmat_stride;
-        const double2* A0 = cm;
-        const double2* Adr = cm + N * N;
-        const double2* ellv = CONV(buf);
-        const double2* kkv = CONV(buf) + elln;
+        QCK_TICK(1);
+        const double2* A0 = CONV(buf);
+        const double2* ellv = CONV(buf) + N * N;
+        const double2* kkv = ellv + elln;
         const int* ellc = CONI(buf);
         const int* kkptr = CONI(buf) + elln;
         const int* kkrc = kkptr + npair + 1;
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
 
         // ---- stage 0: unpack the staged knot pair into D, S, M; build A = -i H(a) -----------------------------
         {
-            for (int idx = tid; idx < dim; idx += nthreads) {
+            for (int idx = tid; idx < dim; idx += nthreads) {  // the last warp joins once A is built
                 int cc = idx / n2, q = idx - cc * n2;
                 int im = q >= N, r = q - im * N;
                 double u0 = stage[idx], u1 = stage[dim + idx];
@@ -326,38 +349,52 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
                 reinterpret_cast<double*>(MS(QS_S))[o] = u1 + u0;
                 if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = stage[2 * dim + idx];
             }
-            for (int e = nthreads - 1 - tid; e < N * N; e += nthreads) {
-                int r = e % N, k = e / N;
-                double2 v = __ldg(A0 + e);
+            if (warp == nwarps_ - 1) {
+                // A = A0 + sum_j a_j A_j on the last warp: dense copy of the drift, then one sparse update per drive
+                // (entries of one drive never collide; zero-padded entries are skipped)
+                for (int e = lane; e < N * N; e += 32) MA(QA_A)[(e % N) + NP * (e / N)] = A0[e];
+                __syncwarp();
                 for (int j = 0; j < nd; ++j) {
-                    double aj = stage[3 * dim + j];
-                    double2 d = __ldg(Adr + j * N * N + e);
-                    v.x = fma(aj, d.x, v.x);
-                    v.y = fma(aj, d.y, v.y);
+                    const double aj = stage[3 * dim + j];
+                    for (int e = lane; e < N * W; e += 32) {
+                        const double2 v = ellv[(j * 2) * N * W + e];
+                        if (v.x != 0.0 || v.y != 0.0) {
+                            double2* ap = MA(QA_A) + (e / W) + NP * ellc[(j * 2) * N * W + e];
+                            double2 a = *ap;
+                            a.x = fma(aj, v.x, a.x);
+                            a.y = fma(aj, v.y, a.y);
+                            *ap = a;
+                        }
+                    }
+                    __syncwarp();
                 }
-                MA(QA_A)[r + NP * k] = v;
             }
         }
         __syncthreads();
+        QCK_TICK(2);
         // staging is free again: fetch the next item's inputs (and tables, if its member differs) behind the compute
         int next_buf = buf, next_member = buf_member;
         {
             const long long nitem = item + gridDim.x;
             if (nitem < n_items) {
-                const int nm = p.member_begin + (int)(nitem % nact);
+                int nmi = mi + step_m;
+                long long nt = t + step_t;
+                if (nmi >= nact) { nmi -= nact; ++nt; }
+                const int nm = p.member_begin + nmi;
                 const bool tables = nm != buf_member;
                 if (tables) { next_buf = buf ^ 1; next_member = nm; }  // several active members => two table buffers
-                prefetch(nitem, next_buf, tables);
+                prefetch(nt, nm, next_buf, tables);
             }
         }
 
+        QCK_TICK(3);
         // ---- stage 1: A2 = A A (+ F, B blocks), AS = A S, AhM = A^H M, G = D M^H, G2 = S M^H;  C_j = A_j A + A A_j ----
         {
             const int nG = needH ? (free_time ? 2 : 1) : 0;
             const int nA = (1 + nG) * tilesA;
             const int nS = (needH && free_time ? 2 : 1) * tilesS;
             const int nDense = nA + nS;
-            for (int w = tid; w < nDense; w += nthreads) {
+            for (int w = vtid; w < nDense; w += nthreads) {
                 if (w < nA) {
                     const int pi = w / tilesA, tl = w - pi * tilesA;
                     const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
@@ -403,7 +440,7 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
                 int first = ((nDense + 31) >> 5) << 5;
                 if (first >= nthreads) first = 0;
                 const int nsp = nd * N * N, stride = nthreads - first;
-                for (int w = tid - first; w >= 0 && w < nsp; w += stride) {
+                for (int w = vtid - first; w >= 0 && w < nsp; w += stride) {
                     const int j = w / (N * N), e = w - j * N * N;
                     const int r = e % N, cc = e / N;
                     const int o0 = ((j * 2) * N + r) * W, o1 = ((j * 2 + 1) * N + cc) * W;
@@ -421,13 +458,14 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
             }
         }
         __syncthreads();
+        QCK_TICK(4);
 
         // ---- stage 2: A2 D, (A2)^H M, C_j D, C_j^H M with fused epilogues into the image;  scalar traces ------------
         {
             const bool hdt = needH && free_time;  // timestep Hessian blocks exist
             const int nP = 1 + (needT ? nd : 0) + (hdt ? 1 : 0) + (needH ? nd : 0);
             const int nDense = nP * tilesS;
-            for (int w = tid; w < nDense; w += nthreads) {
+            for (int w = vtid; w < nDense; w += nthreads) {
                 const int pi = w / tilesS, tl = w - pi * tilesS;
                 const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
                 // product list: [A2 D -> R, TH] [C_j D -> TA_j]*nd [A2^H M -> KH0, KH1] [C_j^H M -> KA0_j, KA1_j]*nd
@@ -506,8 +544,8 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
                 if (first >= nthreads) first = 0;
                 const int fw = first >> 5, nfw = (nthreads >> 5) - fw;
                 const int n4 = free_time ? 1 + nd : 0, nv = 4 * n4 + npair;
-                if (warp >= fw)
-                    for (int vb = (warp - fw) * 32; vb < nv; vb += nfw * 32) {
+                if (vwarp >= fw)
+                    for (int vb = (vwarp - fw) * 32; vb < nv; vb += nfw * 32) {
                         const int v = vb + lane;
                         double val = 0.0;
                         int q = -1;
@@ -551,12 +589,17 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
             }
         }
         __syncthreads();
+        QCK_TICK(5);
 
         // ---- stage 3: write-out: contiguous copies image -> value arrays ---------------------------------------------
-        write_units(image, segs, seghdr[warp], seghdr[warp + 1], p, t, lane);
+        write_units(image, segs, seghdr[vwarp], seghdr[vwarp + 1], p, t, lane);
         if (mi == 0 && p.n_aux) do_aux_staged(p, auxs, auxv, h, t, tid, nthreads);
+        QCK_TICK(6);
         buf = next_buf;
         buf_member = next_member;
+        mi += step_m;
+        t += step_t;
+        if (mi >= nact) { mi -= nact; ++t; }
     }
     cp_async_wait_all();
 #undef MA
@@ -604,7 +647,7 @@ void qck_smem_finalize(QckClassDev& c) {
     c.sm_seg = al(c.scratch_doubles * 8);
     c.seg_bytes = al((QCK_SEG_HDR / 4 + c.nseg) * (int)sizeof(QckSeg));
     c.sm_con = c.sm_seg + c.n_tbuf * c.seg_bytes;
-    c.con_bytes = al((c.ell_stride + c.kk_cap) * 16 + c.icon_stride * 4);
+    c.con_bytes = al((c.N * c.N + c.ell_stride + c.kk_cap) * 16 + c.icon_stride * 4);
     c.sm_stage = c.sm_con + c.n_tbuf * c.con_bytes;
     c.sm_bytes = al(c.sm_stage + (3 * dim + c.nd + 1) * 8);
 }
@@ -648,7 +691,10 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = pade4_for<QCK_TILE>(c.N);
     else if (c.kind == QCK_KET_PADE && c.order == 4) kern = pade4_for<1>(c.N);
     else return (int)cudaErrorNotSupported;
-    size_t smem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double));
+    const int nact = L.member_end - L.member_begin;
+    L.moff_smem = nact <= 1024 ? 1 : 0;
+    L.sm_count = sm_count;
+    size_t smem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double)) + (L.moff_smem ? (size_t)nact * 12 + 16 : 0);
     int threads = c.threads;
     (void)tc;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -659,7 +705,23 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
     long long grid = (long long)sm_count * per_sm;
     if (grid > n_items) grid = n_items;
+    static const bool dbg = getenv("QCK_DEBUG") != nullptr;
+    static const bool tim = getenv("QCK_DEBUG_TIMING") != nullptr;
+    static long long* d_tim = nullptr;
+    if (tim) {
+        if (!d_tim) cudaMalloc(&d_tim, 8 * sizeof(long long));
+        cudaMemsetAsync(d_tim, 0, 8 * sizeof(long long), stream);
+        L.timing = d_tim;
+    }
+    if (dbg) fprintf(stderr, "[qcknot] N=%d nd=%d threads=%d smem=%zu B (image %d doubles) CTAs/SM=%d grid=%lld units=%d\n", c.N, c.nd, threads, smem, c.img_doubles, per_sm, grid, c.nseg);
     kern<<<(unsigned)grid, threads, smem, stream>>>(L);
+    if (tim) {
+        long long h[8];
+        cudaMemcpyAsync(h, d_tim, sizeof h, cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        double per = 1.0 / (double)n_items;
+        fprintf(stderr, "[qcknot timing] cycles/item (thread 0): loop-top %.0f | wait+bar %.0f | stage0 %.0f | prefetch-issue %.0f | stage1 %.0f | stage2 %.0f | write-out %.0f | mask=%u\n", h[0] * per, h[1] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per, L.mask);
+    }
     if (launches) ++*launches;
     return (int)cudaGetLastError();
 }
