@@ -637,7 +637,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
             I.dim = 2 * I.N * I.nc;
             if (I.state_len != I.dim) { fail(h, QCK_EINVAL, "integrator %d: state_len %d != %d", q, I.state_len, I.dim); return bail(QCK_EINVAL); }
             if (I.pade() && I.order != 4) { fail(h, QCK_EINVAL, "integrator %d: Pade order %d not supported by this build (4 only)", q, I.order); return bail(QCK_EINVAL); }
-            if (!I.pade()) { fail(h, QCK_EINVAL, "integrator %d: exponential integrators not supported by this build yet", q); return bail(QCK_EINVAL); }
+            if (!I.pade() && h->eval_hessian) { fail(h, QCK_EINVAL, "integrator %d: the exponential integrators have no Hessian in this build (as in the reference); create the dynamics with eval_hessian=false", q); return bail(QCK_EINVAL); }
             if (I.nd > 0 && !s.H_drives) { fail(h, QCK_EINVAL, "integrator %d: H_drives is NULL", q); return bail(QCK_EINVAL); }
             if (I.ctrl_off < 0 || I.ctrl_off + I.nd > h->zdim) { fail(h, QCK_EINVAL, "integrator %d: drive component out of range", q); return bail(QCK_EINVAL); }
             size_t nn = (size_t)I.N * I.N;

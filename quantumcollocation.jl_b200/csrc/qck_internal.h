@@ -9,6 +9,7 @@
 #define QCK_TILE 3          // register tile edge of the small complex products (3x3 complex per thread)
 #define QCK_MAX_DRIVES 6
 #define QCK_MAX_PADE_M 5    // Pade order <= 10
+enum { QK_PADE4 = 0, QK_EXP = 1 };  // kernel families
 
 // ---- shared-memory scratch of the quantum kernels -----------------------------------------------------------------
 // "A-type" matrices are NP x NP complex, "state-type" are NP x ncp complex (ncp = NP for unitaries, 1 for kets),

@@ -38,13 +38,15 @@ __device__ __forceinline__ void cfma(double2& c, double2 a, double2 b) {
 // acc[i][j] = sum_k opA(A)[r0+i, k] * opB(B)[k, c0+j],  k < K, 3 x TC complex register tile.
 // Operands are column-major with leading dimension ld.  opX = conj-transpose when tX is set, expressed through
 // runtime strides + a sign on the imaginary part so that every product of a stage runs the same instruction stream.
-template <int TC>
+template <int TC, bool ZERO = true>
 __device__ __forceinline__ void tile_mm(const double2* __restrict__ A, bool tA, const double2* __restrict__ B, bool tB,
                                         int K, int ld, int r0, int c0, double2 (&acc)[QCK_TILE][TC]) {
+    if (ZERO) {
 #pragma unroll
-    for (int i = 0; i < QCK_TILE; ++i)
+        for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
-        for (int j = 0; j < TC; ++j) acc[i][j] = make_double2(0.0, 0.0);
+            for (int j = 0; j < TC; ++j) acc[i][j] = make_double2(0.0, 0.0);
+    }
     const int ar = tA ? ld : 1, ak = tA ? 1 : ld;  // A[(r0+i)*ar + k*ak]
     const int bc = tB ? 1 : ld, bk = tB ? ld : 1;  // B[(c0+j)*bc + k*bk]
     const double sa = tA ? -1.0 : 1.0, sb = tB ? -1.0 : 1.0;  // conjugation = sign of the imaginary part
@@ -225,8 +227,8 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
         tick_ = now_;                                                                \
     }
 
-template <int TC, int CN>
-__global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade4_kernel(const QckLaunch p) {
+template <int KIND, int TC, int CN>
+__global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quantum_kernel(const QckLaunch p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const QckClassDev& c = p.c;
@@ -345,8 +347,8 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
                 int im = q >= N, r = q - im * N;
                 double u0 = stage[idx], u1 = stage[dim + idx];
                 int o = 2 * (r + NP * cc) + im;
-                reinterpret_cast<double*>(MS(QS_D))[o] = u1 - u0;
-                reinterpret_cast<double*>(MS(QS_S))[o] = u1 + u0;
+                reinterpret_cast<double*>(MS(QS_D))[o] = KIND == QK_EXP ? u0 : u1 - u0;  // exp kernel keeps U0, U1 themselves
+                reinterpret_cast<double*>(MS(QS_S))[o] = KIND == QK_EXP ? u1 : u1 + u0;
                 if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = stage[2 * dim + idx];
             }
             if (warp == nwarps_ - 1) {
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
         }
 
         QCK_TICK(3);
+        if constexpr (KIND == QK_PADE4) {
         // ---- stage 1: A2 = A A (+ F, B blocks), AS = A S, AhM = A^H M, G = D M^H, G2 = S M^H;  C_j = A_j A + A A_j ----
         {
             const int nG = needH ? (free_time ? 2 : 1) : 0;
@@ -589,6 +592,160 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_pade
             }
         }
         __syncthreads();
+        } else {
+        // ============================ exponential integrators =============================================================
+        // residual U1 - exp(h A) U0.  exp and its Frechet derivatives d/da_j by scaling and squaring of a degree-8 Taylor
+        // polynomial: Y = h A / 2^s with ||Y||_1 <= 1/16 (truncation: exp 4e-17, first derivatives 6e-15 relative),
+        //   Horner:    P <- I + (Y/m) P,        L_j <- (Y_j P + Y L_j)/m        m = 8 .. 1,  Y_j = h A_j / 2^s
+        //   squaring:  E <- E E,                L_j <- E L_j + L_j E            s times
+        // Outputs: -iso(E) block, identity block, d/da_j = -L_j U0, d/dh = -A E U0.
+        constexpr int TK = 8;
+        const int nthr_tiles = (1 + nd) * tilesA;
+#define XE(b) MA(1 + (b))
+#define XL(b, j) MA(3 + (b) * nd + (j))
+        // scaling parameter from the 1-norm (|re| + |im| per entry bounds the modulus)
+        if (tid < N) {
+            double cs = 0.0;
+            for (int r = 0; r < N; ++r) { const double2 a = MA(QA_A)[r + NP * tid]; cs += fabs(a.x) + fabs(a.y); }
+            image[tid] = cs;
+        }
+        __syncthreads();
+        double nrm = 0.0;
+        for (int cc = 0; cc < N; ++cc) nrm = fmax(nrm, image[cc]);
+        nrm *= fabs(h);
+        int sq = 0;
+        while (nrm > 0.0625 && sq < 40) { nrm *= 0.5; ++sq; }
+        const double y = ldexp(h, -sq);
+        int cur = 0;
+        {   // Horner start (m = TK): P = I + (Y/TK), L_j = Y_j/TK
+            const double c0 = y / TK;
+            for (int e = tid; e < N * N; e += nthreads) {
+                const int r = e % N, cc = e / N;
+                const double2 a = MA(QA_A)[r + NP * cc];
+                XE(0)[r + NP * cc] = make_double2((r == cc ? 1.0 : 0.0) + c0 * a.x, c0 * a.y);
+                for (int j = 0; j < nd; ++j) {
+                    const int o = ((j * 2) * N + r) * W;
+                    double2 v = make_double2(0.0, 0.0);
+                    for (int u = 0; u < W; ++u)
+                        if (ellc[o + u] == cc) { v.x += ellv[o + u].x; v.y += ellv[o + u].y; }
+                    XL(0, j)[r + NP * cc] = make_double2(c0 * v.x, c0 * v.y);
+                }
+            }
+        }
+        __syncthreads();
+        for (int mth = TK - 1; mth >= 1; --mth) {
+            const double cm = y / mth;
+            for (int w = tid; w < nthr_tiles; w += nthreads) {
+                const int pi = w / tilesA, tl = w - pi * tilesA;
+                const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
+                double2 acc[QCK_TILE][QCK_TILE];
+                tile_mm<QCK_TILE>(MA(QA_A), false, pi == 0 ? XE(cur) : XL(cur, pi - 1), false, N, NP, r0, c0, acc);
+                double2* Cop = pi == 0 ? XE(cur ^ 1) : XL(cur ^ 1, pi - 1);
+                const int eo = ((pi - 1) * 2) * N * W;
+#pragma unroll
+                for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < QCK_TILE; ++jj) {
+                        const int r = r0 + i, cc = c0 + jj;
+                        double2 v = acc[i][jj];
+                        if (pi == 0) {
+                            v = make_double2((r == cc ? 1.0 : 0.0) + cm * v.x, cm * v.y);
+                        } else {
+                            if (r < N && cc < N)
+                                for (int u = 0; u < W; ++u) cfma(v, ellv[eo + r * W + u], XE(cur)[ellc[eo + r * W + u] + NP * cc]);
+                            v = make_double2(cm * v.x, cm * v.y);
+                        }
+                        if (r < N && cc < N) Cop[r + NP * cc] = v;
+                    }
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        for (int k = 0; k < sq; ++k) {
+            for (int w = tid; w < nthr_tiles; w += nthreads) {
+                const int pi = w / tilesA, tl = w - pi * tilesA;
+                const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
+                double2 acc[QCK_TILE][QCK_TILE];
+                if (pi == 0) {
+                    tile_mm<QCK_TILE>(XE(cur), false, XE(cur), false, N, NP, r0, c0, acc);
+                } else {
+                    tile_mm<QCK_TILE>(XE(cur), false, XL(cur, pi - 1), false, N, NP, r0, c0, acc);
+                    tile_mm<QCK_TILE, false>(XL(cur, pi - 1), false, XE(cur), false, N, NP, r0, c0, acc);
+                }
+                double2* Cop = pi == 0 ? XE(cur ^ 1) : XL(cur ^ 1, pi - 1);
+#pragma unroll
+                for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < QCK_TILE; ++jj)
+                        if (r0 + i < N && c0 + jj < N) Cop[r0 + i + NP * (c0 + jj)] = acc[i][jj];
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        QCK_TICK(4);
+        // ---- outputs: E U0 (-> residual), L_j U0 (-> d/da_j), -iso(E) block;  then A (E U0) (-> d/dh) --------------------
+        {
+            const int nP = 1 + (needJ ? nd : 0);
+            const int nDense = nP * tilesS;
+            for (int w = tid; w < nDense; w += nthreads) {
+                const int pi = w / tilesS, tl = w - pi * tilesS;
+                const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
+                double2 acc[QCK_TILE][TC];
+                tile_mm<TC>(pi == 0 ? XE(cur) : XL(cur, pi - 1), false, MS(QS_D), false, N, NP, r0, c0, acc);
+                const int q1 = pi == 0 ? QO_R : QO_TA + (pi - 1);
+                const int b1 = c.pl_base[q1], s1 = c.pl_stride[q1];
+#pragma unroll
+                for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < TC; ++jj) {
+                        const int r = r0 + i, cc = c0 + jj;
+                        if (r < N && cc < nc) {
+                            double2 v = acc[i][jj];
+                            if (pi == 0) {
+                                MS(QS_AS)[r + NP * cc] = v;  // E U0, operand of the d/dh product
+                                const double2 u1 = MS(QS_S)[r + NP * cc];
+                                v = make_double2(v.x - u1.x, v.y - u1.y);
+                            }
+                            const int ire = cc * n2 + r;
+                            if (b1 >= 0) { image[b1 + ire * s1] = -v.x; image[b1 + (ire + N) * s1] = -v.y; }
+                        }
+                    }
+            }
+            if (needJ) {
+                int first = ((nDense + 31) >> 5) << 5;
+                if (first >= nthreads) first = 0;
+                for (int e = tid - first; e >= 0 && e < N * N; e += nthreads - first) {
+                    const int r = e % N, cc = e / N;
+                    const double2 v = XE(cur)[r + NP * cc];
+                    const int k00 = r + n2 * cc, k01 = r + n2 * (cc + N);
+                    PUT(QO_ISOF, k00, -v.x); PUT(QO_ISOF, k00 + N, -v.y); PUT(QO_ISOF, k01, v.y); PUT(QO_ISOF, k01 + N, -v.x);
+                }
+            }
+        }
+        __syncthreads();
+        if (needJ && free_time) {
+            const int b1 = c.pl_base[QO_TH], s1 = c.pl_stride[QO_TH];
+            for (int w = tid; w < tilesS; w += nthreads) {
+                const int r0 = (w / tcols) * QCK_TILE, c0 = (w - (w / tcols) * tcols) * TC;
+                double2 acc[QCK_TILE][TC];
+                tile_mm<TC>(MA(QA_A), false, MS(QS_AS), false, N, NP, r0, c0, acc);
+#pragma unroll
+                for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < TC; ++jj) {
+                        const int r = r0 + i, cc = c0 + jj;
+                        if (r < N && cc < nc && b1 >= 0) {
+                            const int ire = cc * n2 + r;
+                            image[b1 + ire * s1] = -acc[i][jj].x;
+                            image[b1 + (ire + N) * s1] = -acc[i][jj].y;
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+#undef XE
+#undef XL
+        }
         QCK_TICK(5);
 
         // ---- stage 3: write-out: contiguous copies image -> value arrays ---------------------------------------------
@@ -633,7 +790,8 @@ void qck_scratch_layout(QckClassDev& c) {
     c.msa = 2 * c.NP * c.NP;
     c.mss = 2 * c.NP * c.ncp;
     c.off_A = 0;
-    c.off_S = c.off_A + (QA_C + c.nd) * c.msa;
+    const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
+    c.off_S = c.off_A + (is_exp ? 3 + 2 * c.nd : QA_C + c.nd) * c.msa;
     c.off_img = c.off_S + QS_COUNT * c.mss;
 }
 
@@ -655,8 +813,9 @@ void qck_smem_finalize(QckClassDev& c) {
 int qck_pick_threads(const QckClassDev& c) {
     const int tc = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP) ? QCK_TILE : 1;
     int tilesS = (c.NP / QCK_TILE) * (c.ncp / tc);
-    int items = (2 + 2 * c.nd) * tilesS;
-    int th = ((items + 31) / 32) * 32 + 32;  // one extra warp for the sparse products / scalar traces
+    const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
+    int items = is_exp ? (1 + c.nd) * (c.NP / QCK_TILE) * (c.NP / QCK_TILE) : (2 + 2 * c.nd) * tilesS;
+    int th = ((items + 31) / 32) * 32 + (is_exp ? 0 : 32);  // Pade: one extra warp for the sparse products / scalar traces
     if (th < 64) th = 64;
     if (th > 256) th = 256;
     if (c.N != 2 && c.N != 3 && c.N != 4 && c.N != 5 && c.N != 6 && c.N != 8 && c.N != 9) return th;  // generic kernel: up to 256
@@ -664,17 +823,17 @@ int qck_pick_threads(const QckClassDev& c) {
 }
 
 typedef void (*qck_kernel_t)(const QckLaunch);
-template <int TC>
-static qck_kernel_t pade4_for(int N) {
+template <int KIND, int TC>
+static qck_kernel_t kernel_for(int N) {
     switch (N) {
-        case 2: return qck_pade4_kernel<TC, 2>;
-        case 3: return qck_pade4_kernel<TC, 3>;
-        case 4: return qck_pade4_kernel<TC, 4>;
-        case 5: return qck_pade4_kernel<TC, 5>;
-        case 6: return qck_pade4_kernel<TC, 6>;
-        case 8: return qck_pade4_kernel<TC, 8>;
-        case 9: return qck_pade4_kernel<TC, 9>;
-        default: return qck_pade4_kernel<TC, 0>;
+        case 2: return qck_quantum_kernel<KIND, TC, 2>;
+        case 3: return qck_quantum_kernel<KIND, TC, 3>;
+        case 4: return qck_quantum_kernel<KIND, TC, 4>;
+        case 5: return qck_quantum_kernel<KIND, TC, 5>;
+        case 6: return qck_quantum_kernel<KIND, TC, 6>;
+        case 8: return qck_quantum_kernel<KIND, TC, 8>;
+        case 9: return qck_quantum_kernel<KIND, TC, 9>;
+        default: return qck_quantum_kernel<KIND, TC, 0>;
     }
 }
 
@@ -688,8 +847,10 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     const bool unitary = c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP;
     qck_kernel_t kern = nullptr;
     int tc = unitary ? QCK_TILE : 1;
-    if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = pade4_for<QCK_TILE>(c.N);
-    else if (c.kind == QCK_KET_PADE && c.order == 4) kern = pade4_for<1>(c.N);
+    if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = kernel_for<QK_PADE4, QCK_TILE>(c.N);
+    else if (c.kind == QCK_KET_PADE && c.order == 4) kern = kernel_for<QK_PADE4, 1>(c.N);
+    else if (c.kind == QCK_UNITARY_EXP) kern = kernel_for<QK_EXP, QCK_TILE>(c.N);
+    else if (c.kind == QCK_KET_EXP) kern = kernel_for<QK_EXP, 1>(c.N);
     else return (int)cudaErrorNotSupported;
     const int nact = L.member_end - L.member_begin;
     L.moff_smem = nact <= 1024 ? 1 : 0;

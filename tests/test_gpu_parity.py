@@ -62,3 +62,18 @@ def test_random_dense_systems(levels, nd):
     sys_ = wl.random_hermitian_system(levels, nd, seed=levels * 10 + nd, scale=0.7)
     traj = wl.random_pulse_trajectory([sys_], 4, 0.3, seed=7)
     check([sys_], traj, wl.build_integrators([sys_], traj))
+
+
+@pytest.mark.parametrize("name,kw", [("hadamard", {"T": 9}), ("hadamard", {"T": 6, "free_time": False}), ("cz", {"T": 5}),
+                                     ("ket", {"T": 8}), ("sampling", {"T": 3, "n_systems": 4})])
+def test_exponential_integrators(name, kw):
+    """UnitaryExponentialIntegrator / QuantumStateExponentialIntegrator: residual + Jacobian (the reference has no
+    Hessian for them: SURVEY 8a3), against scipy expm / expm_frechet in the oracle."""
+    check(*wl.config(name, integrator="exponential", **kw), eval_hessian=False)
+
+
+def test_exponential_large_norm():
+    """Scaling-and-squaring with many squarings: ||h A|| ~ 30."""
+    sys_ = wl.random_hermitian_system(5, 2, seed=3, scale=4.0)
+    traj = wl.random_pulse_trajectory([sys_], 4, 1.5, seed=11)
+    check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=False)
