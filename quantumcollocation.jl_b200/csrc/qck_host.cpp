@@ -520,7 +520,8 @@ int build(qck_handle* h) {
         if (JE[k].cls < 0 && JE[k].member >= h->ib && JE[k].member < h->ie)
             h->aux.push_back({1, JE[k].aux_op, (int32_t)k, JE[k].aux_i0, 0, 0, JE[k].aux_c});
     for (size_t k = 0; k < HE.size(); ++k)
-        if (HE[k].cls < 0 && hdst[k] >= 0) h->aux.push_back({2, HE[k].aux_op, (int32_t)hdst[k], HE[k].aux_i0, 0, 0, 0.0});
+        if (HE[k].cls < 0 && hdst[k] >= 0 && HE[k].contrib >= h->ib && HE[k].contrib < h->ie)
+            h->aux.push_back({2, HE[k].aux_op, (int32_t)hdst[k], HE[k].aux_i0, 0, 0, 0.0});
     cudaError_t e;
     if ((e = upload(h->aux, &h->d_aux, h->allocs)) != cudaSuccess) return fail(h, QCK_ECUDA, "uploading aux entries: %s", cudaGetErrorString(e));
     h->red.n_shared = (int)h->sh_pos.size();

@@ -341,6 +341,9 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
         const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
 
         // ---- stage 0: unpack the staged knot pair into D, S, M; build A = -i H(a) -----------------------------
+        // (the derivative-integrator entries depend on the staged inputs only: written now, before the next prefetch
+        //  reuses the staging buffers)
+        if (mi == 0 && p.n_aux) do_aux_staged(p, auxs, auxv, h, t, tid, nthreads);
         {
             for (int idx = tid; idx < dim; idx += nthreads) {  // the last warp joins once A is built
                 int cc = idx / n2, q = idx - cc * n2;
@@ -750,7 +753,6 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
 
         // ---- stage 3: write-out: contiguous copies image -> value arrays ---------------------------------------------
         write_units(image, segs, seghdr[vwarp], seghdr[vwarp + 1], p, t, lane);
-        if (mi == 0 && p.n_aux) do_aux_staged(p, auxs, auxv, h, t, tid, nthreads);
         QCK_TICK(6);
         buf = next_buf;
         buf_member = next_member;
