@@ -507,6 +507,18 @@ int build(qck_handle* h) {
             (e = upload(cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(icon, &c.ell_col, C.allocs)) != cudaSuccess ||
             (e = upload(moff, &c.moff, C.allocs)) != cudaSuccess)
             return fail(h, QCK_ECUDA, "uploading class constants: %s", cudaGetErrorString(e));
+        c.tape = nullptr; c.tape_stride = 0; c.tape_levels = 0; c.max_ctas = 0;
+        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && !g_structure_only) {
+            // reverse-sweep tape of the exponential Hessian: 7 Horner steps x nd jets + 16 squaring levels x (1 + nd) matrices per CTA
+            c.tape_levels = 16;
+            c.tape_stride = (long long)(7 * nd + c.tape_levels * (1 + nd)) * N * N;
+            c.max_ctas = h->sm_count * 4;
+            void* tp = nullptr;
+            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas)) != cudaSuccess)
+                return fail(h, QCK_ENOMEM, "tape allocation failed: %s", cudaGetErrorString(e));
+            C.allocs.push_back(tp);
+            c.tape = static_cast<double2*>(tp);
+        }
     }
 
     // ---- aux entries (derivative integrators inside the active range) ---------------------------------------------------------------
@@ -638,7 +650,6 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
             I.dim = 2 * I.N * I.nc;
             if (I.state_len != I.dim) { fail(h, QCK_EINVAL, "integrator %d: state_len %d != %d", q, I.state_len, I.dim); return bail(QCK_EINVAL); }
             if (I.pade() && I.order != 4) { fail(h, QCK_EINVAL, "integrator %d: Pade order %d not supported by this build (4 only)", q, I.order); return bail(QCK_EINVAL); }
-            if (!I.pade() && h->eval_hessian) { fail(h, QCK_EINVAL, "integrator %d: the exponential integrators have no Hessian in this build (as in the reference); create the dynamics with eval_hessian=false", q); return bail(QCK_EINVAL); }
             if (I.nd > 0 && !s.H_drives) { fail(h, QCK_EINVAL, "integrator %d: H_drives is NULL", q); return bail(QCK_EINVAL); }
             if (I.ctrl_off < 0 || I.ctrl_off + I.nd > h->zdim) { fail(h, QCK_EINVAL, "integrator %d: drive component out of range", q); return bail(QCK_EINVAL); }
             size_t nn = (size_t)I.N * I.N;

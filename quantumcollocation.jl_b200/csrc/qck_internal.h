@@ -85,6 +85,11 @@ struct QckClassDev {
     int sm_seg, sm_con, sm_stage, sm_bytes;
     int seg_bytes, con_bytes;  // size of ONE buffer of the double-buffered per-member tables
     int n_tbuf;                // 1 when a single member is active (tables never change), else 2
+    // exponential integrators with a Hessian: per-CTA tape in global memory for the reverse sweep
+    double2* tape;
+    long long tape_stride;     // double2 elements per CTA
+    int tape_levels;           // squaring levels the tape can hold
+    int max_ctas;              // CTAs the tape was sized for (0 = no limit)
 };
 
 struct QckLaunch {

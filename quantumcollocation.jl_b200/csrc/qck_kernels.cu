@@ -636,8 +636,21 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
             }
         }
         __syncthreads();
+        // Hessian: the inputs of every Horner step / squaring level are kept on a per-CTA tape in global memory (L2)
+        double2* tapeH = c.tape ? c.tape + (size_t)blockIdx.x * c.tape_stride : nullptr;  // [(TK-1) steps][nd][N*N]
+        double2* tapeS = tapeH ? tapeH + (size_t)(TK - 1) * nd * N * N : nullptr;        // [levels][1 + nd][N*N]
+        const bool taping = needH && tapeH != nullptr;
+        if (taping && sq > c.tape_levels) sq = c.tape_levels;  // (never for ||h A||_1 <= 2^(tape_levels-4))
+        auto tape_put = [&](double2* dst, const double2* src) {
+            for (int e = tid; e < N * N; e += nthreads) dst[e] = src[(e % N) + NP * (e / N)];
+        };
+        auto tape_get = [&](double2* dst, const double2* src) {
+            for (int e = tid; e < N * N; e += nthreads) dst[(e % N) + NP * (e / N)] = src[e];
+        };
         for (int mth = TK - 1; mth >= 1; --mth) {
             const double cm = y / mth;
+            if (taping)
+                for (int j = 0; j < nd; ++j) tape_put(tapeH + (size_t)((TK - 1 - mth) * nd + j) * N * N, XL(cur, j));
             for (int w = tid; w < nthr_tiles; w += nthreads) {
                 const int pi = w / tilesA, tl = w - pi * tilesA;
                 const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
@@ -665,6 +678,10 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
             cur ^= 1;
         }
         for (int k = 0; k < sq; ++k) {
+            if (taping) {
+                tape_put(tapeS + (size_t)(k * (1 + nd)) * N * N, XE(cur));
+                for (int j = 0; j < nd; ++j) tape_put(tapeS + (size_t)(k * (1 + nd) + 1 + j) * N * N, XL(cur, j));
+            }
             for (int w = tid; w < nthr_tiles; w += nthreads) {
                 const int pi = w / tilesA, tl = w - pi * tilesA;
                 const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
@@ -686,17 +703,40 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
             cur ^= 1;
         }
         QCK_TICK(4);
-        // ---- outputs: E U0 (-> residual), L_j U0 (-> d/da_j), -iso(E) block;  then A (E U0) (-> d/dh) --------------------
+        // ---- outputs 1: E U0 (-> residual), L_j U0 (-> d/da_j), -iso(E) block; Hessian: -L_j^H M, A^H M, Gamma = U0 M^H ------
+        const bool hdt = needH && free_time;
         {
-            const int nP = 1 + (needJ ? nd : 0);
-            const int nDense = nP * tilesS;
+            const int nP = 1 + (needT ? nd : 0) + (needH ? nd : 0) + (hdt ? 1 : 0);
+            const int nS = nP * tilesS, nDense = nS + (needH ? tilesA : 0);
             for (int w = tid; w < nDense; w += nthreads) {
+                if (w >= nS) {  // Gamma = U0 M^H  (Re <M, K U0> = Re tr(K Gamma)) into the idle E buffer
+                    const int tl = w - nS;
+                    const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
+                    double2 acc[QCK_TILE][QCK_TILE];
+                    tile_mm<QCK_TILE>(MS(QS_D), false, MS(QS_M), true, nc, NP, r0, c0, acc);
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < QCK_TILE; ++jj) XE(cur ^ 1)[r0 + i + NP * (c0 + jj)] = acc[i][jj];
+                    continue;
+                }
                 const int pi = w / tilesS, tl = w - pi * tilesS;
                 const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
+                // product list: [E U0] [L_j U0]*nd (needT) [L_j^H M]*nd (needH) [A^H M] (hdt)
+                int kind = 0, j = -1, rest = pi - 1;  // kind 0: E U0, 1: L_j U0, 2: L_j^H M, 3: A^H M
+                if (pi > 0) {
+                    if (needT && rest < nd) { kind = 1; j = rest; }
+                    else {
+                        if (needT) rest -= nd;
+                        if (needH && rest < nd) { kind = 2; j = rest; }
+                        else kind = 3;
+                    }
+                }
+                const double2* Aop = kind == 0 ? XE(cur) : (kind == 3 ? MA(QA_A) : XL(cur, j));
                 double2 acc[QCK_TILE][TC];
-                tile_mm<TC>(pi == 0 ? XE(cur) : XL(cur, pi - 1), false, MS(QS_D), false, N, NP, r0, c0, acc);
-                const int q1 = pi == 0 ? QO_R : QO_TA + (pi - 1);
-                const int b1 = c.pl_base[q1], s1 = c.pl_stride[q1];
+                tile_mm<TC>(Aop, kind >= 2, kind >= 2 ? MS(QS_M) : MS(QS_D), false, N, NP, r0, c0, acc);
+                const int q1 = kind == 0 ? QO_R : (kind == 1 ? QO_TA + j : (kind == 2 ? QO_KA0 + j : -1));
+                const int b1 = q1 >= 0 ? c.pl_base[q1] : -1, s1 = q1 >= 0 ? c.pl_stride[q1] : 0;
 #pragma unroll
                 for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
@@ -704,7 +744,8 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
                         const int r = r0 + i, cc = c0 + jj;
                         if (r < N && cc < nc) {
                             double2 v = acc[i][jj];
-                            if (pi == 0) {
+                            if (kind == 3) { MS(QS_AHM)[r + NP * cc] = v; continue; }
+                            if (kind == 0) {
                                 MS(QS_AS)[r + NP * cc] = v;  // E U0, operand of the d/dh product
                                 const double2 u1 = MS(QS_S)[r + NP * cc];
                                 v = make_double2(v.x - u1.x, v.y - u1.y);
@@ -726,26 +767,162 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
             }
         }
         __syncthreads();
-        if (needJ && free_time) {
-            const int b1 = c.pl_base[QO_TH], s1 = c.pl_stride[QO_TH];
-            for (int w = tid; w < tilesS; w += nthreads) {
-                const int r0 = (w / tcols) * QCK_TILE, c0 = (w - (w / tcols) * tcols) * TC;
+        // ---- outputs 2: V = A (E U0) -> d/dh (V kept in an idle L buffer);  state_t x dt = -E^H (A^H M) ---------------------
+        double2* Vbuf = XL(cur ^ 1, 0);
+        if (free_time && needT) {
+            const int nP = 1 + (hdt ? 1 : 0);
+            for (int w = tid; w < nP * tilesS; w += nthreads) {
+                const int pi = w / tilesS, tl = w - pi * tilesS;
+                const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
                 double2 acc[QCK_TILE][TC];
-                tile_mm<TC>(MA(QA_A), false, MS(QS_AS), false, N, NP, r0, c0, acc);
+                tile_mm<TC>(pi == 0 ? MA(QA_A) : XE(cur), pi == 1, pi == 0 ? MS(QS_AS) : MS(QS_AHM), false, N, NP, r0, c0, acc);
+                const int q1 = pi == 0 ? QO_TH : QO_KH0;
+                const int b1 = c.pl_base[q1], s1 = c.pl_stride[q1];
 #pragma unroll
                 for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
                     for (int jj = 0; jj < TC; ++jj) {
                         const int r = r0 + i, cc = c0 + jj;
-                        if (r < N && cc < nc && b1 >= 0) {
+                        if (r < N && cc < nc) {
+                            if (pi == 0) Vbuf[r + NP * cc] = acc[i][jj];
                             const int ire = cc * n2 + r;
-                            image[b1 + ire * s1] = -acc[i][jj].x;
-                            image[b1 + (ire + N) * s1] = -acc[i][jj].y;
+                            if (b1 >= 0) { image[b1 + ire * s1] = -acc[i][jj].x; image[b1 + (ire + N) * s1] = -acc[i][jj].y; }
                         }
                     }
             }
         }
         __syncthreads();
+        if (needH) {
+            // ---- dt x dt = -Re <A^H M, V>,  a_j x dt = -Re <M, A_j (E U0)> - Re <A^H M, L_j U0>  (one warp per scalar) ----------
+            if (free_time)
+                for (int task = warp; task < 1 + nd; task += nwarps_) {
+                    double sacc = 0.0;
+                    const int j = task - 1;
+                    const int bt = j >= 0 ? c.pl_base[QO_TA + j] : 0, st = j >= 0 ? c.pl_stride[QO_TA + j] : 0;
+                    for (int e = lane; e < N * nc; e += 32) {
+                        const int r = e % N, cc = e / N, o = r + NP * cc;
+                        const double2 ahm = MS(QS_AHM)[o];
+                        if (j < 0) {
+                            const double2 v = Vbuf[o];
+                            sacc -= ahm.x * v.x + ahm.y * v.y;
+                        } else {
+                            const double2 aeu = ell_row(ellv + (j * 2) * N * W, ellc + (j * 2) * N * W, W, MS(QS_AS), NP, r, cc);
+                            const double2 mm = MS(QS_M)[o];
+                            const int ire = cc * n2 + r;
+                            const double lr = -image[bt + ire * st], li = -image[bt + (ire + N) * st];  // L_j U0
+                            sacc -= mm.x * aeu.x + mm.y * aeu.y + ahm.x * lr + ahm.y * li;
+                        }
+                    }
+                    sacc = warp_sum(sacc);
+                    if (lane == 0) {
+                        const int q = j < 0 ? QO_HHH : QO_HAH + j;
+                        if (c.pl_base[q] >= 0) image[c.pl_base[q]] = sacc;
+                    }
+                }
+            // ---- a_i x a_j = -Re tr(Gamma d2E/da_i da_j): reverse sweep over the tape ------------------------------------------
+            //   squaring level k (E_k = E_{k-1}^2):  += Re tr(Gamma_k (L^i L^j + L^j L^i)),  Gamma_{k-1} = Gamma_k E + E Gamma_k
+            //   Horner step (P' = I + Y P / m):       += (y/m) Re tr(Lam (A_i L^j + A_j L^i)),  Lam' = (y/m) Lam A
+            // with E = E_{k-1}, L = L_{k-1} (resp. the step's input jets) read back from the tape.
+            double hacc[QCK_MAX_DRIVES * (QCK_MAX_DRIVES + 1) / 2];
+#pragma unroll
+            for (int q = 0; q < QCK_MAX_DRIVES * (QCK_MAX_DRIVES + 1) / 2; ++q) hacc[q] = 0.0;
+            int gb = cur ^ 1;             // Gamma lives in XE(gb), the other E buffer receives the update
+            double2* XT = MA(3 + 2 * nd);  // E_{k-1} read back from the tape
+            auto pair_traces = [&](double wgt) {  // hacc[(i,j)] += wgt * Re(tr(Q^i L^j) + tr(Q^j L^i)),  Q in XL(1,.), L in XL(0,.)
+                for (int e = tid; e < N * N; e += nthreads) {
+                    const int a = e % N, b = e / N;
+                    int q = 0;
+                    for (int j = 0; j < nd; ++j) {
+                        const double2 lj = XL(0, j)[b + NP * a], qj = XL(1, j)[a + NP * b];
+                        for (int i = 0; i <= j; ++i, ++q) {
+                            const double2 li = XL(0, i)[b + NP * a], qi = XL(1, i)[a + NP * b];
+                            hacc[q] += wgt * (qi.x * lj.x - qi.y * lj.y + qj.x * li.x - qj.y * li.y);
+                        }
+                    }
+                }
+            };
+            if (taping) {
+                for (int k = sq - 1; k >= 0; --k) {
+                    __syncthreads();  // previous level's traces / products are done with the buffers
+                    tape_get(XT, tapeS + (size_t)(k * (1 + nd)) * N * N);
+                    for (int j = 0; j < nd; ++j) tape_get(XL(0, j), tapeS + (size_t)(k * (1 + nd) + 1 + j) * N * N);
+                    __syncthreads();
+                    for (int w = tid; w < nthr_tiles; w += nthreads) {
+                        const int pi = w / tilesA, tl = w - pi * tilesA;
+                        const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
+                        double2 acc[QCK_TILE][QCK_TILE];
+                        if (pi == 0) {
+                            tile_mm<QCK_TILE>(XE(gb), false, XT, false, N, NP, r0, c0, acc);
+                            tile_mm<QCK_TILE, false>(XT, false, XE(gb), false, N, NP, r0, c0, acc);
+                        } else {
+                            tile_mm<QCK_TILE>(XE(gb), false, XL(0, pi - 1), false, N, NP, r0, c0, acc);
+                        }
+                        double2* Cop = pi == 0 ? XE(gb ^ 1) : XL(1, pi - 1);
+#pragma unroll
+                        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                            for (int jj = 0; jj < QCK_TILE; ++jj)
+                                if (r0 + i < N && c0 + jj < N) Cop[r0 + i + NP * (c0 + jj)] = acc[i][jj];
+                    }
+                    __syncthreads();
+                    pair_traces(1.0);
+                    gb ^= 1;
+                }
+                for (int n = TK - 2; n >= 0; --n) {
+                    const double cm = y / (TK - 1 - n);
+                    __syncthreads();
+                    for (int j = 0; j < nd; ++j) tape_get(XL(0, j), tapeH + (size_t)(n * nd + j) * N * N);
+                    __syncthreads();
+                    // Q^i = Lam A_i (sparse, walks row b of A_i^H: A_i[k, b] = conj(A_i^H[b, k])), Lam' = cm Lam A (dense)
+                    for (int w = tid; w < tilesA; w += nthreads) {
+                        const int r0 = (w / tcolsA) * QCK_TILE, c0 = (w - (w / tcolsA) * tcolsA) * QCK_TILE;
+                        double2 acc[QCK_TILE][QCK_TILE];
+                        tile_mm<QCK_TILE>(XE(gb), false, MA(QA_A), false, N, NP, r0, c0, acc);
+#pragma unroll
+                        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                            for (int jj = 0; jj < QCK_TILE; ++jj)
+                                if (r0 + i < N && c0 + jj < N) XE(gb ^ 1)[r0 + i + NP * (c0 + jj)] = make_double2(cm * acc[i][jj].x, cm * acc[i][jj].y);
+                    }
+                    {
+                        int first = ((tilesA + 31) >> 5) << 5;
+                        if (first >= nthreads) first = 0;
+                        for (int w = tid - first; w >= 0 && w < nd * N * N; w += nthreads - first) {
+                            const int i = w / (N * N), e = w - i * N * N;
+                            const int a = e % N, b = e / N;
+                            const int o1 = ((i * 2 + 1) * N + b) * W;
+                            double2 v = make_double2(0.0, 0.0);
+                            for (int u = 0; u < W; ++u) {
+                                double2 ah = ellv[o1 + u];
+                                ah.y = -ah.y;
+                                cfma(v, XE(gb)[a + NP * ellc[o1 + u]], ah);
+                            }
+                            XL(1, i)[a + NP * b] = v;
+                        }
+                    }
+                    __syncthreads();
+                    pair_traces(cm);
+                    gb ^= 1;
+                }
+            }
+            // block reduction of the pair sums: shuffles inside the warps, then across warps through the V buffer
+            __syncthreads();
+            double* red = reinterpret_cast<double*>(XL(0, 0));
+            for (int q = 0; q < npair; ++q) {
+                const double v = warp_sum(hacc[q]);
+                if (lane == 0) red[q * nwarps_ + warp] = v;
+            }
+            __syncthreads();
+            if (tid < npair) {
+                double v = 0.0;
+                for (int w2 = 0; w2 < nwarps_; ++w2) v += red[tid * nwarps_ + w2];
+                int j = 0, rem = tid;
+                while (rem > j) { rem -= j + 1; ++j; }
+                const int qq = qo_haa(rem, j);
+                if (c.pl_base[qq] >= 0) image[c.pl_base[qq]] = -v;
+            }
+            __syncthreads();
+        }
 #undef XE
 #undef XL
         }
@@ -793,7 +970,7 @@ void qck_scratch_layout(QckClassDev& c) {
     c.mss = 2 * c.NP * c.ncp;
     c.off_A = 0;
     const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
-    c.off_S = c.off_A + (is_exp ? 3 + 2 * c.nd : QA_C + c.nd) * c.msa;
+    c.off_S = c.off_A + (is_exp ? 4 + 2 * c.nd : QA_C + c.nd) * c.msa;
     c.off_img = c.off_S + QS_COUNT * c.mss;
 }
 
@@ -867,6 +1044,7 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
     long long grid = (long long)sm_count * per_sm;
+    if (c.max_ctas > 0 && grid > c.max_ctas) grid = c.max_ctas;  // the Hessian tape was sized for this many CTAs
     if (grid > n_items) grid = n_items;
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
     static const bool tim = getenv("QCK_DEBUG_TIMING") != nullptr;

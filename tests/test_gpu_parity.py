@@ -72,8 +72,17 @@ def test_exponential_integrators(name, kw):
     check(*wl.config(name, integrator="exponential", **kw), eval_hessian=False)
 
 
+@pytest.mark.parametrize("name,kw", [("hadamard", {"T": 9}), ("hadamard", {"T": 6, "free_time": False}), ("cz", {"T": 4}),
+                                     ("ket", {"T": 8}), ("sampling", {"T": 3, "n_systems": 3})])
+def test_exponential_integrators_with_hessian(name, kw):
+    """Hessian of mu^T (U1 - exp(h A) U0): second Frechet derivatives by a reverse sweep over the scaling-and-squaring
+    tape; oracle = scipy expm / expm_frechet + block-triangular second derivative."""
+    check(*wl.config(name, integrator="exponential", **kw), eval_hessian=True)
+
+
 def test_exponential_large_norm():
     """Scaling-and-squaring with many squarings: ||h A|| ~ 30."""
     sys_ = wl.random_hermitian_system(5, 2, seed=3, scale=4.0)
     traj = wl.random_pulse_trajectory([sys_], 4, 1.5, seed=11)
     check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=False)
+    check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=True)

@@ -34,15 +34,14 @@ def _type1_problem(kind, free_time):
 def test_golden_fixture(kind, free_time):
     sys_, traj, integrators = _type1_problem(kind, free_time)
     tag = f"{kind}_{'free' if free_time else 'fixed'}"
-    D = qcknot.QuantumDynamics(integrators, traj, eval_hessian=(kind == "pade"))
+    D = qcknot.QuantumDynamics(integrators, traj)
     Z = traj.datavec
     assert np.array_equal(Z, GOLD[f"{tag}_Z"])
     assert np.array_equal(D.dF_structure, GOLD[f"{tag}_Js"])
     assert rel_err(D.F(Z), GOLD[f"{tag}_F"]) < TOL
     assert rel_err(D.dF(Z), GOLD[f"{tag}_J"]) < TOL
-    if kind == "pade":
-        assert np.array_equal(D.mu_d2F_structure, GOLD[f"{tag}_Hs"])
-        assert rel_err(D.mu_d2F(Z, GOLD[f"{tag}_mu"]), GOLD[f"{tag}_H"]) < TOL
+    assert np.array_equal(D.mu_d2F_structure, GOLD[f"{tag}_Hs"])
+    assert rel_err(D.mu_d2F(Z, GOLD[f"{tag}_mu"]), GOLD[f"{tag}_H"]) < TOL
 
 
 def test_full_size_properties_cz():
@@ -200,22 +199,23 @@ def test_edge_cases():
         qcknot.QuantumDynamics(wl.build_integrators([big], tb), tb)
 
 
-@pytest.mark.parametrize("name,T,integ", [("cz", 2500, "pade"), ("hadamard", 5000, "pade"), ("ket", 3000, "pade"), ("cz", 1300, "exponential")])
+@pytest.mark.parametrize("name,T,integ", [("cz", 2500, "pade"), ("hadamard", 5000, "pade"), ("ket", 3000, "pade"), ("cz", 1300, "exponential"),
+                                          ("hadamard", 4000, "exponential")])
 def test_every_block_when_ctas_loop_over_many_items(name, T, integ):
     """More work items than resident CTAs: the persistent loop + prefetch path.  Every block is compared with the C port
     of the oracle (Pade) or the numpy oracle on a strided sample (exponential)."""
     from oracle.c_port import CPort
     systems, traj, integrators = wl.config(name, T=T, integrator=integ)
-    hess = integ == "pade"
-    D = qcknot.QuantumDynamics(integrators, traj, eval_hessian=hess)
+    D = qcknot.QuantumDynamics(integrators, traj)
     Z, mu = traj.datavec, wl.random_multipliers(D.n_blocks * D.dyn)
     F, J, H = D.eval_all(Z, mu)
-    if hess:
+    if integ == "pade":
         Fo, Jo, Ho = CPort(oracle_dynamics(integrators, traj)).eval(Z, mu)
         assert rel_err(F, Fo) < TOL and rel_err(J, Jo) < TOL and rel_err(H, Ho) < TOL
     else:
         for t in range(0, D.n_blocks, 97):
             sub = qcknot.NamedTrajectory({n: traj[n][:, t:t + 2] for n in traj.names}, controls=("dda", "Δt"), timestep="Δt")
-            O = oracle_dynamics(wl.build_integrators(systems, sub, integrator=integ), sub, eval_hessian=False)
+            O = oracle_dynamics(wl.build_integrators(systems, sub, integrator=integ), sub)
             assert rel_err(F[t * D.dyn:(t + 1) * D.dyn], O.F(sub.datavec)) < TOL
             assert rel_err(J[t * D.nnzJ:(t + 1) * D.nnzJ], O.dF(sub.datavec)) < TOL
+            assert rel_err(H[t * D.nnzH:(t + 1) * D.nnzH], O.mu_d2F(sub.datavec, mu[t * D.dyn:(t + 1) * D.dyn])) < TOL

@@ -12,7 +12,7 @@ nsys = int(sys.argv[4]) if len(sys.argv) > 4 else None
 t0 = time.time()
 systems, traj, integrators = wl.config(name, T=T, integrator=integ, n_systems=nsys)
 print(f"workload built in {time.time()-t0:.1f}s")
-hess = integ == 'pade'
+hess = True
 D = qcknot.QuantumDynamics(integrators, traj, eval_hessian=hess)
 nb = D.n_blocks
 print(f"dyn={D.dyn} nnzJ={D.nnzJ} nnzH={D.nnzH} blocks={nb}")
