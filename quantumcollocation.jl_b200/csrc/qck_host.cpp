@@ -225,6 +225,7 @@ std::vector<QckSeg> balance_units(const std::vector<Run> (&runs)[3], int nwarps,
         for (size_t i : mine[w]) out.push_back(units[i].s);
     }
     for (int w = nwarps; w < QCK_SEG_HDR; ++w) hdr[w] = (int)out.size();
+    for (auto& sgm : out) sgm.arr |= (32 % std::max(sgm.n / 2, 1)) << 8;
     return out;
 }
 
@@ -410,7 +411,7 @@ int build(qck_handle* h) {
                 if (same && m2 > C.member_begin)
                     for (size_t u = 0; u < per_member[m2].size(); ++u) {
                         const QckSeg &a = per_member[m2][u], &b = per_member[C.member_begin][u];
-                        same = same && a.n == b.n && a.img_nrep == b.img_nrep && a.arr == b.arr;
+                        same = same && a.n == b.n && a.img_nrep == b.img_nrep && a.arr == b.arr;  // arr includes the wrap step
                     }
                 if (!same)
                     return fail(h, QCK_EINVAL, "integrators of one kind must see the same relative component order (state/control/timestep layout differs between members)");

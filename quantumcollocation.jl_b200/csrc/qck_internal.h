@@ -42,7 +42,7 @@ struct QckSeg {
     int dst;       // first position inside the knot block (Hessian: >= nnzH means partial column dst - nnzH)
     int n;
     int img_nrep;  // image offset (doubles, always even) | nrep << 16
-    int arr;       // 0 F, 1 J, 2 H
+    int arr;       // (0 F, 1 J, 2 H) | (32 mod max(n/2, 1)) << 8
 };
 #define QCK_SEG_HDR 16  // ints (warp w owns units [hdr[w], hdr[w+1]))
 

@@ -156,20 +156,23 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
                                             const QckLaunch& p, long long t, int lane) {
     for (int s = s0; s < s1; ++s) {
         const QckSeg sg = segs[s];
-        if (!((p.mask >> sg.arr) & 1u)) continue;
+        const int arr = sg.arr & 255;
+        if (!((p.mask >> arr) & 1u)) continue;
         double* dst;
-        if (sg.arr == 0) dst = p.F + t * p.c.dyn + sg.dst;
-        else if (sg.arr == 1) dst = p.J + t * p.nnzJ + sg.dst;
+        if (arr == 0) dst = p.F + t * p.c.dyn + sg.dst;
+        else if (arr == 1) dst = p.J + t * p.nnzJ + sg.dst;
         else dst = (long long)sg.dst < p.nnzH ? p.H + t * p.nnzH + sg.dst : p.partial + t * p.npart + (sg.dst - p.nnzH);
         const double* src = image + (sg.img_nrep & 0xffff);
         const int nrep = sg.img_nrep >> 16, n = sg.n;
         const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
         if (!odd && !(n & 1)) {
             // 16-byte path: the destination is walked linearly (nrep * n/2 pairs), the source index wraps every n/2 pairs
-            const int hp = n >> 1, total = hp * nrep, step = 32 % hp;
+            // (the wrap step 32 mod n/2 comes precomputed with the unit: no integer division here)
+            const int hp = n >> 1, total = hp * nrep, step = sg.arr >> 8;
             const double2* s2 = reinterpret_cast<const double2*>(src);
             double2* d2 = reinterpret_cast<double2*>(dst) + lane;
-            int k = lane % hp;
+            int k = lane;
+            while (k >= hp) k -= hp;
 #pragma unroll 2
             for (int idx = lane; idx < total; idx += 32) {
                 *d2 = s2[k];
@@ -189,7 +192,7 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
             }
             for (int k = lane; k < pairs; k += 32) d2[k] = make_double2(sh[2 * k], sh[2 * k + 1]);
         } else {
-            const int total = n * nrep, step = 32 % n;
+            const int total = n * nrep, step = 32 % n;  // rare path (odd period or misaligned repeated block)
             int k = lane % n;
             for (int idx = lane; idx < total; idx += 32) {
                 dst[idx] = src[k];
@@ -1046,6 +1049,9 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     long long grid = (long long)sm_count * per_sm;
     if (c.max_ctas > 0 && grid > c.max_ctas) grid = c.max_ctas;  // the Hessian tape was sized for this many CTAs
     if (grid > n_items) grid = n_items;
+    // several active members: a grid that is a multiple of their number keeps every CTA on ONE member (its tables are
+    // fetched once instead of once per item)
+    if (nact > 1 && grid >= nact) grid -= grid % nact;
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
     static const bool tim = getenv("QCK_DEBUG_TIMING") != nullptr;
     static long long* d_tim = nullptr;
