@@ -231,7 +231,8 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
     }
 
 template <int KIND, int TC, int CN>
-__global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quantum_kernel(const QckLaunch p) {
+__global__ void __launch_bounds__(CN == 0 ? 256 : (KIND == QK_EXP ? 160 : 128), CN == 0 ? 1 : (KIND == QK_EXP ? 3 : 4))
+qck_quantum_kernel(const QckLaunch p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const QckClassDev& c = p.c;
@@ -606,7 +607,11 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
         //   squaring:  E <- E E,                L_j <- E L_j + L_j E            s times
         // Outputs: -iso(E) block, identity block, d/da_j = -L_j U0, d/dh = -A E U0.
         constexpr int TK = 8;
-        const int nthr_tiles = (1 + nd) * tilesA;
+        // N x N products use 3 x 1 tiles here: the phases are strictly sequential (7 Horner steps + s squarings), so the
+        // latency of one phase matters more than shared-memory traffic -> three times as many, three times shorter tasks
+        constexpr int XC = 1;
+        const int tcolsX = NP / XC, tilesX = (NP / QCK_TILE) * tcolsX;
+        const int nthr_tiles = (1 + nd) * tilesX;
 #define XE(b) MA(1 + (b))
 #define XL(b, j) MA(3 + (b) * nd + (j))
         // scaling parameter from the 1-norm (|re| + |im| per entry bounds the modulus)
@@ -655,16 +660,16 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
             if (taping)
                 for (int j = 0; j < nd; ++j) tape_put(tapeH + (size_t)((TK - 1 - mth) * nd + j) * N * N, XL(cur, j));
             for (int w = tid; w < nthr_tiles; w += nthreads) {
-                const int pi = w / tilesA, tl = w - pi * tilesA;
-                const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
-                double2 acc[QCK_TILE][QCK_TILE];
-                tile_mm<QCK_TILE>(MA(QA_A), false, pi == 0 ? XE(cur) : XL(cur, pi - 1), false, N, NP, r0, c0, acc);
+                const int pi = w / tilesX, tl = w - pi * tilesX;
+                const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
+                double2 acc[QCK_TILE][XC];
+                tile_mm<XC>(MA(QA_A), false, pi == 0 ? XE(cur) : XL(cur, pi - 1), false, N, NP, r0, c0, acc);
                 double2* Cop = pi == 0 ? XE(cur ^ 1) : XL(cur ^ 1, pi - 1);
                 const int eo = ((pi - 1) * 2) * N * W;
 #pragma unroll
                 for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
-                    for (int jj = 0; jj < QCK_TILE; ++jj) {
+                    for (int jj = 0; jj < XC; ++jj) {
                         const int r = r0 + i, cc = c0 + jj;
                         double2 v = acc[i][jj];
                         if (pi == 0) {
@@ -686,20 +691,20 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
                 for (int j = 0; j < nd; ++j) tape_put(tapeS + (size_t)(k * (1 + nd) + 1 + j) * N * N, XL(cur, j));
             }
             for (int w = tid; w < nthr_tiles; w += nthreads) {
-                const int pi = w / tilesA, tl = w - pi * tilesA;
-                const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
-                double2 acc[QCK_TILE][QCK_TILE];
+                const int pi = w / tilesX, tl = w - pi * tilesX;
+                const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
+                double2 acc[QCK_TILE][XC];
                 if (pi == 0) {
-                    tile_mm<QCK_TILE>(XE(cur), false, XE(cur), false, N, NP, r0, c0, acc);
+                    tile_mm<XC>(XE(cur), false, XE(cur), false, N, NP, r0, c0, acc);
                 } else {
-                    tile_mm<QCK_TILE>(XE(cur), false, XL(cur, pi - 1), false, N, NP, r0, c0, acc);
-                    tile_mm<QCK_TILE, false>(XL(cur, pi - 1), false, XE(cur), false, N, NP, r0, c0, acc);
+                    tile_mm<XC>(XE(cur), false, XL(cur, pi - 1), false, N, NP, r0, c0, acc);
+                    tile_mm<XC, false>(XL(cur, pi - 1), false, XE(cur), false, N, NP, r0, c0, acc);
                 }
                 double2* Cop = pi == 0 ? XE(cur ^ 1) : XL(cur ^ 1, pi - 1);
 #pragma unroll
                 for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
-                    for (int jj = 0; jj < QCK_TILE; ++jj)
+                    for (int jj = 0; jj < XC; ++jj)
                         if (r0 + i < N && c0 + jj < N) Cop[r0 + i + NP * (c0 + jj)] = acc[i][jj];
             }
             __syncthreads();
@@ -710,17 +715,17 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
         const bool hdt = needH && free_time;
         {
             const int nP = 1 + (needT ? nd : 0) + (needH ? nd : 0) + (hdt ? 1 : 0);
-            const int nS = nP * tilesS, nDense = nS + (needH ? tilesA : 0);
+            const int nS = nP * tilesS, nDense = nS + (needH ? tilesX : 0);
             for (int w = tid; w < nDense; w += nthreads) {
                 if (w >= nS) {  // Gamma = U0 M^H  (Re <M, K U0> = Re tr(K Gamma)) into the idle E buffer
                     const int tl = w - nS;
-                    const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
-                    double2 acc[QCK_TILE][QCK_TILE];
-                    tile_mm<QCK_TILE>(MS(QS_D), false, MS(QS_M), true, nc, NP, r0, c0, acc);
+                    const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
+                    double2 acc[QCK_TILE][XC];
+                    tile_mm<XC>(MS(QS_D), false, MS(QS_M), true, nc, NP, r0, c0, acc);
 #pragma unroll
                     for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
-                        for (int jj = 0; jj < QCK_TILE; ++jj) XE(cur ^ 1)[r0 + i + NP * (c0 + jj)] = acc[i][jj];
+                        for (int jj = 0; jj < XC; ++jj) XE(cur ^ 1)[r0 + i + NP * (c0 + jj)] = acc[i][jj];
                     continue;
                 }
                 const int pi = w / tilesS, tl = w - pi * tilesS;
@@ -851,20 +856,20 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
                     for (int j = 0; j < nd; ++j) tape_get(XL(0, j), tapeS + (size_t)(k * (1 + nd) + 1 + j) * N * N);
                     __syncthreads();
                     for (int w = tid; w < nthr_tiles; w += nthreads) {
-                        const int pi = w / tilesA, tl = w - pi * tilesA;
-                        const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
-                        double2 acc[QCK_TILE][QCK_TILE];
+                        const int pi = w / tilesX, tl = w - pi * tilesX;
+                        const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
+                        double2 acc[QCK_TILE][XC];
                         if (pi == 0) {
-                            tile_mm<QCK_TILE>(XE(gb), false, XT, false, N, NP, r0, c0, acc);
-                            tile_mm<QCK_TILE, false>(XT, false, XE(gb), false, N, NP, r0, c0, acc);
+                            tile_mm<XC>(XE(gb), false, XT, false, N, NP, r0, c0, acc);
+                            tile_mm<XC, false>(XT, false, XE(gb), false, N, NP, r0, c0, acc);
                         } else {
-                            tile_mm<QCK_TILE>(XE(gb), false, XL(0, pi - 1), false, N, NP, r0, c0, acc);
+                            tile_mm<XC>(XE(gb), false, XL(0, pi - 1), false, N, NP, r0, c0, acc);
                         }
                         double2* Cop = pi == 0 ? XE(gb ^ 1) : XL(1, pi - 1);
 #pragma unroll
                         for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
-                            for (int jj = 0; jj < QCK_TILE; ++jj)
+                            for (int jj = 0; jj < XC; ++jj)
                                 if (r0 + i < N && c0 + jj < N) Cop[r0 + i + NP * (c0 + jj)] = acc[i][jj];
                     }
                     __syncthreads();
@@ -877,18 +882,18 @@ __global__ void __launch_bounds__(CN == 0 ? 256 : 128, CN == 0 ? 1 : 4) qck_quan
                     for (int j = 0; j < nd; ++j) tape_get(XL(0, j), tapeH + (size_t)(n * nd + j) * N * N);
                     __syncthreads();
                     // Q^i = Lam A_i (sparse, walks row b of A_i^H: A_i[k, b] = conj(A_i^H[b, k])), Lam' = cm Lam A (dense)
-                    for (int w = tid; w < tilesA; w += nthreads) {
-                        const int r0 = (w / tcolsA) * QCK_TILE, c0 = (w - (w / tcolsA) * tcolsA) * QCK_TILE;
-                        double2 acc[QCK_TILE][QCK_TILE];
-                        tile_mm<QCK_TILE>(XE(gb), false, MA(QA_A), false, N, NP, r0, c0, acc);
+                    for (int w = tid; w < tilesX; w += nthreads) {
+                        const int r0 = (w / tcolsX) * QCK_TILE, c0 = (w - (w / tcolsX) * tcolsX) * XC;
+                        double2 acc[QCK_TILE][XC];
+                        tile_mm<XC>(XE(gb), false, MA(QA_A), false, N, NP, r0, c0, acc);
 #pragma unroll
                         for (int i = 0; i < QCK_TILE; ++i)
 #pragma unroll
-                            for (int jj = 0; jj < QCK_TILE; ++jj)
+                            for (int jj = 0; jj < XC; ++jj)
                                 if (r0 + i < N && c0 + jj < N) XE(gb ^ 1)[r0 + i + NP * (c0 + jj)] = make_double2(cm * acc[i][jj].x, cm * acc[i][jj].y);
                     }
                     {
-                        int first = ((tilesA + 31) >> 5) << 5;
+                        int first = ((tilesX + 31) >> 5) << 5;
                         if (first >= nthreads) first = 0;
                         for (int w = tid - first; w >= 0 && w < nd * N * N; w += nthreads - first) {
                             const int i = w / (N * N), e = w - i * N * N;
@@ -996,12 +1001,12 @@ int qck_pick_threads(const QckClassDev& c) {
     const int tc = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP) ? QCK_TILE : 1;
     int tilesS = (c.NP / QCK_TILE) * (c.ncp / tc);
     const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
-    int items = is_exp ? (1 + c.nd) * (c.NP / QCK_TILE) * (c.NP / QCK_TILE) : (2 + 2 * c.nd) * tilesS;
+    int items = is_exp ? (1 + c.nd) * (c.NP / QCK_TILE) * c.NP : (2 + 2 * c.nd) * tilesS;
     int th = ((items + 31) / 32) * 32 + (is_exp ? 0 : 32);  // Pade: one extra warp for the sparse products / scalar traces
     if (th < 64) th = 64;
     if (th > 256) th = 256;
     if (c.N != 2 && c.N != 3 && c.N != 4 && c.N != 5 && c.N != 6 && c.N != 8 && c.N != 9) return th;  // generic kernel: up to 256
-    return th > 128 ? 128 : th;
+    return th > (is_exp ? 160 : 128) ? (is_exp ? 160 : 128) : th;
 }
 
 typedef void (*qck_kernel_t)(const QckLaunch);
