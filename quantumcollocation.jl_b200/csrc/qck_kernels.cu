@@ -52,7 +52,7 @@ __device__ __forceinline__ void tile_mm(const double2* __restrict__ A, bool tA, 
     const double sa = tA ? -1.0 : 1.0, sb = tB ? -1.0 : 1.0;  // conjugation = sign of the imaginary part
     const double2* a = A + r0 * ar;
     const double2* b = B + c0 * bc;
-#pragma unroll 9
+#pragma unroll 3
     for (int k = 0; k < K; ++k) {
         double2 av[QCK_TILE], bv[TC];
 #pragma unroll
