@@ -998,6 +998,7 @@ void qck_smem_finalize(QckClassDev& c) {
 }
 
 int qck_pick_threads(const QckClassDev& c) {
+    if (const char* e = getenv("QCK_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }  // tuning knob
     const int tc = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP) ? QCK_TILE : 1;
     int tilesS = (c.NP / QCK_TILE) * (c.ncp / tc);
     const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
