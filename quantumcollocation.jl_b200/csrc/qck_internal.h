@@ -110,6 +110,8 @@ struct QckLaunch {
     const int* moff_global;  // [active member][state_off, ctrl_off, row_off]
     int moff_smem;           // copy them to shared memory at kernel start (set by the launcher)
     int sm_count;
+    int group_threads;       // threads cooperating on one work item (set by the launcher)
+    int group_smem;          // bytes of shared memory per group
     long long* timing;       // optional per-stage cycle counters (debug)
 };
 

@@ -230,13 +230,25 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
         tick_ = now_;                                                                \
     }
 
-template <int KIND, int TC, int CN>
+template <int KIND, int TC, int CN, bool MULTI>
 __global__ void __launch_bounds__(CN == 0 ? 256 : (KIND == QK_EXP ? 160 : 128), CN == 0 ? 1 : (KIND == QK_EXP ? 3 : 4))
 qck_quantum_kernel(const QckLaunch p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // A CTA holds `ngroups` independent groups of G threads; each group works through its own sequence of work items in
+    // its own slice of shared memory.  Large problems use one group per CTA (block barrier); for small level counts a
+    // group is a single warp (warp barrier only), so several items per CTA progress independently of one another.
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    // (MULTI is a template parameter so that the single-group kernels keep absolute shared-memory addressing)
+    const int G = MULTI ? 32 : (int)blockDim.x, grp = MULTI ? (int)(threadIdx.x >> 5) : 0, ngroups = MULTI ? (int)(blockDim.x >> 5) : 1;
+    unsigned char* smem_raw = MULTI ? smem_all + (size_t)grp * p.group_smem : smem_all;
+    const long long gid = (long long)blockIdx.x * ngroups + grp, gstride = (long long)gridDim.x * ngroups;
+#define GSYNC()                     \
+    do {                            \
+        if (MULTI) __syncwarp();    \
+        else __syncthreads();       \
+    } while (0)
     double* sm = reinterpret_cast<double*>(smem_raw);
     const QckClassDev& c = p.c;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x - grp * G, nthreads = G;
     // CN > 0: levels known at compile time (index arithmetic folds, k-loops unroll); CN == 0: generic fallback
     const int N = CN > 0 ? CN : c.N;
     const int NP = CN > 0 ? ((CN + QCK_TILE - 1) / QCK_TILE) * QCK_TILE : c.NP;
@@ -314,24 +326,24 @@ qck_quantum_kernel(const QckLaunch p) {
     for (int i = tid; i < p.n_aux; i += nthreads) auxs[i] = p.aux[i];
     if (p.moff_smem)
         for (int i = tid; i < 3 * nact; i += nthreads) const_cast<int*>(moff)[i] = p.moff_global[i];
-    __syncthreads();
+    GSYNC();
     if (tid == 0 && c.pl_base[QO_ONE] >= 0) image[c.pl_base[QO_ONE]] = 1.0;
     int buf = 0, buf_member = -1;
-    if ((long long)blockIdx.x < n_items) {
-        buf_member = p.member_begin + (int)(blockIdx.x % nact);
-        prefetch(blockIdx.x / nact, buf_member, buf, true);
+    if (gid < n_items) {
+        buf_member = p.member_begin + (int)(gid % nact);
+        prefetch(gid / nact, buf_member, buf, true);
     }
 
     // (t, mi) of the current item are advanced incrementally: a 64-bit division per item is not free
-    const int step_t = (int)(gridDim.x / nact), step_m = (int)(gridDim.x % nact);
-    long long t = blockIdx.x / nact;
-    int mi = (int)(blockIdx.x % nact);
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int step_t = (int)(gstride / nact), step_m = (int)(gstride % nact);
+    long long t = gid / nact;
+    int mi = (int)(gid % nact);
+    for (long long item = gid; item < n_items; item += gstride) {
         const int vwarp = warp, vtid = tid;
         const int m = p.member_begin + mi;
         QCK_TICK(0);
         cp_async_wait_all();
-        __syncthreads();  // staged inputs visible; previous item's write-out has finished reading the image
+        GSYNC();  // staged inputs visible; previous item's write-out has finished reading the image
         QCK_TICK(1);
         const double2* A0 = CONV(buf);
         const double2* ellv = CONV(buf) + N * N;
@@ -379,12 +391,12 @@ qck_quantum_kernel(const QckLaunch p) {
                 }
             }
         }
-        __syncthreads();
+        GSYNC();
         QCK_TICK(2);
         // staging is free again: fetch the next item's inputs (and tables, if its member differs) behind the compute
         int next_buf = buf, next_member = buf_member;
         {
-            const long long nitem = item + gridDim.x;
+            const long long nitem = item + gstride;
             if (nitem < n_items) {
                 int nmi = mi + step_m;
                 long long nt = t + step_t;
@@ -467,7 +479,7 @@ qck_quantum_kernel(const QckLaunch p) {
                 }
             }
         }
-        __syncthreads();
+        GSYNC();
         QCK_TICK(4);
 
         // ---- stage 2: A2 D, (A2)^H M, C_j D, C_j^H M with fused epilogues into the image;  scalar traces ------------
@@ -598,7 +610,7 @@ qck_quantum_kernel(const QckLaunch p) {
                     }
             }
         }
-        __syncthreads();
+        GSYNC();
         } else {
         // ============================ exponential integrators =============================================================
         // residual U1 - exp(h A) U0.  exp and its Frechet derivatives d/da_j by scaling and squaring of a degree-8 Taylor
@@ -620,7 +632,7 @@ qck_quantum_kernel(const QckLaunch p) {
             for (int r = 0; r < N; ++r) { const double2 a = MA(QA_A)[r + NP * tid]; cs += fabs(a.x) + fabs(a.y); }
             image[tid] = cs;
         }
-        __syncthreads();
+        GSYNC();
         double nrm = 0.0;
         for (int cc = 0; cc < N; ++cc) nrm = fmax(nrm, image[cc]);
         nrm *= fabs(h);
@@ -643,9 +655,9 @@ qck_quantum_kernel(const QckLaunch p) {
                 }
             }
         }
-        __syncthreads();
+        GSYNC();
         // Hessian: the inputs of every Horner step / squaring level are kept on a per-CTA tape in global memory (L2)
-        double2* tapeH = c.tape ? c.tape + (size_t)blockIdx.x * c.tape_stride : nullptr;  // [(TK-1) steps][nd][N*N]
+        double2* tapeH = c.tape ? c.tape + (size_t)gid * c.tape_stride : nullptr;  // [(TK-1) steps][nd][N*N]
         double2* tapeS = tapeH ? tapeH + (size_t)(TK - 1) * nd * N * N : nullptr;        // [levels][1 + nd][N*N]
         const bool taping = needH && tapeH != nullptr;
         if (taping && sq > c.tape_levels) sq = c.tape_levels;  // (never for ||h A||_1 <= 2^(tape_levels-4))
@@ -682,7 +694,7 @@ qck_quantum_kernel(const QckLaunch p) {
                         if (r < N && cc < N) Cop[r + NP * cc] = v;
                     }
             }
-            __syncthreads();
+            GSYNC();
             cur ^= 1;
         }
         for (int k = 0; k < sq; ++k) {
@@ -707,7 +719,7 @@ qck_quantum_kernel(const QckLaunch p) {
                     for (int jj = 0; jj < XC; ++jj)
                         if (r0 + i < N && c0 + jj < N) Cop[r0 + i + NP * (c0 + jj)] = acc[i][jj];
             }
-            __syncthreads();
+            GSYNC();
             cur ^= 1;
         }
         QCK_TICK(4);
@@ -774,7 +786,7 @@ qck_quantum_kernel(const QckLaunch p) {
                 }
             }
         }
-        __syncthreads();
+        GSYNC();
         // ---- outputs 2: V = A (E U0) -> d/dh (V kept in an idle L buffer);  state_t x dt = -E^H (A^H M) ---------------------
         double2* Vbuf = XL(cur ^ 1, 0);
         if (free_time && needT) {
@@ -799,7 +811,7 @@ qck_quantum_kernel(const QckLaunch p) {
                     }
             }
         }
-        __syncthreads();
+        GSYNC();
         if (needH) {
             // ---- dt x dt = -Re <A^H M, V>,  a_j x dt = -Re <M, A_j (E U0)> - Re <A^H M, L_j U0>  (one warp per scalar) ----------
             if (free_time)
@@ -851,10 +863,10 @@ qck_quantum_kernel(const QckLaunch p) {
             };
             if (taping) {
                 for (int k = sq - 1; k >= 0; --k) {
-                    __syncthreads();  // previous level's traces / products are done with the buffers
+                    GSYNC();  // previous level's traces / products are done with the buffers
                     tape_get(XT, tapeS + (size_t)(k * (1 + nd)) * N * N);
                     for (int j = 0; j < nd; ++j) tape_get(XL(0, j), tapeS + (size_t)(k * (1 + nd) + 1 + j) * N * N);
-                    __syncthreads();
+                    GSYNC();
                     for (int w = tid; w < nthr_tiles; w += nthreads) {
                         const int pi = w / tilesX, tl = w - pi * tilesX;
                         const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
@@ -872,15 +884,15 @@ qck_quantum_kernel(const QckLaunch p) {
                             for (int jj = 0; jj < XC; ++jj)
                                 if (r0 + i < N && c0 + jj < N) Cop[r0 + i + NP * (c0 + jj)] = acc[i][jj];
                     }
-                    __syncthreads();
+                    GSYNC();
                     pair_traces(1.0);
                     gb ^= 1;
                 }
                 for (int n = TK - 2; n >= 0; --n) {
                     const double cm = y / (TK - 1 - n);
-                    __syncthreads();
+                    GSYNC();
                     for (int j = 0; j < nd; ++j) tape_get(XL(0, j), tapeH + (size_t)(n * nd + j) * N * N);
-                    __syncthreads();
+                    GSYNC();
                     // Q^i = Lam A_i (sparse, walks row b of A_i^H: A_i[k, b] = conj(A_i^H[b, k])), Lam' = cm Lam A (dense)
                     for (int w = tid; w < tilesX; w += nthreads) {
                         const int r0 = (w / tcolsX) * QCK_TILE, c0 = (w - (w / tcolsX) * tcolsX) * XC;
@@ -908,19 +920,19 @@ qck_quantum_kernel(const QckLaunch p) {
                             XL(1, i)[a + NP * b] = v;
                         }
                     }
-                    __syncthreads();
+                    GSYNC();
                     pair_traces(cm);
                     gb ^= 1;
                 }
             }
             // block reduction of the pair sums: shuffles inside the warps, then across warps through the V buffer
-            __syncthreads();
+            GSYNC();
             double* red = reinterpret_cast<double*>(XL(0, 0));
             for (int q = 0; q < npair; ++q) {
                 const double v = warp_sum(hacc[q]);
                 if (lane == 0) red[q * nwarps_ + warp] = v;
             }
-            __syncthreads();
+            GSYNC();
             if (tid < npair) {
                 double v = 0.0;
                 for (int w2 = 0; w2 < nwarps_; ++w2) v += red[tid * nwarps_ + w2];
@@ -929,7 +941,7 @@ qck_quantum_kernel(const QckLaunch p) {
                 const int qq = qo_haa(rem, j);
                 if (c.pl_base[qq] >= 0) image[c.pl_base[qq]] = -v;
             }
-            __syncthreads();
+            GSYNC();
         }
 #undef XE
 #undef XL
@@ -952,6 +964,7 @@ qck_quantum_kernel(const QckLaunch p) {
 #undef CONV
 #undef CONI
 #undef PUT
+#undef GSYNC
 }
 
 __global__ void qck_aux_kernel(const QckLaunch p) {
@@ -1004,25 +1017,30 @@ int qck_pick_threads(const QckClassDev& c) {
     const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
     int items = is_exp ? (1 + c.nd) * (c.NP / QCK_TILE) * c.NP : (2 + 2 * c.nd) * tilesS;
     int th = ((items + 31) / 32) * 32 + (is_exp ? 0 : 32);  // Pade: one extra warp for the sparse products / scalar traces
-    if (th < 64) th = 64;
+    if (items <= 32 && !is_exp) th = 32;  // everything fits one warp: warp-sized groups, several items per CTA
+    else if (th < 64) th = 64;
     if (th > 256) th = 256;
-    if (c.N != 2 && c.N != 3 && c.N != 4 && c.N != 5 && c.N != 6 && c.N != 8 && c.N != 9) return th;  // generic kernel: up to 256
+    if (c.N != 2 && c.N != 3 && c.N != 4 && c.N != 9) return th;  // generic kernel: up to 256
     return th > (is_exp ? 160 : 128) ? (is_exp ? 160 : 128) : th;
 }
 
 typedef void (*qck_kernel_t)(const QckLaunch);
-template <int KIND, int TC>
+template <int KIND, int TC, bool MULTI>
 static qck_kernel_t kernel_for(int N) {
     switch (N) {
-        case 2: return qck_quantum_kernel<KIND, TC, 2>;
-        case 3: return qck_quantum_kernel<KIND, TC, 3>;
-        case 4: return qck_quantum_kernel<KIND, TC, 4>;
-        case 5: return qck_quantum_kernel<KIND, TC, 5>;
-        case 6: return qck_quantum_kernel<KIND, TC, 6>;
-        case 8: return qck_quantum_kernel<KIND, TC, 8>;
-        case 9: return qck_quantum_kernel<KIND, TC, 9>;
-        default: return qck_quantum_kernel<KIND, TC, 0>;
+        case 2: return qck_quantum_kernel<KIND, TC, 2, MULTI>;
+        case 3: return qck_quantum_kernel<KIND, TC, 3, MULTI>;
+        case 4: return qck_quantum_kernel<KIND, TC, 4, MULTI>;
+        case 9: return qck_quantum_kernel<KIND, TC, 9, MULTI>;
+        default: return qck_quantum_kernel<KIND, TC, 0, MULTI>;
     }
+}
+template <int KIND, int TC>
+static qck_kernel_t kernel_for(int N, bool multi) {
+    if constexpr (KIND == QK_PADE4) {  // warp-sized groups exist for the Pade kernels only
+        if (multi) return kernel_for<KIND, TC, true>(N);
+    }
+    return kernel_for<KIND, TC, false>(N);
 }
 
 #define QCK_MAX_FUSED_AUX 256
@@ -1035,16 +1053,24 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     const bool unitary = c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP;
     qck_kernel_t kern = nullptr;
     int tc = unitary ? QCK_TILE : 1;
-    if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = kernel_for<QK_PADE4, QCK_TILE>(c.N);
-    else if (c.kind == QCK_KET_PADE && c.order == 4) kern = kernel_for<QK_PADE4, 1>(c.N);
-    else if (c.kind == QCK_UNITARY_EXP) kern = kernel_for<QK_EXP, QCK_TILE>(c.N);
-    else if (c.kind == QCK_KET_EXP) kern = kernel_for<QK_EXP, 1>(c.N);
+    const bool is_pade = c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE;
+    const bool multi = is_pade && c.threads == 32;  // warp-sized groups: four independent items per CTA
+    if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = kernel_for<QK_PADE4, QCK_TILE>(c.N, multi);
+    else if (c.kind == QCK_KET_PADE && c.order == 4) kern = kernel_for<QK_PADE4, 1>(c.N, multi);
+    else if (c.kind == QCK_UNITARY_EXP) kern = kernel_for<QK_EXP, QCK_TILE>(c.N, multi);
+    else if (c.kind == QCK_KET_EXP) kern = kernel_for<QK_EXP, 1>(c.N, multi);
     else return (int)cudaErrorNotSupported;
     const int nact = L.member_end - L.member_begin;
     L.moff_smem = nact <= 1024 ? 1 : 0;
     L.sm_count = sm_count;
-    size_t smem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double)) + (L.moff_smem ? (size_t)nact * 12 + 16 : 0);
-    int threads = c.threads;
+    const int G = c.threads;
+    const int ngroups = multi ? 4 : 1;
+    size_t gsmem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double)) + (L.moff_smem ? (size_t)nact * 12 + 16 : 0);
+    gsmem = (gsmem + 15) & ~(size_t)15;
+    L.group_threads = G;
+    L.group_smem = (int)gsmem;
+    size_t smem = gsmem * ngroups;
+    int threads = G * ngroups;
     (void)tc;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1053,11 +1079,15 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
     long long grid = (long long)sm_count * per_sm;
-    if (c.max_ctas > 0 && grid > c.max_ctas) grid = c.max_ctas;  // the Hessian tape was sized for this many CTAs
-    if (grid > n_items) grid = n_items;
-    // several active members: a grid that is a multiple of their number keeps every CTA on ONE member (its tables are
-    // fetched once instead of once per item)
-    if (nact > 1 && grid >= nact) grid -= grid % nact;
+    if (c.max_ctas > 0 && grid * ngroups > c.max_ctas) grid = c.max_ctas / ngroups;  // the Hessian tape was sized for this many groups
+    if (grid * ngroups > n_items) grid = (n_items + ngroups - 1) / ngroups;
+    // several active members: a group count that is a multiple of their number keeps every group on ONE member (its
+    // tables are fetched once instead of once per item)
+    if (nact > 1 && grid * ngroups >= nact) {
+        long long total = grid * ngroups;
+        total -= total % nact;
+        if (total % ngroups == 0) grid = total / ngroups;
+    }
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
     static const bool tim = getenv("QCK_DEBUG_TIMING") != nullptr;
     static long long* d_tim = nullptr;
@@ -1066,7 +1096,7 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         cudaMemsetAsync(d_tim, 0, 8 * sizeof(long long), stream);
         L.timing = d_tim;
     }
-    if (dbg) fprintf(stderr, "[qcknot] N=%d nd=%d threads=%d smem=%zu B (image %d doubles) CTAs/SM=%d grid=%lld units=%d\n", c.N, c.nd, threads, smem, c.img_doubles, per_sm, grid, c.nseg);
+    if (dbg) fprintf(stderr, "[qcknot] N=%d nd=%d threads=%dx%d smem=%zu B (image %d doubles) CTAs/SM=%d grid=%lld units=%d\n", c.N, c.nd, G, ngroups, smem, c.img_doubles, per_sm, grid, c.nseg);
     kern<<<(unsigned)grid, threads, smem, stream>>>(L);
     if (tim) {
         long long h[8];
