@@ -264,11 +264,13 @@ qck_quantum_kernel(const QckLaunch p) {
     double2* SS = reinterpret_cast<double2*>(sm + c.off_S);
     double* image = sm + c.off_img;
     double* stage = reinterpret_cast<double*>(smem_raw + c.sm_stage);  // [z_t state | z_t+1 state | mu | a | h]
-    QckAux* auxs = reinterpret_cast<QckAux*>(smem_raw + c.sm_bytes);
-    double* auxv = reinterpret_cast<double*>(smem_raw + c.sm_bytes + p.n_aux * (int)sizeof(QckAux));
+    // per group: operands of the auxiliary entries; per CTA (behind all groups): the entries themselves and the member offsets
+    double* auxv = reinterpret_cast<double*>(smem_raw + c.sm_bytes);
+    unsigned char* cta_shared = smem_all + (size_t)ngroups * p.group_smem;
+    QckAux* auxs = reinterpret_cast<QckAux*>(cta_shared);
     const int nact = p.member_end - p.member_begin;
     // per-member offsets (state, drive, row) of the active members: in shared memory when they fit, else global
-    const int* moff = p.moff_smem ? reinterpret_cast<const int*>(auxv + 3 * p.n_aux) : p.moff_global;
+    const int* moff = p.moff_smem ? reinterpret_cast<const int*>(cta_shared + p.n_aux * (int)sizeof(QckAux)) : p.moff_global;
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;  // 16-byte records of the per-member write-out table
     const int lane = tid & 31, warp = tid >> 5, nwarps_ = nthreads >> 5;
     const int elln = c.ell_stride, kkc = c.kk_cap;
@@ -323,10 +325,10 @@ qck_quantum_kernel(const QckLaunch p) {
     };
 
     for (int i = tid; i < c.scratch_doubles; i += nthreads) sm[i] = 0.0;
-    for (int i = tid; i < p.n_aux; i += nthreads) auxs[i] = p.aux[i];
+    for (int i = threadIdx.x; i < p.n_aux; i += blockDim.x) auxs[i] = p.aux[i];
     if (p.moff_smem)
-        for (int i = tid; i < 3 * nact; i += nthreads) const_cast<int*>(moff)[i] = p.moff_global[i];
-    GSYNC();
+        for (int i = threadIdx.x; i < 3 * nact; i += blockDim.x) const_cast<int*>(moff)[i] = p.moff_global[i];
+    __syncthreads();  // CTA-wide tables ready (every thread of the CTA gets here)
     if (tid == 0 && c.pl_base[QO_ONE] >= 0) image[c.pl_base[QO_ONE]] = 1.0;
     int buf = 0, buf_member = -1;
     if (gid < n_items) {
@@ -1065,28 +1067,36 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     L.sm_count = sm_count;
     const int G = c.threads;
     const int ngroups = multi ? 4 : 1;
-    size_t gsmem = (size_t)c.sm_bytes + (size_t)L.n_aux * (sizeof(QckAux) + 3 * sizeof(double)) + (L.moff_smem ? (size_t)nact * 12 + 16 : 0);
-    gsmem = (gsmem + 15) & ~(size_t)15;
+    // Launch geometry.  With several active members the per-member tables are double-buffered in shared memory unless the
+    // group count is a multiple of the member count (then every group stays on ONE member and one buffer is enough):
+    // try the single-buffer layout first, fall back to two buffers if the grid cannot be aligned.
     L.group_threads = G;
-    L.group_smem = (int)gsmem;
-    size_t smem = gsmem * ngroups;
-    int threads = G * ngroups;
+    size_t smem = 0;
+    int threads = G * ngroups, per_sm = 0;
+    long long grid = 0;
     (void)tc;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
-    long long grid = (long long)sm_count * per_sm;
-    if (c.max_ctas > 0 && grid * ngroups > c.max_ctas) grid = c.max_ctas / ngroups;  // the Hessian tape was sized for this many groups
-    if (grid * ngroups > n_items) grid = (n_items + ngroups - 1) / ngroups;
-    // several active members: a group count that is a multiple of their number keeps every group on ONE member (its
-    // tables are fetched once instead of once per item)
-    if (nact > 1 && grid * ngroups >= nact) {
-        long long total = grid * ngroups;
-        total -= total % nact;
-        if (total % ngroups == 0) grid = total / ngroups;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        L.c.n_tbuf = (nact > 1 && attempt == 1) ? 2 : 1;
+        qck_smem_finalize(L.c);
+        size_t gsmem = (size_t)L.c.sm_bytes + (size_t)L.n_aux * 3 * sizeof(double);
+        gsmem = (gsmem + 15) & ~(size_t)15;
+        L.group_smem = (int)gsmem;
+        smem = gsmem * ngroups + (size_t)L.n_aux * sizeof(QckAux) + (L.moff_smem ? (size_t)nact * 12 + 16 : 0);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
+        grid = (long long)sm_count * per_sm;
+        if (c.max_ctas > 0 && grid * ngroups > c.max_ctas) grid = c.max_ctas / ngroups;  // the Hessian tape was sized for this many groups
+        if (grid * ngroups > n_items) grid = (n_items + ngroups - 1) / ngroups;
+        bool aligned = nact == 1;
+        if (nact > 1 && grid * ngroups >= nact) {
+            long long total = grid * ngroups;
+            total -= total % nact;
+            if (total % ngroups == 0) { grid = total / ngroups; aligned = true; }
+        }
+        if (aligned || attempt == 1) break;
     }
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
     static const bool tim = getenv("QCK_DEBUG_TIMING") != nullptr;
