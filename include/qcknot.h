@@ -63,7 +63,7 @@ extern "C" {
  * Derivative:    x component = [state_off, +state_len), dx component = [ctrl_off, +state_len); H_* ignored. */
 typedef struct qck_integrator_desc {
     int32_t kind;
-    int32_t order; /* Pade order (4, 6, 8, 10; even); ignored for the other kinds */
+    int32_t order; /* Pade order (4, 6, 8, 10, 12); ignored for the other kinds */
     int32_t levels; /* N */
     int32_t n_drives;
     int32_t state_off;

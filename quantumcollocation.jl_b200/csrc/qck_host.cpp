@@ -252,6 +252,12 @@ int build(qck_handle* h) {
             c.NP = ((I.N + QCK_TILE - 1) / QCK_TILE) * QCK_TILE;
             c.ncp = I.unitary() ? c.NP : 1;
             c.free_time = free_time; c.dt_off = h->dt_off; c.zdim = zdim; c.dyn = h->dyn; c.dt_fixed = h->dt_fixed;
+            c.pade_m = 0;
+            if (I.pade()) {  // c_k = (2m-k)! m! / ((2m)! k! (m-k)!)  ->  r_k = c_{k+1}/c_k = (m-k) / ((2m-k)(k+1))
+                const int m = I.order / 2;
+                c.pade_m = m;
+                for (int k2 = 0; k2 < m; ++k2) c.pade_r[k2] = (double)(m - k2) / ((double)(2 * m - k2) * (k2 + 1));
+            }
             qck_scratch_layout(c);
         } else ci = it->second;
         cls_idx[q] = ci;
@@ -509,6 +515,16 @@ int build(qck_handle* h) {
             (e = upload(moff, &c.moff, C.allocs)) != cudaSuccess)
             return fail(h, QCK_ECUDA, "uploading class constants: %s", cudaGetErrorString(e));
         c.tape = nullptr; c.tape_stride = 0; c.tape_levels = 0; c.max_ctas = 0;
+        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order != 4 && h->eval_hessian && !g_structure_only) {
+            // reverse-sweep tape of the general-order Pade Hessian: (m-1) Horner levels x (P + nd + 1 tangents) per group
+            c.tape_stride = (long long)(c.pade_m - 1) * (2 + nd) * N * N;
+            c.max_ctas = h->sm_count * 4;
+            void* tp = nullptr;
+            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas)) != cudaSuccess)
+                return fail(h, QCK_ENOMEM, "tape allocation failed: %s", cudaGetErrorString(e));
+            C.allocs.push_back(tp);
+            c.tape = static_cast<double2*>(tp);
+        }
         if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && !g_structure_only) {
             // reverse-sweep tape of the exponential Hessian: 7 Horner steps x nd jets + 16 squaring levels x (1 + nd) matrices per CTA
             c.tape_levels = 16;
@@ -650,7 +666,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
             I.nc = I.unitary() ? I.N : 1;
             I.dim = 2 * I.N * I.nc;
             if (I.state_len != I.dim) { fail(h, QCK_EINVAL, "integrator %d: state_len %d != %d", q, I.state_len, I.dim); return bail(QCK_EINVAL); }
-            if (I.pade() && I.order != 4) { fail(h, QCK_EINVAL, "integrator %d: Pade order %d not supported by this build (4 only)", q, I.order); return bail(QCK_EINVAL); }
+            if (I.pade() && (I.order < 4 || I.order > 12 || (I.order & 1))) { fail(h, QCK_EINVAL, "integrator %d: Pade order %d not supported (even orders 4..12)", q, I.order); return bail(QCK_EINVAL); }
             if (I.nd > 0 && !s.H_drives) { fail(h, QCK_EINVAL, "integrator %d: H_drives is NULL", q); return bail(QCK_EINVAL); }
             if (I.ctrl_off < 0 || I.ctrl_off + I.nd > h->zdim) { fail(h, QCK_EINVAL, "integrator %d: drive component out of range", q); return bail(QCK_EINVAL); }
             size_t nn = (size_t)I.N * I.N;

@@ -9,7 +9,7 @@
 #define QCK_TILE 3          // register tile edge of the small complex products (3x3 complex per thread)
 #define QCK_MAX_DRIVES 6
 #define QCK_MAX_PADE_M 5    // Pade order <= 10
-enum { QK_PADE4 = 0, QK_EXP = 1 };  // kernel families
+enum { QK_PADE4 = 0, QK_EXP = 1, QK_PADEN = 2 };  // kernel families
 
 // ---- shared-memory scratch of the quantum kernels -----------------------------------------------------------------
 // "A-type" matrices are NP x NP complex, "state-type" are NP x ncp complex (ncp = NP for unitaries, 1 for kets),
@@ -90,6 +90,9 @@ struct QckClassDev {
     long long tape_stride;     // double2 elements per CTA
     int tape_levels;           // squaring levels the tape can hold
     int max_ctas;              // CTAs the tape was sized for (0 = no limit)
+    // general-order Pade: degree m = order/2 and coefficient ratios r_k = c_{k+1}/c_k
+    int pade_m;
+    double pade_r[8];
 };
 
 struct QckLaunch {

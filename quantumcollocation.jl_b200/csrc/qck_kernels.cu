@@ -231,7 +231,7 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
     }
 
 template <int KIND, int TC, int CN, bool MULTI>
-__global__ void __launch_bounds__(CN == 0 ? 256 : (KIND == QK_EXP ? 160 : 128), CN == 0 ? 1 : (KIND == QK_EXP ? 3 : 4))
+__global__ void __launch_bounds__(CN == 0 ? 256 : (KIND != QK_PADE4 ? 160 : 128), CN == 0 ? 1 : (KIND != QK_PADE4 ? 3 : 4))
 qck_quantum_kernel(const QckLaunch p) {
     // A CTA holds `ngroups` independent groups of G threads; each group works through its own sequence of work items in
     // its own slice of shared memory.  Large problems use one group per CTA (block barrier); for small level counts a
@@ -368,8 +368,8 @@ qck_quantum_kernel(const QckLaunch p) {
                 int im = q >= N, r = q - im * N;
                 double u0 = stage[idx], u1 = stage[dim + idx];
                 int o = 2 * (r + NP * cc) + im;
-                reinterpret_cast<double*>(MS(QS_D))[o] = KIND == QK_EXP ? u0 : u1 - u0;  // exp kernel keeps U0, U1 themselves
-                reinterpret_cast<double*>(MS(QS_S))[o] = KIND == QK_EXP ? u1 : u1 + u0;
+                reinterpret_cast<double*>(MS(QS_D))[o] = KIND != QK_PADE4 ? u0 : u1 - u0;  // exp / general Pade keep U0, U1 themselves
+                reinterpret_cast<double*>(MS(QS_S))[o] = KIND != QK_PADE4 ? u1 : u1 + u0;
                 if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = stage[2 * dim + idx];
             }
             if (warp == nwarps_ - 1) {
@@ -613,7 +613,7 @@ qck_quantum_kernel(const QckLaunch p) {
             }
         }
         GSYNC();
-        } else {
+        } else if constexpr (KIND == QK_EXP) {
         // ============================ exponential integrators =============================================================
         // residual U1 - exp(h A) U0.  exp and its Frechet derivatives d/da_j by scaling and squaring of a degree-8 Taylor
         // polynomial: Y = h A / 2^s with ||Y||_1 <= 1/16 (truncation: exp 4e-17, first derivatives 6e-15 relative),
@@ -947,6 +947,270 @@ qck_quantum_kernel(const QckLaunch p) {
         }
 #undef XE
 #undef XL
+        } else {
+        // ============================ Pade integrators of general order 2m (6, 8, 10, 12) ====================================
+        // F = p(X), B = p(-X), X = h A, p(X) = sum_k c_k X^k evaluated in ratio form P_k = I + r_k X P_{k+1} (r_k = c_{k+1}/c_k,
+        // P_m = I, p = P_0), with tangents in the directions a_j (dX = h A_j, sparse) and h (dX = A):
+        //     T^d_k = r_k (X_d P_{k+1} + X T^d_{k+1}),
+        // and the second derivatives contracted with Gamma = V M^H (V = U0 for F, U1 for B) by a reverse sweep
+        //     += r_k Re tr(Lam_k (X_de P_{k+1} + X_d T^e_{k+1} + X_e T^d_{k+1})),  Lam_{k+1} = r_k Lam_k X,  X_(a_j h) = A_j.
+        // The two polynomials are processed one after the other (sg = +1: F, sg = -1: B) in the same buffers; the image
+        // entries that receive both parts (residual, d/da_j, d/dh) are assigned by the F pass and updated by the B pass.
+        constexpr int XC = 1;
+        const int tcolsX = NP / XC, tilesX = (NP / QCK_TILE) * tcolsX;
+        const int mdeg = c.pade_m;
+        const int ndir = nd + (free_time ? 1 : 0);  // tangent directions: a_0..a_{nd-1}, then h
+#define XP(b) MA(1 + (b))
+#define XJ(b, d) MA(3 + (b) * (nd + 1) + (d))
+#define XT MA(3 + 2 * (nd + 1))
+#define XG(b) MA(4 + 2 * (nd + 1) + (b))
+        double2* tape = c.tape ? c.tape + (size_t)gid * c.tape_stride : nullptr;  // [(m-1) levels][1 + ndir][N*N]
+        const bool taping = needH && tape != nullptr;
+        auto tape_put = [&](double2* dst, const double2* src) {
+            for (int e = tid; e < N * N; e += nthreads) dst[e] = src[(e % N) + NP * (e / N)];
+        };
+        auto tape_get = [&](double2* dst, const double2* src) {
+            for (int e = tid; e < N * N; e += nthreads) dst[(e % N) + NP * (e / N)] = src[e];
+        };
+        constexpr int NPAIR_MAX = (QCK_MAX_DRIVES + 1) * (QCK_MAX_DRIVES + 2) / 2;
+        double hacc[NPAIR_MAX];
+#pragma unroll
+        for (int q = 0; q < NPAIR_MAX; ++q) hacc[q] = 0.0;
+        // hacc[e(e+1)/2 + d] += wgt * Re tr(X Y),  tr(X Y) = sum_ab X[a,b] Y[b,a]
+        auto tr_acc = [&](int d, int e2, double wgt, const double2* X, const double2* Y) {
+            double s = 0.0;
+            for (int el = tid; el < N * N; el += nthreads) {
+                const int a = el % N, b = el / N;
+                const double2 x = X[a + NP * b], yv = Y[b + NP * a];
+                s += x.x * yv.x - x.y * yv.y;
+            }
+            hacc[e2 * (e2 + 1) / 2 + d] += wgt * s;
+        };
+        for (int pass = 0; pass < 2; ++pass) {
+            const double sg = pass == 0 ? 1.0 : -1.0;  // F = p(X), B = p(-X)
+            const double2* V = pass == 0 ? MS(QS_D) : MS(QS_S);  // U0 | U1
+            int cur = 0;
+            GSYNC();
+            {   // level m-1: P = I + sg r X,  T^j = sg r h A_j,  T^h = sg r A
+                const double r = sg * c.pade_r[mdeg - 1];
+                for (int e = tid; e < N * N; e += nthreads) {
+                    const int rr = e % N, cc = e / N;
+                    const double2 a = MA(QA_A)[rr + NP * cc];
+                    XP(0)[rr + NP * cc] = make_double2((rr == cc ? 1.0 : 0.0) + r * h * a.x, r * h * a.y);
+                    for (int j = 0; j < nd; ++j) {
+                        const int o = ((j * 2) * N + rr) * W;
+                        double2 v = make_double2(0.0, 0.0);
+                        for (int u = 0; u < W; ++u)
+                            if (ellc[o + u] == cc) { v.x += ellv[o + u].x; v.y += ellv[o + u].y; }
+                        XJ(0, j)[rr + NP * cc] = make_double2(r * h * v.x, r * h * v.y);
+                    }
+                    if (free_time) XJ(0, nd)[rr + NP * cc] = make_double2(r * a.x, r * a.y);
+                }
+            }
+            GSYNC();
+            for (int kk = mdeg - 2; kk >= 0; --kk) {  // P_kk from level kk+1 (buffers `cur`)
+                const double r = sg * c.pade_r[kk];
+                if (taping) {
+                    double2* tp = tape + (size_t)(kk * (1 + ndir)) * N * N;
+                    tape_put(tp, XP(cur));
+                    for (int d = 0; d < ndir; ++d) tape_put(tp + (size_t)(1 + d) * N * N, XJ(cur, d));
+                }
+                for (int w = tid; w < (1 + ndir) * tilesX; w += nthreads) {
+                    const int pi = w / tilesX, tl = w - pi * tilesX;
+                    const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
+                    double2 acc[QCK_TILE][XC], acc2[QCK_TILE][XC];
+                    const int d = pi - 1;  // -1: P itself
+                    tile_mm<XC>(MA(QA_A), false, d < 0 ? XP(cur) : XJ(cur, d), false, N, NP, r0, c0, acc);
+                    if (d == nd) tile_mm<XC>(MA(QA_A), false, XP(cur), false, N, NP, r0, c0, acc2);  // X_h P = A P
+                    double2* Cop = d < 0 ? XP(cur ^ 1) : XJ(cur ^ 1, d);
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < XC; ++jj) {
+                            const int rr = r0 + i, cc = c0 + jj;
+                            if (rr < N && cc < N) {
+                                double2 v = make_double2(h * acc[i][jj].x, h * acc[i][jj].y);  // X (.) = h A (.)
+                                if (d < 0) {
+                                    v = make_double2((rr == cc ? 1.0 : 0.0) + r * v.x, r * v.y);
+                                } else {
+                                    if (d < nd) {  // + h A_j P
+                                        double2 s2 = make_double2(0.0, 0.0);
+                                        const int eo = (d * 2) * N * W + rr * W;
+                                        for (int u = 0; u < W; ++u) cfma(s2, ellv[eo + u], XP(cur)[ellc[eo + u] + NP * cc]);
+                                        v.x += h * s2.x; v.y += h * s2.y;
+                                    } else {       // + A P
+                                        v.x += acc2[i][jj].x; v.y += acc2[i][jj].y;
+                                    }
+                                    v = make_double2(r * v.x, r * v.y);
+                                }
+                                Cop[rr + NP * cc] = v;
+                            }
+                        }
+                }
+                GSYNC();
+                cur ^= 1;
+            }
+            // ---- outputs of this polynomial: P_0 V, T^d_0 V (accumulated), (T^d_0)^H M, iso block, Gamma_0 = V M^H ---------
+            {
+                const int nP = 1 + ndir + (needH ? ndir : 0);
+                const int nS = nP * tilesS, nDense = nS + (needH ? tilesX : 0);
+                for (int w = tid; w < nDense; w += nthreads) {
+                    if (w >= nS) {
+                        const int tl = w - nS;
+                        const int r0 = (tl / tcolsX) * QCK_TILE, c0 = (tl - (tl / tcolsX) * tcolsX) * XC;
+                        double2 acc[QCK_TILE][XC];
+                        tile_mm<XC>(V, false, MS(QS_M), true, nc, NP, r0, c0, acc);
+#pragma unroll
+                        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                            for (int jj = 0; jj < XC; ++jj) XG(0)[r0 + i + NP * (c0 + jj)] = acc[i][jj];
+                        continue;
+                    }
+                    const int pi = w / tilesS, tl = w - pi * tilesS;
+                    const int r0 = (tl / tcols) * QCK_TILE, c0 = (tl - (tl / tcols) * tcols) * TC;
+                    // product list: [P_0 V] [T^d_0 V]*ndir [(T^d_0)^H M]*ndir
+                    const bool adj = pi > ndir;
+                    const int d = pi == 0 ? -1 : (adj ? pi - 1 - ndir : pi - 1);
+                    double2 acc[QCK_TILE][TC];
+                    tile_mm<TC>(d < 0 ? XP(cur) : XJ(cur, d), adj, adj ? MS(QS_M) : V, false, N, NP, r0, c0, acc);
+                    int q1;
+                    if (!adj) q1 = d < 0 ? QO_R : (d < nd ? QO_TA + d : QO_TH);
+                    else if (pass == 0) q1 = d < nd ? QO_KA0 + d : QO_KH0;
+                    else q1 = d < nd ? QO_KA1 + d : QO_KH1;
+                    const int b1 = c.pl_base[q1], s1 = c.pl_stride[q1];
+                    // signs: R = B U1 - F U0 -> the F pass enters with -, the B pass with +; K0 = -(dF)^H M, K1 = +(dB)^H M
+                    const double sgn = pass == 0 ? -1.0 : 1.0;
+                    const bool accumulate = !adj && pass == 1;
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < TC; ++jj) {
+                            const int rr = r0 + i, cc = c0 + jj;
+                            if (rr < N && cc < nc && b1 >= 0) {
+                                const int ire = cc * n2 + rr;
+                                double vr = sgn * acc[i][jj].x, vi = sgn * acc[i][jj].y;
+                                if (accumulate) { vr += image[b1 + ire * s1]; vi += image[b1 + (ire + N) * s1]; }
+                                image[b1 + ire * s1] = vr;
+                                image[b1 + (ire + N) * s1] = vi;
+                            }
+                        }
+                }
+                if (needJ) {
+                    int first = ((nDense + 31) >> 5) << 5;
+                    if (first >= nthreads) first = 0;
+                    const int qb = pass == 0 ? QO_ISOF : QO_ISOB;
+                    for (int e = tid - first; e >= 0 && e < N * N; e += nthreads - first) {
+                        const int rr = e % N, cc = e / N;
+                        const double2 v = XP(cur)[rr + NP * cc];
+                        const double s = pass == 0 ? -1.0 : 1.0;
+                        const int k00 = rr + n2 * cc, k01 = rr + n2 * (cc + N);
+                        PUT(qb, k00, s * v.x); PUT(qb, k00 + N, s * v.y); PUT(qb, k01, -s * v.y); PUT(qb, k01 + N, s * v.x);
+                    }
+                }
+            }
+            // ---- reverse sweep: scalar second derivatives of Re <M, (B U1 - F U0)> ----------------------------------------------
+            if (needH) {
+                const double fs = pass == 0 ? -1.0 : 1.0;
+                int gb = 0;
+                for (int kk = 0; kk < mdeg; ++kk) {
+                    const double wk = fs * sg * c.pade_r[kk];
+                    const bool trivial = kk == mdeg - 1;  // level m: P = I, tangents = 0
+                    GSYNC();
+                    if (!trivial && taping) {
+                        const double2* tp = tape + (size_t)(kk * (1 + ndir)) * N * N;
+                        tape_get(XT, tp);
+                        for (int d = 0; d < ndir; ++d) tape_get(XJ(0, d), tp + (size_t)(1 + d) * N * N);
+                    }
+                    GSYNC();
+                    // Q^j = Lam A_j (sparse: walks row b of A_j^H), Q^h = Lam A (dense) -> XJ(1, .)
+                    for (int w = tid; w < tilesX; w += nthreads) {
+                        const int r0 = (w / tcolsX) * QCK_TILE, c0 = (w - (w / tcolsX) * tcolsX) * XC;
+                        double2 acc[QCK_TILE][XC];
+                        tile_mm<XC>(XG(gb), false, MA(QA_A), false, N, NP, r0, c0, acc);
+#pragma unroll
+                        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                            for (int jj = 0; jj < XC; ++jj)
+                                if (r0 + i < N && c0 + jj < N) XJ(1, nd)[r0 + i + NP * (c0 + jj)] = acc[i][jj];
+                    }
+                    {
+                        int first = ((tilesX + 31) >> 5) << 5;
+                        if (first >= nthreads) first = 0;
+                        for (int w = tid - first; w >= 0 && w < nd * N * N; w += nthreads - first) {
+                            const int i = w / (N * N), e = w - i * N * N;
+                            const int a = e % N, b = e / N;
+                            const int o1 = ((i * 2 + 1) * N + b) * W;
+                            double2 v = make_double2(0.0, 0.0);
+                            for (int u = 0; u < W; ++u) {
+                                double2 ah = ellv[o1 + u];
+                                ah.y = -ah.y;
+                                cfma(v, XG(gb)[a + NP * ellc[o1 + u]], ah);
+                            }
+                            XJ(1, i)[a + NP * b] = v;
+                        }
+                    }
+                    GSYNC();
+                    if (!trivial) {
+                        for (int j = 0; j < nd; ++j) {
+                            for (int i = 0; i <= j; ++i) {  // a_i x a_j: wk h (tr(Q^i T^j) + tr(Q^j T^i))
+                                tr_acc(i, j, wk * h, XJ(1, i), XJ(0, j));
+                                tr_acc(i, j, wk * h, XJ(1, j), XJ(0, i));
+                            }
+                            if (free_time) {  // a_j x h: wk (tr(Q^j P) + h tr(Q^j T^h) + tr(Q^h T^j))
+                                tr_acc(j, nd, wk, XJ(1, j), XT);
+                                tr_acc(j, nd, wk * h, XJ(1, j), XJ(0, nd));
+                                tr_acc(j, nd, wk, XJ(1, nd), XJ(0, j));
+                            }
+                        }
+                        if (free_time) tr_acc(nd, nd, 2.0 * wk, XJ(1, nd), XJ(0, nd));
+                    } else if (free_time) {  // P = I: only tr(Q^j) remains
+                        for (int j = 0; j < nd; ++j) {
+                            double s = 0.0;
+                            for (int a = tid; a < N; a += nthreads) s += XJ(1, j)[a + NP * a].x;
+                            hacc[nd * (nd + 1) / 2 + j] += wk * s;
+                        }
+                    }
+                    // Lam <- wk/fs * h * Lam A  (the sign fs belongs to the contraction, not to the recursion)
+                    GSYNC();
+                    {
+                        const double lam = sg * c.pade_r[kk] * h;
+                        for (int e = tid; e < N * N; e += nthreads) {
+                            const int o = (e % N) + NP * (e / N);
+                            const double2 q = XJ(1, nd)[o];
+                            XG(gb ^ 1)[o] = make_double2(lam * q.x, lam * q.y);
+                        }
+                    }
+                    gb ^= 1;
+                }
+                // hand the Gamma buffer back: the next pass writes its Gamma_0 into XG(0)
+                GSYNC();
+            }
+        }
+        if (needH) {
+            // block reduction of the pair sums and placement
+            GSYNC();
+            double* red = reinterpret_cast<double*>(MA(1));  // every N x N work matrix is free by now
+            const int npd = (ndir) * (ndir + 1) / 2;
+            for (int q = 0; q < npd; ++q) {
+                const double v = warp_sum(hacc[q]);
+                if (lane == 0) red[q * nwarps_ + warp] = v;
+            }
+            GSYNC();
+            if (tid < npd) {
+                double v = 0.0;
+                for (int w2 = 0; w2 < nwarps_; ++w2) v += red[tid * nwarps_ + w2];
+                int e2 = 0, rem = tid;
+                while (rem > e2) { rem -= e2 + 1; ++e2; }
+                const int d = rem;
+                const int qq = e2 < nd ? qo_haa(d, e2) : (d < nd ? QO_HAH + d : QO_HHH);
+                if (c.pl_base[qq] >= 0) image[c.pl_base[qq]] = v;
+            }
+        }
+        GSYNC();
+#undef XP
+#undef XJ
+#undef XT
+#undef XG
         }
         QCK_TICK(5);
 
@@ -993,7 +1257,8 @@ void qck_scratch_layout(QckClassDev& c) {
     c.mss = 2 * c.NP * c.ncp;
     c.off_A = 0;
     const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
-    c.off_S = c.off_A + (is_exp ? 4 + 2 * c.nd : QA_C + c.nd) * c.msa;
+    const bool is_paden = !is_exp && c.order != 4;
+    c.off_S = c.off_A + (is_exp ? 4 + 2 * c.nd : (is_paden ? 6 + 2 * (c.nd + 1) : QA_C + c.nd)) * c.msa;
     c.off_img = c.off_S + QS_COUNT * c.mss;
 }
 
@@ -1016,7 +1281,7 @@ int qck_pick_threads(const QckClassDev& c) {
     if (const char* e = getenv("QCK_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }  // tuning knob
     const int tc = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP) ? QCK_TILE : 1;
     int tilesS = (c.NP / QCK_TILE) * (c.ncp / tc);
-    const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP;
+    const bool is_exp = c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP || c.order != 4;  // (general-order Pade shares the exponential kernel's task shape)
     int items = is_exp ? (1 + c.nd) * (c.NP / QCK_TILE) * c.NP : (2 + 2 * c.nd) * tilesS;
     int th = ((items + 31) / 32) * 32 + (is_exp ? 0 : 32);  // Pade: one extra warp for the sparse products / scalar traces
     if (items <= 32 && !is_exp) th = 32;  // everything fits one warp: warp-sized groups, several items per CTA
@@ -1056,9 +1321,11 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     qck_kernel_t kern = nullptr;
     int tc = unitary ? QCK_TILE : 1;
     const bool is_pade = c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE;
-    const bool multi = is_pade && c.threads == 32;  // warp-sized groups: four independent items per CTA
+    const bool multi = is_pade && c.order == 4 && c.threads == 32;  // warp-sized groups: four independent items per CTA
     if (c.kind == QCK_UNITARY_PADE && c.order == 4) kern = kernel_for<QK_PADE4, QCK_TILE>(c.N, multi);
     else if (c.kind == QCK_KET_PADE && c.order == 4) kern = kernel_for<QK_PADE4, 1>(c.N, multi);
+    else if (c.kind == QCK_UNITARY_PADE) kern = kernel_for<QK_PADEN, QCK_TILE>(c.N, false);
+    else if (c.kind == QCK_KET_PADE) kern = kernel_for<QK_PADEN, 1>(c.N, false);
     else if (c.kind == QCK_UNITARY_EXP) kern = kernel_for<QK_EXP, QCK_TILE>(c.N, multi);
     else if (c.kind == QCK_KET_EXP) kern = kernel_for<QK_EXP, 1>(c.N, multi);
     else return (int)cudaErrorNotSupported;

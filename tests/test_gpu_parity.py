@@ -86,3 +86,16 @@ def test_exponential_large_norm():
     traj = wl.random_pulse_trajectory([sys_], 4, 1.5, seed=11)
     check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=False)
     check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=True)
+
+
+@pytest.mark.parametrize("order", [6, 8, 10, 12])
+@pytest.mark.parametrize("name,kw", [("hadamard", {"T": 5}), ("hadamard", {"T": 4, "free_time": False}), ("cz", {"T": 3}), ("ket", {"T": 5})])
+def test_general_pade_orders(order, name, kw):
+    """UnitaryPadeIntegrator(...; order) for the other orders the reference's PADE_COEFFICIENTS cover:
+    ratio-form Horner with tangents + reverse sweep for the Hessian, against the oracle's explicit power sums."""
+    systems, traj, integrators = wl.config(name, **kw)
+    ket = name == "ket"
+    integrators = wl.build_integrators(systems, traj, order=order, ket=ket)
+    check(systems, traj, integrators)
+    if name == "hadamard":
+        check(systems, traj, integrators, eval_hessian=False)

@@ -200,12 +200,16 @@ def test_edge_cases():
 
 
 @pytest.mark.parametrize("name,T,integ", [("cz", 2500, "pade"), ("hadamard", 5000, "pade"), ("ket", 3000, "pade"), ("cz", 1300, "exponential"),
-                                          ("hadamard", 4000, "exponential")])
+                                          ("hadamard", 4000, "exponential"), ("cz", 1300, "pade8")])
 def test_every_block_when_ctas_loop_over_many_items(name, T, integ):
     """More work items than resident CTAs: the persistent loop + prefetch path.  Every block is compared with the C port
     of the oracle (Pade) or the numpy oracle on a strided sample (exponential)."""
     from oracle.c_port import CPort
-    systems, traj, integrators = wl.config(name, T=T, integrator=integ)
+    order = int(integ[4:]) if integ.startswith("pade") and len(integ) > 4 else 4
+    kind = "pade" if integ.startswith("pade") else integ
+    systems, traj, integrators = wl.config(name, T=T, integrator=kind)
+    if order != 4:
+        integrators = wl.build_integrators(systems, traj, order=order)
     D = qcknot.QuantumDynamics(integrators, traj)
     Z, mu = traj.datavec, wl.random_multipliers(D.n_blocks * D.dyn)
     F, J, H = D.eval_all(Z, mu)
@@ -215,7 +219,7 @@ def test_every_block_when_ctas_loop_over_many_items(name, T, integ):
     else:
         for t in range(0, D.n_blocks, 97):
             sub = qcknot.NamedTrajectory({n: traj[n][:, t:t + 2] for n in traj.names}, controls=("dda", "Δt"), timestep="Δt")
-            O = oracle_dynamics(wl.build_integrators(systems, sub, integrator=integ), sub)
+            O = oracle_dynamics(wl.build_integrators(systems, sub, integrator=kind, order=order), sub)
             assert rel_err(F[t * D.dyn:(t + 1) * D.dyn], O.F(sub.datavec)) < TOL
             assert rel_err(J[t * D.nnzJ:(t + 1) * D.nnzJ], O.dF(sub.datavec)) < TOL
             assert rel_err(H[t * D.nnzH:(t + 1) * D.nnzH], O.mu_d2F(sub.datavec, mu[t * D.dyn:(t + 1) * D.dyn])) < TOL

@@ -111,7 +111,7 @@ def test_bad_arguments_are_errors_not_crashes():
         qcknot.UnitaryPadeIntegrator("nope", "a", systems[0], traj)
     with pytest.raises(ValueError):  # state length inconsistent with the system's levels
         qcknot.UnitaryPadeIntegrator("a", "a", systems[0], traj)
-    bad = qcknot.UnitaryPadeIntegrator("Ũ⃗", "a", systems[0], traj, order=5)
+    bad = qcknot.UnitaryPadeIntegrator("Ũ⃗", "a", systems[0], traj, order=14)
     with pytest.raises(qcknot.QcknotError, match="order"):
         qcknot.QuantumDynamics([bad], traj, device=-1)
     # raw ABI: NULL description
