@@ -468,10 +468,18 @@ int build(qck_handle* h) {
         }
         if (N > 255) return fail(h, QCK_EINVAL, "levels > 255 unsupported");
         c.kk_cap = kk_cap;
+        int ac_cap = 0;
+        for (int q : C.members) {
+            const Integ& I = h->integ[q];
+            int tot = 0;
+            for (size_t e2 = 0; e2 < I.Hdrives.size(); ++e2) tot += I.Hdrives[e2] != 0.0;
+            ac_cap = std::max(ac_cap, tot);
+        }
+        c.ac_cap = ac_cap;
         qck_smem_finalize(c);
         if ((size_t)c.sm_bytes > 227 * 1024 - 4096)
             return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024 - 4096);
-        c.cmat_stride = N * N + c.ell_stride + kk_cap;
+        c.cmat_stride = N * N + c.ell_stride + kk_cap + ac_cap;
         std::vector<double2> cmat((size_t)nm * c.cmat_stride, make_double2(0.0, 0.0));
         std::vector<int> icon((size_t)nm * c.icon_stride, 0);
         std::vector<int> moff(3 * (size_t)nm);
@@ -508,6 +516,19 @@ int build(qck_handle* h) {
                 for (auto& t : kk[m2][pidx]) { krc[u] = t.first; kv[u] = make_double2(t.second.real(), t.second.imag()); ++u; }
             }
             kptr[npair] = u;
+            // per-element contributor lists: A[e] = A0[e] + sum over (j, -i H_j[e]) with H_j[e] != 0
+            double2* av = kv + kk_cap;
+            int* aptr = krc + kk_cap;
+            int* aj = aptr + N * N + 1;
+            int au = 0;
+            for (int e2 = 0; e2 < N * N; ++e2) {
+                aptr[e2] = au;
+                for (int j = 0; j < nd; ++j) {
+                    const std::complex<double> hv = I.Hdrives[(size_t)j * N * N + e2];
+                    if (hv != 0.0) { av[au] = minus_i(hv); aj[au] = j; ++au; }
+                }
+            }
+            aptr[N * N] = au;
         }
         cudaError_t e;
         if ((e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||

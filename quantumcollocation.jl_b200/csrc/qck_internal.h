@@ -72,12 +72,13 @@ struct QckClassDev {
     short pl_stride[QO_COUNT];
     // per member
     const int* moff;      // [member][state_off, ctrl_off, row_off]
-    const double2* cmat;  // [member][A0: N*N | ell_val: nd*2*N*W | kk_val: kk_cap]
+    const double2* cmat;  // [member][A0: N*N | ell_val: nd*2*N*W | kk_val: kk_cap | ac_val: ac_cap]
     int cmat_stride;
-    const int* ell_col;   // [member][ell_col: nd*2*N*W | kk_ptr: npair+1 | kk_rc: kk_cap]   (kk = sparse {A_i, A_j})
+    const int* ell_col;   // [member][ell_col: nd*2*N*W | kk_ptr: npair+1 | kk_rc: kk_cap | ac_ptr: N*N+1 | ac_j: ac_cap]
     int ell_stride;       // nd*2*N*W
     int icon_stride;      // ints per member in ell_col
     int kk_cap;
+    int ac_cap;           // total nonzeros of the drives (per-element contributor lists of A)
     // write-out units per member: [member][QCK_SEG_HDR ints | nseg units], balanced over `threads`/32 warps
     int nseg, threads;
     const QckSeg* segs;  // (QCK_SEG_HDR/4 + nseg) QckSeg-sized records per member

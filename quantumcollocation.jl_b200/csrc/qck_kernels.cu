@@ -273,13 +273,13 @@ qck_quantum_kernel(const QckLaunch p) {
     const int* moff = p.moff_smem ? reinterpret_cast<const int*>(cta_shared + p.n_aux * (int)sizeof(QckAux)) : p.moff_global;
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;  // 16-byte records of the per-member write-out table
     const int lane = tid & 31, warp = tid >> 5, nwarps_ = nthreads >> 5;
-    const int elln = c.ell_stride, kkc = c.kk_cap;
+    const int elln = c.ell_stride, kkc = c.kk_cap, acc_n = c.ac_cap;
     const int msa = NP * NP, mss = NP * ncp;  // complex elements per matrix
 #define MA(i) (SA + (i) * msa)
 #define MS(i) (SS + (i) * mss)
 #define SEGBUF(b) reinterpret_cast<QckSeg*>(smem_raw + c.sm_seg + (b) * c.seg_bytes)
 #define CONV(b) reinterpret_cast<double2*>(smem_raw + c.sm_con + (b) * c.con_bytes)
-#define CONI(b) reinterpret_cast<int*>(smem_raw + c.sm_con + (b) * c.con_bytes + (N * N + elln + kkc) * 16)
+#define CONI(b) reinterpret_cast<int*>(smem_raw + c.sm_con + (b) * c.con_bytes + (N * N + elln + kkc + acc_n) * 16)
 #define PUT(q, i, v) image[c.pl_base[q] + (i) * c.pl_stride[q]] = (v)
 
     const long long n_items = p.n_knots * nact;
@@ -318,7 +318,7 @@ qck_quantum_kernel(const QckLaunch p) {
             for (int i = tid; i < nrec; i += nthreads) cp_async16(SEGBUF(b) + i, gs + i);
             const double2* gv = c.cmat + (size_t)m * c.cmat_stride;  // [A0 | ell_val | kk_val]
             const int* gc = c.ell_col + (size_t)m * c.icon_stride;
-            for (int i = tid; i < N * N + elln + kkc; i += nthreads) cp_async16(CONV(b) + i, gv + i);
+            for (int i = tid; i < N * N + elln + kkc + acc_n; i += nthreads) cp_async16(CONV(b) + i, gv + i);
             for (int i = tid; i < c.icon_stride; i += nthreads) cp_async4(CONI(b) + i, gc + i);
         }
         cp_async_commit();
@@ -353,6 +353,9 @@ qck_quantum_kernel(const QckLaunch p) {
         const int* ellc = CONI(buf);
         const int* kkptr = CONI(buf) + elln;
         const int* kkrc = kkptr + npair + 1;
+        const double2* acv = kkv + kkc;        // per-element contributors of A = A0 + sum_j a_j A_j
+        const int* acptr = kkrc + kkc;
+        const int* acj = acptr + N * N + 1;
         const int* seghdr = reinterpret_cast<const int*>(SEGBUF(buf));
         const QckSeg* segs = SEGBUF(buf) + QCK_SEG_HDR / 4;
         const double h = free_time ? stage[3 * dim + nd] : c.dt_fixed;
@@ -372,25 +375,16 @@ qck_quantum_kernel(const QckLaunch p) {
                 reinterpret_cast<double*>(MS(QS_S))[o] = KIND != QK_PADE4 ? u1 : u1 + u0;
                 if (needH) reinterpret_cast<double*>(MS(QS_M))[o] = stage[2 * dim + idx];
             }
-            if (warp == nwarps_ - 1) {
-                // A = A0 + sum_j a_j A_j on the last warp: dense copy of the drift, then one sparse update per drive
-                // (entries of one drive never collide; zero-padded entries are skipped)
-                for (int e = lane; e < N * N; e += 32) MA(QA_A)[(e % N) + NP * (e / N)] = A0[e];
-                __syncwarp();
-                for (int j = 0; j < nd; ++j) {
-                    const double aj = stage[3 * dim + j];
-                    for (int e = lane; e < N * W; e += 32) {
-                        const double2 v = ellv[(j * 2) * N * W + e];
-                        if (v.x != 0.0 || v.y != 0.0) {
-                            double2* ap = MA(QA_A) + (e / W) + NP * ellc[(j * 2) * N * W + e];
-                            double2 a = *ap;
-                            a.x = fma(aj, v.x, a.x);
-                            a.y = fma(aj, v.y, a.y);
-                            *ap = a;
-                        }
-                    }
-                    __syncwarp();
+            // A = A0 + sum_j a_j A_j: every element gathers its own (host-listed) drive contributions, no ordering constraints
+            for (int e = nthreads - 1 - tid; e < N * N; e += nthreads) {
+                double2 v = A0[e];
+                for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
+                    const double aj = stage[3 * dim + acj[u]];
+                    const double2 d = acv[u];
+                    v.x = fma(aj, d.x, v.x);
+                    v.y = fma(aj, d.y, v.y);
                 }
+                MA(QA_A)[(e % N) + NP * (e / N)] = v;
             }
         }
         GSYNC();
@@ -1268,11 +1262,11 @@ void qck_smem_finalize(QckClassDev& c) {
     const int dim = 2 * c.N * c.nc;
     const int npair = c.nd * (c.nd + 1) / 2;
     c.scratch_doubles = (c.off_img + c.img_doubles + 1) & ~1;
-    c.icon_stride = c.ell_stride + npair + 1 + c.kk_cap;
+    c.icon_stride = c.ell_stride + npair + 1 + c.kk_cap + c.N * c.N + 1 + c.ac_cap;
     c.sm_seg = al(c.scratch_doubles * 8);
     c.seg_bytes = al((QCK_SEG_HDR / 4 + c.nseg) * (int)sizeof(QckSeg));
     c.sm_con = c.sm_seg + c.n_tbuf * c.seg_bytes;
-    c.con_bytes = al((c.N * c.N + c.ell_stride + c.kk_cap) * 16 + c.icon_stride * 4);
+    c.con_bytes = al((c.N * c.N + c.ell_stride + c.kk_cap + c.ac_cap) * 16 + c.icon_stride * 4);
     c.sm_stage = c.sm_con + c.n_tbuf * c.con_bytes;
     c.sm_bytes = al(c.sm_stage + (3 * dim + c.nd + 1) * 8);
 }
