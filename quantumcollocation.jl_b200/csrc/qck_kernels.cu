@@ -413,7 +413,40 @@ qck_quantum_kernel(const QckLaunch p) {
             const int nS = (needH && free_time ? 2 : 1) * tilesS;
             const int nDense = nA + nS;
             for (int w = vtid; w < nDense; w += nthreads) {
-                if (w < nA) {
+                if constexpr (TC == QCK_TILE) {
+                    // unitaries: every stage-1 product is an N x N x K product in 3 x 3 tiles -> ONE instruction stream for the
+                    // whole warp (separate A-type / state-type branches would run one after the other inside a warp)
+                    const int pi = w / tilesA, tl = w - pi * tilesA;
+                    const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
+                    // product list: [A A] [D M^H] [S M^H] (1 + nG of them), then [A S] [A^H M]
+                    const int ps = pi - (1 + nG);  // >= 0: state-type product
+                    const double2* Aop = ps >= 0 ? MA(QA_A) : (pi == 0 ? MA(QA_A) : (pi == 1 ? MS(QS_D) : MS(QS_S)));
+                    const double2* Bop = ps >= 0 ? (ps == 0 ? MS(QS_S) : MS(QS_M)) : (pi == 0 ? MA(QA_A) : MS(QS_M));
+                    double2* Cop = ps >= 0 ? MS(ps == 0 ? QS_AS : QS_AHM) : MA(pi == 0 ? QA_A2 : (pi == 1 ? QA_G : QA_G2));
+                    double2 acc[QCK_TILE][QCK_TILE];
+                    tile_mm<QCK_TILE>(Aop, ps == 1, Bop, ps < 0 && pi != 0, N, NP, r0, c0, acc);
+#pragma unroll
+                    for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                        for (int j = 0; j < QCK_TILE; ++j) Cop[r0 + i + NP * (c0 + j)] = acc[i][j];
+                    if (pi == 0 && needJ) {
+#pragma unroll
+                        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+                            for (int j = 0; j < QCK_TILE; ++j) {
+                                const int r = r0 + i, cc = c0 + j;
+                                if (r < N && cc < N) {
+                                    const double2 a = MA(QA_A)[r + NP * cc];
+                                    const double id = r == cc ? 1.0 : 0.0;
+                                    const double fr = id + c1h * a.x + c2h2 * acc[i][j].x, fi = c1h * a.y + c2h2 * acc[i][j].y;
+                                    const double br = id - c1h * a.x + c2h2 * acc[i][j].x, bi = -c1h * a.y + c2h2 * acc[i][j].y;
+                                    const int k00 = r + n2 * cc, k01 = r + n2 * (cc + N);
+                                    PUT(QO_ISOF, k00, -fr); PUT(QO_ISOF, k00 + N, -fi); PUT(QO_ISOF, k01, fi); PUT(QO_ISOF, k01 + N, -fr);
+                                    PUT(QO_ISOB, k00, br);  PUT(QO_ISOB, k00 + N, bi);  PUT(QO_ISOB, k01, -bi); PUT(QO_ISOB, k01 + N, br);
+                                }
+                            }
+                    }
+                } else if (w < nA) {
                     const int pi = w / tilesA, tl = w - pi * tilesA;
                     const int r0 = (tl / tcolsA) * QCK_TILE, c0 = (tl - (tl / tcolsA) * tcolsA) * QCK_TILE;
                     double2 acc[QCK_TILE][QCK_TILE];
