@@ -117,6 +117,7 @@ struct QckLaunch {
     int group_threads;       // threads cooperating on one work item (set by the launcher)
     int group_smem;          // bytes of shared memory per group
     long long* timing;       // optional per-stage cycle counters (debug)
+    unsigned stagger_ns;     // start-up delay step between the CTAs of one SM
 };
 
 struct QckReduce {  // fixed-order reduction of shared Hessian positions

@@ -84,6 +84,12 @@ __device__ __forceinline__ double2 ell_row(const double2* __restrict__ val, cons
     return acc;
 }
 
+// FP64 tensor-core tile product: D(8x8) += A(8x4, row-major fragment) * B(4x8, column fragment).  Lane (g = lane/4,
+// t = lane%4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ double warp_sum(double s) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -148,49 +154,89 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// TMA bulk copy shared -> global (one thread issues; the copy engine drains the image while the CTA computes on)
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (the bulk copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // Write-out: every unit is nrep back-to-back contiguous copies image -> value array, owned by ONE warp (the host
-// balanced the units over the warps).  Consecutive lanes store consecutive positions; 16-byte loads/stores whenever
-// the destination is 16-byte aligned (unit image offsets are always even), 8-byte otherwise.
+// balanced the units over the warps).  Consecutive lanes store consecutive positions with 16-byte stores; a destination
+// that sits at 8 mod 16 takes a scalar head/tail and pairs shifted by one double.  Repeated (kron(I_N, .)) blocks of
+// the compile-time size 2*HPC doubles are read ONCE into registers and stored nrep times (no loads, no index wrap in
+// the store loop); all loops are kept free of integer division and of per-element address arithmetic.
+#define QCK_BULK_STORE 1
+template <int HPC>
 __device__ __forceinline__ void write_units(const double* __restrict__ image, const QckSeg* __restrict__ segs, int s0, int s1,
                                             const QckLaunch& p, long long t, int lane) {
+    double* const baseF = p.F + t * p.c.dyn;
+    double* const baseJ = p.J + t * p.nnzJ;
+    double* const baseH = p.H + t * p.nnzH;
+    double* const baseP = p.partial + t * p.npart - p.nnzH;
     for (int s = s0; s < s1; ++s) {
         const QckSeg sg = segs[s];
         const int arr = sg.arr & 255;
         if (!((p.mask >> arr) & 1u)) continue;
-        double* dst;
-        if (arr == 0) dst = p.F + t * p.c.dyn + sg.dst;
-        else if (arr == 1) dst = p.J + t * p.nnzJ + sg.dst;
-        else dst = (long long)sg.dst < p.nnzH ? p.H + t * p.nnzH + sg.dst : p.partial + t * p.npart + (sg.dst - p.nnzH);
+        double* dst = (arr == 0 ? baseF : (arr == 1 ? baseJ : ((long long)sg.dst < p.nnzH ? baseH : baseP))) + sg.dst;
         const double* src = image + (sg.img_nrep & 0xffff);
         const int nrep = sg.img_nrep >> 16, n = sg.n;
         const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
-        if (!odd && !(n & 1)) {
-            // 16-byte path: the destination is walked linearly (nrep * n/2 pairs), the source index wraps every n/2 pairs
-            // (the wrap step 32 mod n/2 comes precomputed with the unit: no integer division here)
-            const int hp = n >> 1, total = hp * nrep, step = sg.arr >> 8;
-            const double2* s2 = reinterpret_cast<const double2*>(src);
-            double2* d2 = reinterpret_cast<double2*>(dst) + lane;
-            int k = lane;
-            while (k >= hp) k -= hp;
-#pragma unroll 2
-            for (int idx = lane; idx < total; idx += 32) {
-                *d2 = s2[k];
-                d2 += 32;
-                k += step;
-                if (k >= hp) k -= hp;
-            }
+        if (nrep == 1 && !odd && !(n & 1) && QCK_BULK_STORE) {
+            if (lane == 0) bulk_store(dst, src, (unsigned)n * 8u);
         } else if (nrep == 1) {
-            // misaligned and/or odd length: scalar head / tail, 16-byte body
+            // plain run: scalar head (misaligned destination) / tail, 16-byte body
             const int head = odd ? 1 : 0;
             const int pairs = (n - head) >> 1;
-            double2* d2 = reinterpret_cast<double2*>(dst + head);
-            const double* sh = src + head;
             if (lane == 31) {
                 if (head) dst[0] = src[0];
                 if (head + 2 * pairs < n) dst[n - 1] = src[n - 1];
             }
-            for (int k = lane; k < pairs; k += 32) d2[k] = make_double2(sh[2 * k], sh[2 * k + 1]);
+            double2* d2 = reinterpret_cast<double2*>(dst + head) + lane;
+            int k = lane;
+            if (!head) {
+                const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
+                for (; k + 96 < pairs; k += 128, s2 += 128, d2 += 128) {
+                    const double2 v0 = s2[0], v1 = s2[32], v2 = s2[64], v3 = s2[96];
+                    d2[0] = v0; d2[32] = v1; d2[64] = v2; d2[96] = v3;
+                }
+                for (; k < pairs; k += 32, s2 += 32, d2 += 32) *d2 = *s2;
+            } else {
+                const double* sh = src + 1 + 2 * lane;
+                for (; k + 32 < pairs; k += 64, sh += 128, d2 += 64) {
+                    const double a0 = sh[0], a1 = sh[1], b0 = sh[64], b1 = sh[65];
+                    d2[0] = make_double2(a0, a1); d2[32] = make_double2(b0, b1);
+                }
+                for (; k < pairs; k += 32, sh += 64, d2 += 32) *d2 = make_double2(sh[0], sh[1]);
+            }
+        } else if (!odd && !(n & 1) && QCK_BULK_STORE) {
+            if (lane == 0)
+                for (int r = 0; r < nrep; ++r) bulk_store(dst + (size_t)r * n, src, (unsigned)n * 8u);
+        } else if (!odd && !(n & 1)) {
+            const int hp = n >> 1;
+            const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
+            double2* d2 = reinterpret_cast<double2*>(dst) + lane;
+            if (HPC > 0 && hp == HPC) {
+                constexpr int NV = HPC > 0 ? (HPC + 31) / 32 : 1;
+                double2 v[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (32 * (i + 1) <= HPC || lane + 32 * i < HPC) v[i] = s2[32 * i];
+                for (int r = 0; r < nrep; ++r, d2 += HPC) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+                        if (32 * (i + 1) <= HPC || lane + 32 * i < HPC) d2[32 * i] = v[i];
+                }
+            } else {
+                for (int r = 0; r < nrep; ++r, d2 += hp) {
+#pragma unroll 2
+                    for (int k = lane; k < hp; k += 32) d2[k - lane] = s2[k - lane];
+                }
+            }
         } else {
             const int total = n * nrep, step = 32 % n;  // rare path (odd period or misaligned repeated block)
             int k = lane % n;
@@ -237,6 +283,9 @@ qck_quantum_kernel(const QckLaunch p) {
     // its own slice of shared memory.  Large problems use one group per CTA (block barrier); for small level counts a
     // group is a single warp (warp barrier only), so several items per CTA progress independently of one another.
     extern __shared__ __align__(16) unsigned char smem_all[];
+    // FP64 tensor-core (DMMA) variant of the Pade-4 unitary path for 9 levels (see the DM block below)
+    constexpr bool DM = KIND == QK_PADE4 && TC == QCK_TILE && CN == 9 && !MULTI;
+    constexpr int QDM_LD = 2 * (CN + 1);
     // (MULTI is a template parameter so that the single-group kernels keep absolute shared-memory addressing)
     const int G = MULTI ? 32 : (int)blockDim.x, grp = MULTI ? (int)(threadIdx.x >> 5) : 0, ngroups = MULTI ? (int)(blockDim.x >> 5) : 1;
     unsigned char* smem_raw = MULTI ? smem_all + (size_t)grp * p.group_smem : smem_all;
@@ -324,6 +373,10 @@ qck_quantum_kernel(const QckLaunch p) {
         cp_async_commit();
     };
 
+    if (p.stagger_ns) {  // de-phase the CTAs that share an SM (they run identical sequences and would otherwise stay in lockstep)
+        const unsigned k = blockIdx.x / (unsigned)p.sm_count;
+        for (unsigned i = 0; i < k; ++i) __nanosleep(p.stagger_ns);
+    }
     for (int i = tid; i < c.scratch_doubles; i += nthreads) sm[i] = 0.0;
     for (int i = threadIdx.x; i < p.n_aux; i += blockDim.x) auxs[i] = p.aux[i];
     if (p.moff_smem)
@@ -365,7 +418,31 @@ qck_quantum_kernel(const QckLaunch p) {
         // (the derivative-integrator entries depend on the staged inputs only: written now, before the next prefetch
         //  reuses the staging buffers)
         if (mi == 0 && p.n_aux) do_aux_staged(p, auxs, auxv, h, t, tid, nthreads);
-        {
+        if constexpr (DM) {
+            // tensor-core path: every matrix is row-major complex with QDM_LD doubles per row (fragment loads are then free
+            // of bank conflicts); [D; S] and [A2; C_1 .. C_nd] are stacked so that they form ONE left operand each
+            double* const mA = sm;
+            double* const mD = sm + (1 + (1 + nd) + 2) * N * QDM_LD;
+            double* const mM = mD + 2 * N * QDM_LD;
+            for (int e = tid; e < N * N; e += nthreads) {
+                const int n = e % N, r = e / N;  // column index fastest: conflict-free 16-byte stores
+                const double u0r = stage[n * n2 + r], u0i = stage[n * n2 + N + r];
+                const double u1r = stage[dim + n * n2 + r], u1i = stage[dim + n * n2 + N + r];
+                *reinterpret_cast<double2*>(mD + r * QDM_LD + 2 * n) = make_double2(u1r - u0r, u1i - u0i);
+                *reinterpret_cast<double2*>(mD + (N + r) * QDM_LD + 2 * n) = make_double2(u1r + u0r, u1i + u0i);
+                if (needH) *reinterpret_cast<double2*>(mM + r * QDM_LD + 2 * n) = make_double2(stage[2 * dim + n * n2 + r], stage[2 * dim + n * n2 + N + r]);
+            }
+            for (int e = nthreads - 1 - tid; e < N * N; e += nthreads) {
+                double2 v = A0[e];
+                for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
+                    const double aj = stage[3 * dim + acj[u]];
+                    const double2 d = acv[u];
+                    v.x = fma(aj, d.x, v.x);
+                    v.y = fma(aj, d.y, v.y);
+                }
+                *reinterpret_cast<double2*>(mA + (e % N) * QDM_LD + 2 * (e / N)) = v;
+            }
+        } else {
             for (int idx = tid; idx < dim; idx += nthreads) {  // the last warp joins once A is built
                 int cc = idx / n2, q = idx - cc * n2;
                 int im = q >= N, r = q - im * N;
@@ -387,6 +464,7 @@ qck_quantum_kernel(const QckLaunch p) {
                 MA(QA_A)[(e % N) + NP * (e / N)] = v;
             }
         }
+        if (QCK_BULK_STORE && lane == 0) bulk_wait_read();  // the copy engine has finished reading the previous item's image
         GSYNC();
         QCK_TICK(2);
         // staging is free again: fetch the next item's inputs (and tables, if its member differs) behind the compute
@@ -405,7 +483,284 @@ qck_quantum_kernel(const QckLaunch p) {
         }
 
         QCK_TICK(3);
-        if constexpr (KIND == QK_PADE4) {
+        if constexpr (DM) {
+        // ============================ Pade-4, unitaries, FP64 tensor cores (DMMA m8n8k4) ====================================
+        // Complex products run as REAL tile products on the tensor cores.  For Z = X Y (X: m x N, Y: N x n complex):
+        //     [Zr Zi] = [Xr Xi] [[Yr Yi]; [-Yi Yr]]     with interleaved real indices  k' = 2c + (im),  n' = 2n + (im),
+        // so the left operand IS the row-major complex storage of X, the right operand is read from the complex storage of Y
+        // with a per-lane sign, and lane (g, t) of an 8 x 8 accumulator tile holds the complete complex Z[8i + g][4j + t].
+        // Conjugate-transposed left operands (X^H Y) read the storage of X transposed and fold the conjugation into the sign
+        // pattern of the right operand; Y = M^H is read from the storage of M likewise.  K = 2N = 18 is padded to 20: the
+        // two padding k' of the last step are masked to zero in both fragments.
+        //   stage 1:  warp 0: A [A | S] -> A2 (stored), AS (kept in registers for stage 2)
+        //             warp 1: [D; S] M^H -> G, G2              warp 2: A^H M -> AhM (registers)
+        //             warps 3 (+2, or 1..3 without a Hessian): C_j = A_j A + A A_j (sparse)
+        //   stage 2:  warps 0, 1: [A2; C_j] D   -> R, d/dh, d/da_j         (rows split between the two warps)
+        //             warps 2, 3: [A2; C_j]^H M -> state x dt, state x a_j Hessian blocks
+        //             then the scalar traces and the -iso(F) / iso(B) blocks on all warps
+        constexpr int LD = QDM_LD, KS = (2 * CN + 3) / 4, NT = (2 * CN + 7) / 8, MTW = 3;
+        double* const mA = sm;
+        double* const mX = sm + N * LD;
+        const int mrows = (1 + nd) * N;
+        double* const mG = mX + mrows * LD;
+        double* const mD = mG + 2 * N * LD;
+        double* const mS = mD + N * LD;
+        double* const mM = mD + 2 * N * LD;
+        const int g = lane >> 2, tq = lane & 3;
+        const int aoff = g * LD + tq;                                       // left operand, row-major storage
+        const int atoff = (tq >> 1) * LD + 2 * g + (tq & 1);               // left operand = transpose of the storage
+        const int boff = (tq >> 1) * LD + 2 * (g >> 1) + ((g ^ tq) & 1);   // right operand from Y[c][n] storage
+        const int btoff = (g >> 1) * LD + 2 * (tq >> 1) + ((g ^ tq) & 1);  // right operand from storage indexed [n][c]
+        const double sN = ((tq & 1) && !(g & 1)) ? -1.0 : 1.0;             // X Y
+        const double sC = ((tq & 1) && (g & 1)) ? -1.0 : 1.0;              // X^H Y (left read transposed, unconjugated)
+        const double sH = (!(tq & 1) && (g & 1)) ? -1.0 : 1.0;             // X M^H (right read from M[n][c])
+        const bool kpad = 2 * CN - 4 * (KS - 1) <= tq;                     // this lane's k' of the last step is padding
+        double keep[2][NT][2];  // AS (warp 0) / AhM (warp 2): rows 8i + g, columns 4j + t, for the stage-2 epilogues
+        {
+            if (warp == 0) {
+                double acc[2][2 * NT][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2 * NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const bool z = ks == KS - 1 && kpad;
+                    double a[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) a[i] = z ? 0.0 : mA[i * 8 * LD + aoff + 4 * ks];
+#pragma unroll
+                    for (int j = 0; j < 2 * NT; ++j) {
+                        const double* Y = j < NT ? mA : mS;
+                        const double b = z ? 0.0 : sN * Y[2 * ks * LD + 8 * (j % NT) + boff];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) dmma884(acc[i][j], a[i], b);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const int row = 8 * i + g, col = 4 * j + tq;
+                        if (row < N && col < N) *reinterpret_cast<double2*>(mX + row * LD + 2 * col) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        keep[i][j][0] = acc[i][NT + j][0];
+                        keep[i][j][1] = acc[i][NT + j][1];
+                    }
+            } else if (warp == 1 && needH) {
+                double acc[3][NT][2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const bool z = ks == KS - 1 && kpad;
+                    double a[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) a[i] = z ? 0.0 : mD[i * 8 * LD + aoff + 4 * ks];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double b = z ? 0.0 : sH * mM[4 * j * LD + 4 * ks + btoff];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) dmma884(acc[i][j], a[i], b);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const int row = 8 * i + g, col = 4 * j + tq;
+                        if (row < 2 * N && col < N) *reinterpret_cast<double2*>(mG + row * LD + 2 * col) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    }
+            } else if (warp == 2 && needH) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) keep[i][j][0] = keep[i][j][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const bool z = ks == KS - 1 && kpad;
+                    double a[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) a[i] = z ? 0.0 : mA[2 * ks * LD + 16 * i + atoff];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double b = z ? 0.0 : sC * mM[2 * ks * LD + 8 * j + boff];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) dmma884(keep[i][j], a[i], b);
+                    }
+                }
+            }
+            if (needT && warp >= (needH ? 2 : 1)) {
+                // C_j[r][c] = sum_u A_j[r, k_u] A[k_u, c] + sum_u A[r, k_u] A_j[k_u, c]; the second sum walks row c of A_j^H.
+                // 32-element chunks are dealt to the warps the dense products leave free (two of three to warp 3 with a Hessian).
+                const int total = nd * N * N, nch = (total + 31) >> 5;
+                for (int ch = 0; ch < nch; ++ch) {
+                    const int owner = needH ? (ch % 3 == 2 ? 2 : 3) : 1 + ch % 3;
+                    if (owner != warp) continue;
+                    const int w = ch * 32 + lane;
+                    if (w >= total) continue;
+                    const int j = w / (N * N), e = w - j * N * N;
+                    const int r = e / N, cc = e - r * N;
+                    const int o0 = ((j * 2) * N + r) * W, o1 = ((j * 2 + 1) * N + cc) * W;
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int u = 0; u < W; ++u) {
+                        cfma(acc, ellv[o0 + u], *reinterpret_cast<const double2*>(mA + ellc[o0 + u] * LD + 2 * cc));
+                        double2 ah = ellv[o1 + u];
+                        ah.y = -ah.y;
+                        cfma(acc, *reinterpret_cast<const double2*>(mA + r * LD + 2 * ellc[o1 + u]), ah);
+                    }
+                    *reinterpret_cast<double2*>(mX + (N + j * N + r) * LD + 2 * cc) = acc;
+                }
+            }
+        }
+        GSYNC();
+        QCK_TICK(4);
+        {
+            const int mtiles = (mrows + 7) >> 3;
+            int mt_half = (mtiles + 1) >> 1;
+            if (mt_half < 2) mt_half = 2;  // rows 0 .. N-1 (they pair with `keep`) stay on warps 0 / 2
+            const bool is_b = warp >= 2;
+            const int mt_begin = (warp & 1) * mt_half;
+            const int mt_end = mt_begin + mt_half < mtiles ? mt_begin + mt_half : mtiles;
+            if (is_b ? needH : true)
+            for (int mt0 = mt_begin; mt0 < mt_end; mt0 += MTW) {  // (one pass for up to four drives)
+                const int mtn = mt_end - mt0 < MTW ? mt_end - mt0 : MTW;
+                double acc[MTW][NT][2];
+                int prow[MTW];  // (block p, row r) of this lane's row of m-tile i, packed p * 16 + r
+                int abase[MTW];
+#pragma unroll
+                for (int i = 0; i < MTW; ++i) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                    const int m = (mt0 + i) * 8 + g, pb = m / N, r = m - pb * N;
+                    prow[i] = pb * 16 + r;
+                    abase[i] = is_b ? pb * N * LD + 2 * r + (tq >> 1) * LD + (tq & 1) : m * LD + tq;
+                }
+                const int astep = is_b ? 2 * LD : 4;
+                const double* const Bm = is_b ? mM : mD;
+                const double sB = is_b ? sC : sN;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const bool z = ks == KS - 1 && kpad;
+                    double a[MTW];
+#pragma unroll
+                    for (int i = 0; i < MTW; ++i)
+                        if (i < mtn) a[i] = z ? 0.0 : mX[abase[i] + ks * astep];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double b = z ? 0.0 : sB * Bm[2 * ks * LD + 8 * j + boff];
+#pragma unroll
+                        for (int i = 0; i < MTW; ++i)
+                            if (i < mtn) dmma884(acc[i][j], a[i], b);
+                    }
+                }
+                // epilogue: out1 = extra + e1 E + x1 Z,  out2 = e2 E + x2 Z   (Z = accumulator, E = AS | AhM | A_j S | A_j^H M)
+#pragma unroll
+                for (int i = 0; i < MTW; ++i) {
+                    if (i >= mtn) continue;
+                    const int pb = prow[i] >> 4, r = prow[i] & 15, j = pb - 1;
+                    if (pb > nd) continue;
+                    double e1, x1, e2, x2;
+                    int q1, q2;
+                    if (!is_b && j < 0) { e1 = -c1h; x1 = c2h2; e2 = -0.5; x2 = c2h; q1 = QO_R; q2 = QO_TH; }
+                    else if (is_b && j < 0) { e1 = -0.5; x1 = -c2h; e2 = -0.5; x2 = c2h; q1 = QO_KH0; q2 = QO_KH1; }
+                    else if (!is_b) { e1 = -c1h; x1 = c2h2; e2 = 0.0; x2 = 0.0; q1 = QO_TA + j; q2 = -1; }
+                    else { e1 = -c1h; x1 = -c2h2; e2 = -c1h; x2 = c2h2; q1 = QO_KA0 + j; q2 = QO_KA1 + j; }
+                    const bool want2 = q2 >= 0 && c.pl_base[q2] >= 0;
+                    const int b1 = c.pl_base[q1], s1 = c.pl_stride[q1];
+                    const int b2 = q2 >= 0 ? c.pl_base[q2] : 0, s2 = q2 >= 0 ? c.pl_stride[q2] : 0;
+                    const double* const Es = is_b ? mM : mS;
+                    const int eo = j < 0 ? 0 : ((j * 2 + (is_b ? 1 : 0)) * N + r) * W;
+#pragma unroll
+                    for (int jt = 0; jt < NT; ++jt) {
+                        const int n = 4 * jt + tq;
+                        if (n >= N) continue;
+                        double2 E;
+                        if (j < 0) {
+                            E = make_double2(i < 2 ? keep[i < 2 ? i : 0][jt][0] : 0.0, i < 2 ? keep[i < 2 ? i : 0][jt][1] : 0.0);
+                        } else {
+                            E = make_double2(0.0, 0.0);
+                            for (int u = 0; u < W; ++u) cfma(E, ellv[eo + u], *reinterpret_cast<const double2*>(Es + ellc[eo + u] * LD + 2 * n));
+                        }
+                        const double zr = acc[i][jt][0], zi = acc[i][jt][1];
+                        double o1r = e1 * E.x + x1 * zr, o1i = e1 * E.y + x1 * zi;
+                        if (q1 == QO_R) { const double2 d = *reinterpret_cast<const double2*>(mD + r * LD + 2 * n); o1r += d.x; o1i += d.y; }
+                        const int ire = n * n2 + r;
+                        if (b1 >= 0) {
+                            image[b1 + ire * s1] = o1r;
+                            image[b1 + (ire + N) * s1] = o1i;
+                        }
+                        if (want2) {
+                            image[b2 + ire * s2] = e2 * E.x + x2 * zr;
+                            image[b2 + (ire + N) * s2] = e2 * E.y + x2 * zi;
+                        }
+                    }
+                }
+            }
+            if (needJ) {
+                // -iso(F), +iso(B) blocks from A and A2 (odd warps; even ones carry the rows that need `keep`)
+                if (warp & 1)
+                    for (int e = lane + 32 * (warp >> 1); e < N * N; e += 64) {
+                        const int r = e / N, cc = e - r * N;
+                        const double2 a = *reinterpret_cast<const double2*>(mA + r * LD + 2 * cc);
+                        const double2 a2 = *reinterpret_cast<const double2*>(mX + r * LD + 2 * cc);
+                        const double id = r == cc ? 1.0 : 0.0;
+                        const double fr = id + c1h * a.x + c2h2 * a2.x, fi = c1h * a.y + c2h2 * a2.y;
+                        const double br = id - c1h * a.x + c2h2 * a2.x, bi = -c1h * a.y + c2h2 * a2.y;
+                        const int k00 = r + n2 * cc, k01 = r + n2 * (cc + N);
+                        PUT(QO_ISOF, k00, -fr); PUT(QO_ISOF, k00 + N, -fi); PUT(QO_ISOF, k01, fi); PUT(QO_ISOF, k01 + N, -fr);
+                        PUT(QO_ISOB, k00, br);  PUT(QO_ISOB, k00 + N, bi);  PUT(QO_ISOB, k01, -bi); PUT(QO_ISOB, k01 + N, br);
+                    }
+            }
+            if (needH) {
+                // scalar second derivatives as traces against G = D M^H and G2 = S M^H:
+                //   dt x dt = 1/6 Re tr(A2 G);  a_j x dt = -1/2 Re tr(A_j G2) + h/6 Re tr(C_j G);  a_i x a_j = h^2/12 Re tr({A_i, A_j} G)
+                const double* const mG2 = mG + N * LD;
+                if (free_time)
+                    for (int task = warp; task < 1 + nd; task += nwarps_) {
+                        const int j = task - 1;
+                        const double* X = mX + task * N * LD;
+                        double s1 = 0.0, s2 = 0.0;
+                        for (int e = lane; e < N * N; e += 32) {
+                            const int r = e / N, k = e - r * N;
+                            const double2 xv = *reinterpret_cast<const double2*>(X + r * LD + 2 * k);
+                            const double2 gv = *reinterpret_cast<const double2*>(mG + k * LD + 2 * r);
+                            s2 = fma(xv.x, gv.x, s2);
+                            s2 = fma(-xv.y, gv.y, s2);
+                        }
+                        if (j >= 0)
+                            for (int e = lane; e < N * W; e += 32) {
+                                const int r = e / W;
+                                const double2 av = ellv[(j * 2) * N * W + e];
+                                const double2 gv = *reinterpret_cast<const double2*>(mG2 + ellc[(j * 2) * N * W + e] * LD + 2 * r);
+                                s1 = fma(av.x, gv.x, s1);
+                                s1 = fma(-av.y, gv.y, s1);
+                            }
+                        s1 = warp_sum(s1);
+                        s2 = warp_sum(s2);
+                        const int q = j < 0 ? QO_HHH : QO_HAH + j;
+                        if (lane == 0 && c.pl_base[q] >= 0) image[c.pl_base[q]] = j < 0 ? s2 * (1.0 / 6.0) : -0.5 * s1 + c2h * s2;
+                    }
+                if (warp == nwarps_ - 1 && lane < npair) {  // a_i x a_j; tasks in (j, i <= j) order, one lane each
+                    int j = 0, rem = lane;
+                    while (rem > j) { rem -= j + 1; ++j; }
+                    double val = 0.0;
+                    for (int u = kkptr[lane]; u < kkptr[lane + 1]; ++u) {
+                        const int rc = kkrc[u];
+                        const double2 kv = kkv[u];
+                        const double2 gv = *reinterpret_cast<const double2*>(mG + (rc & 255) * LD + 2 * (rc >> 8));  // K[r, k] G[k, r]
+                        val = fma(kv.x, gv.x, val);
+                        val = fma(-kv.y, gv.y, val);
+                    }
+                    const int q = qo_haa(rem, j);
+                    if (c.pl_base[q] >= 0) image[c.pl_base[q]] = val * c2h2;
+                }
+            }
+        }
+        if (QCK_BULK_STORE) fence_async_smem();
+        GSYNC();
+        } else if constexpr (KIND == QK_PADE4) {
         // ---- stage 1: A2 = A A (+ F, B blocks), AS = A S, AhM = A^H M, G = D M^H, G2 = S M^H;  C_j = A_j A + A A_j ----
         {
             const int nG = needH ? (free_time ? 2 : 1) : 0;
@@ -639,6 +994,7 @@ qck_quantum_kernel(const QckLaunch p) {
                     }
             }
         }
+        if (QCK_BULK_STORE) fence_async_smem();  // image writes -> visible to the copy engine
         GSYNC();
         } else if constexpr (KIND == QK_EXP) {
         // ============================ exponential integrators =============================================================
@@ -1239,10 +1595,15 @@ qck_quantum_kernel(const QckLaunch p) {
 #undef XT
 #undef XG
         }
+        if (QCK_BULK_STORE && KIND != QK_PADE4) {
+            fence_async_smem();
+            GSYNC();
+        }
         QCK_TICK(5);
 
         // ---- stage 3: write-out: contiguous copies image -> value arrays ---------------------------------------------
-        write_units(image, segs, seghdr[vwarp], seghdr[vwarp + 1], p, t, lane);
+        write_units<(TC == QCK_TILE && CN > 0) ? 2 * CN * CN : 0>(image, segs, seghdr[vwarp], seghdr[vwarp + 1], p, t, lane);
+        if (QCK_BULK_STORE && lane == 0) bulk_commit();
         QCK_TICK(6);
         buf = next_buf;
         buf_member = next_member;
@@ -1251,6 +1612,7 @@ qck_quantum_kernel(const QckLaunch p) {
         if (mi >= nact) { mi -= nact; ++t; }
     }
     cp_async_wait_all();
+    if (QCK_BULK_STORE && lane == 0) bulk_wait_all();
 #undef MA
 #undef MS
 #undef SEGBUF
@@ -1305,6 +1667,7 @@ void qck_smem_finalize(QckClassDev& c) {
 }
 
 int qck_pick_threads(const QckClassDev& c) {
+    if (c.kind == QCK_UNITARY_PADE && c.order == 4 && c.N == 9) return 128;  // tensor-core path: fixed roles for four warps
     if (const char* e = getenv("QCK_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }  // tuning knob
     const int tc = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP) ? QCK_TILE : 1;
     int tilesS = (c.NP / QCK_TILE) * (c.ncp / tc);
@@ -1359,6 +1722,10 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     const int nact = L.member_end - L.member_begin;
     L.moff_smem = nact <= 1024 ? 1 : 0;
     L.sm_count = sm_count;
+    {
+        static const int stg = getenv("QCK_STAGGER_NS") ? atoi(getenv("QCK_STAGGER_NS")) : 0;
+        L.stagger_ns = (unsigned)stg;
+    }
     const int G = c.threads;
     const int ngroups = multi ? 4 : 1;
     // Launch geometry.  With several active members the per-member tables are double-buffered in shared memory unless the
