@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqcknot.so")
+LIB_PATH = os.environ.get("QCK_LIB") or os.path.join(HERE, "libqcknot.so")  # QCK_LIB: development override (A/B builds)
 
 QCK_UNITARY_PADE, QCK_UNITARY_EXP, QCK_KET_PADE, QCK_KET_EXP, QCK_DERIVATIVE = range(5)
 QCK_EVAL_F, QCK_EVAL_J, QCK_EVAL_H = 1, 2, 4

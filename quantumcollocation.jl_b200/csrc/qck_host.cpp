@@ -446,6 +446,16 @@ int build(qck_handle* h) {
         }
         c.W = W;
         c.ell_stride = nd * 2 * N * W;
+        c.antiherm = 1;
+        for (int q : C.members) {
+            const Integ& I = h->integ[q];
+            for (int j = -1; j < nd && c.antiherm; ++j) {
+                const std::complex<double>* Hm = j < 0 ? I.Hdrift.data() : I.Hdrives.data() + (size_t)j * N * N;
+                for (int r = 0; r < N && c.antiherm; ++r)
+                    for (int k = 0; k <= r; ++k)
+                        if (Hm[r + (size_t)N * k] != std::conj(Hm[k + (size_t)N * r])) { c.antiherm = 0; break; }
+            }
+        }
         // {A_i, A_j} = -(H_i H_j + H_j H_i) for A = -iH, pairs ordered by (j, i <= j)
         std::vector<std::vector<std::vector<std::pair<int, std::complex<double>>>>> kk(nm);
         int kk_cap = 0;

@@ -63,6 +63,7 @@ struct QckAux {
 struct QckClassDev {
     int kind, N, NP, nc, ncp, nd, order, W;
     int free_time, dt_off, zdim, dyn;
+    int antiherm;  // every member's Hamiltonians are Hermitian: A(a) = -i H(a) is anti-Hermitian
     double dt_fixed;
     int n_members;
     // scratch (offsets in doubles)
@@ -118,6 +119,7 @@ struct QckLaunch {
     int group_smem;          // bytes of shared memory per group
     long long* timing;       // optional per-stage cycle counters (debug)
     unsigned stagger_ns;     // start-up delay step between the CTAs of one SM
+    int hoff;                // row-slice kernel: image offset where the Hessian part starts
 };
 
 struct QckReduce {  // fixed-order reduction of shared Hessian positions
