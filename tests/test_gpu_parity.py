@@ -99,3 +99,60 @@ def test_general_pade_orders(order, name, kw):
     check(systems, traj, integrators)
     if name == "hadamard":
         check(systems, traj, integrators, eval_hessian=False)
+
+
+# ---- 9-level Pade-4 unitaries: the warp-per-knot row-slice kernel and its variants --------------------------------------------
+@pytest.mark.parametrize("nd", [1, 2, 3, 4])
+def test_nine_levels_dense_drives(nd):
+    """Row-slice kernel with dense drive matrices (row width 9 -> dense A_j products), 1..4 drives."""
+    sys_ = wl.random_hermitian_system(9, nd, seed=90 + nd, scale=0.5)
+    traj = wl.random_pulse_trajectory([sys_], 5, 0.25, seed=3 + nd)
+    check([sys_], traj, wl.build_integrators([sys_], traj))
+
+
+def test_nine_levels_non_hermitian():
+    """A(a) = -i H(a) is not anti-Hermitian here: the A^H products must take the general path."""
+    rng = np.random.default_rng(5)
+    mk = lambda: 0.4 * (rng.normal(size=(9, 9)) + 1j * rng.normal(size=(9, 9)))
+    sys_ = qcknot.QuantumSystem(mk(), [mk(), mk()])
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.2, seed=8)
+    check([sys_], traj, wl.build_integrators([sys_], traj))
+
+
+def test_nine_levels_five_drives_fall_back_to_tiled_kernel():
+    """More than four drives: the tiled shared-memory kernel handles the class."""
+    sys_ = wl.random_hermitian_system(9, 5, seed=77, scale=0.4)
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.2, seed=9)
+    check([sys_], traj, wl.build_integrators([sys_], traj))
+
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import qcknot
+from qcknot import workloads as wl
+from helpers import oracle_dynamics, rel_err
+for free_time in (True, False):
+    systems, traj, integrators = wl.config("cz", T=6, free_time=free_time)
+    D = qcknot.QuantumDynamics(integrators, traj); O = oracle_dynamics(integrators, traj)
+    Z = traj.datavec; mu = wl.random_multipliers(D.n_blocks * D.dyn)
+    F, J, H = D.eval_all(Z, mu)
+    assert rel_err(F, O.F(Z)) < 1e-10 and rel_err(J, O.dF(Z)) < 1e-10 and rel_err(H, O.mu_d2F(Z, mu)) < 1e-10
+    assert np.array_equal(J, D.dF(Z)) and np.array_equal(H, D.mu_d2F(Z, mu))
+    D.close()
+print("variant ok")
+"""
+
+
+@pytest.mark.parametrize("env", [{"QCK_ROWSLICE": "0"}, {"QCK_ROWSLICE": "0", "QCK_DMMA": "1"}, {"QCK_ROWSLICE_DENSE": "1"},
+                                 {"QCK_ROWSLICE_WARPS": "3"}])
+def test_cz_kernel_variants(env):
+    """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
+    (QCK_ROWSLICE=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives, and a smaller CTA."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))],
+                         env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout + out.stderr
