@@ -119,7 +119,7 @@ struct MapEnt {
 // image-adjacent (they merge into one segment); groups with a common stride > 1 that interleave share one range.
 struct Run { int dst, len, img, period; };
 bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* base, short* stride, std::vector<Run>& segs,
-                 std::string& why) {
+                 std::string& why, int* dst0 = nullptr) {
     if (e.empty()) return true;
     struct Group { int qid; long long d0; int s, n, period; };
     std::map<int, std::vector<MapEnt>> by_q;
@@ -161,6 +161,7 @@ bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* bas
         if (cursor > 32000) { why = "output image too large"; return false; }
         base[g.qid] = (short)b;
         stride[g.qid] = (short)g.s;
+        if (dst0) dst0[g.qid] = (int)g.d0;  // destination of element 0 (column kernel: values go straight to the arrays)
     }
     // segments: maximal runs contiguous in both destination and image
     std::sort(e.begin(), e.end());
@@ -389,6 +390,7 @@ int build(qck_handle* h) {
         c.threads = qck_pick_threads(c);
         const int nwarps = c.threads / 32;
         for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
+        std::vector<int> qdst((size_t)nm * QO_COUNT, -1);  // per member: first destination of every output quantity
         {
             std::vector<std::vector<QckSeg>> per_member(nm);
             std::vector<std::vector<int>> hdrs(nm, std::vector<int>(QCK_SEG_HDR, 0));
@@ -399,12 +401,13 @@ int build(qck_handle* h) {
                 for (int q2 = 0; q2 < QO_COUNT; ++q2) { base[q2] = -1; stride[q2] = 0; }
                 std::vector<Run> runs[3];
                 std::vector<MapEnt> mf;
+                int* d0 = &qdst[(size_t)m2 * QO_COUNT];
                 for (int i = 0; i < I.dim; ++i) mf.push_back({(long long)I.row_off + i, QO_R, i, 0});
                 int cursor = 0;
                 std::string why;
-                if (!place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why) ||
-                    !place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why) ||
-                    !place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why))
+                if (!place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why, d0) ||
+                    !place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why, d0) ||
+                    !place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why, d0))
                     return fail(h, QCK_EINVAL, "unsupported trajectory layout: %s", why.c_str());
                 per_member[m2] = balance_units(runs, nwarps, hdrs[m2].data());
                 if (first) {
@@ -539,6 +542,23 @@ int build(qck_handle* h) {
                 }
             }
             aptr[N * N] = au;
+        }
+        // column kernel (levels <= 4): dense drive matrices A_j = -i H_j, row-major, and the per-member destinations
+        c.dense_aj = nullptr; c.qdst = nullptr;
+        if (c.kind == QCK_UNITARY_PADE && c.order == 4 && N <= 4) {
+            std::vector<double2> daj((size_t)nm * nd * N * N);
+            for (int m2 = 0; m2 < nm; ++m2) {
+                const Integ& I = h->integ[C.members[m2]];
+                for (int j = 0; j < nd; ++j)
+                    for (int r = 0; r < N; ++r)
+                        for (int k = 0; k < N; ++k) {
+                            const std::complex<double> a = std::complex<double>(0, -1) * I.Hdrives[(size_t)j * N * N + r + (size_t)N * k];
+                            daj[((size_t)(m2 * nd + j) * N + r) * N + k] = make_double2(a.real(), a.imag());
+                        }
+            }
+            cudaError_t e2;
+            if ((e2 = upload(daj, &c.dense_aj, C.allocs)) != cudaSuccess || (e2 = upload(qdst, &c.qdst, C.allocs)) != cudaSuccess)
+                return fail(h, QCK_ECUDA, "uploading column-kernel tables: %s", cudaGetErrorString(e2));
         }
         cudaError_t e;
         if ((e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||

@@ -92,6 +92,10 @@ struct QckClassDev {
     long long tape_stride;     // double2 elements per CTA
     int tape_levels;           // squaring levels the tape can hold
     int max_ctas;              // CTAs the tape was sized for (0 = no limit)
+    // column kernel (levels <= 4): dense A_j per member [member][drive][N*N] row-major; first destination of every
+    // output quantity per member [member][QO_COUNT] (-1 = absent; Hessian: >= nnzH means partial column)
+    const double2* dense_aj;
+    const int* qdst;
     // general-order Pade: degree m = order/2 and coefficient ratios r_k = c_{k+1}/c_k
     int pade_m;
     double pade_r[8];
