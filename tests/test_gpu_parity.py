@@ -57,7 +57,7 @@ def test_sampling_pade():
     check(*wl.config("sampling", T=4, n_systems=5))
 
 
-@pytest.mark.parametrize("levels,nd", [(3, 1), (4, 2), (5, 3), (6, 2)])
+@pytest.mark.parametrize("levels,nd", [(3, 1), (4, 2), (5, 3), (6, 2), (2, 3), (3, 4), (4, 4), (4, 5)])
 def test_random_dense_systems(levels, nd):
     sys_ = wl.random_hermitian_system(levels, nd, seed=levels * 10 + nd, scale=0.7)
     traj = wl.random_pulse_trajectory([sys_], 4, 0.3, seed=7)
@@ -133,7 +133,7 @@ import qcknot
 from qcknot import workloads as wl
 from helpers import oracle_dynamics, rel_err
 for free_time in (True, False):
-    systems, traj, integrators = wl.config("cz", T=6, free_time=free_time)
+    systems, traj, integrators = wl.config({name!r}, T=6, free_time=free_time, **{kw!r})
     D = qcknot.QuantumDynamics(integrators, traj); O = oracle_dynamics(integrators, traj)
     Z = traj.datavec; mu = wl.random_multipliers(D.n_blocks * D.dyn)
     F, J, H = D.eval_all(Z, mu)
@@ -144,15 +144,16 @@ print("variant ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"QCK_ROWSLICE": "0"}, {"QCK_ROWSLICE": "0", "QCK_DMMA": "1"}, {"QCK_ROWSLICE_DENSE": "1"},
-                                 {"QCK_ROWSLICE_WARPS": "3"}])
-def test_cz_kernel_variants(env):
+@pytest.mark.parametrize("name,kw,env", [("cz", {}, {"QCK_ROWSLICE": "0"}), ("cz", {}, {"QCK_ROWSLICE": "0", "QCK_DMMA": "1"}),
+                                         ("cz", {}, {"QCK_ROWSLICE_DENSE": "1"}), ("cz", {}, {"QCK_ROWSLICE_WARPS": "3"}),
+                                         ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"})])
+def test_kernel_variants(name, kw, env):
     """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
-    (QCK_ROWSLICE=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives, and a smaller CTA."""
+    (QCK_ROWSLICE=0 / QCK_COLUMN=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives, a smaller CTA."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ)
     e.update(env)
-    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))],
+    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT.format(root=root, tests=os.path.join(root, "tests"), name=name, kw=kw)],
                          env=e, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "variant ok" in out.stdout, out.stdout + out.stderr
