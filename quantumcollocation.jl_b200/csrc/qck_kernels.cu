@@ -2247,8 +2247,8 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
             }
         }
         if (needH) {
-            double2 w1[N], z1[ND][N];
-            double s_ah[ND], s_aa[NPAIR];
+            double2 w1[N];
+            double s_ah[ND], pz[ND][ND];  // pz[i][j] = Re <A_i^H m, A_j d> (this lane's column)
             {
                 double2 w2[N], o[N];
                 mvAH(w1, mm);
@@ -2262,38 +2262,39 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
             }
 #pragma unroll
             for (int j = 0; j < ND; ++j) {
-                double2 z2[N], z3[N], o[N];
+                double2 z1[N], z2[N], z3[N], o[N];
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
-                    z1[j][r] = z2[r] = make_double2(0.0, 0.0);
+                    z1[r] = z2[r] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
                         double2 w = __ldg(Ajg + (j * N + k) * N + r);  // conj(A_j[k][r])
                         w.y = -w.y;
-                        cfma(z1[j][r], w, mm[k]);
+                        cfma(z1[r], w, mm[k]);
                         cfma(z2[r], w, w1[k]);
                     }
                 }
-                mvAH(z3, z1[j]);
+                mvAH(z3, z1);
                 s_ah[j] = 0.0;
+#pragma unroll
+                for (int i2 = 0; i2 < ND; ++i2) pz[j][i2] = 0.0;
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
                     const double cr = c2h2 * (z2[r].x + z3[r].x), ci = c2h2 * (z2[r].y + z3[r].y);
-                    o[r] = make_double2(-c1h * z1[j][r].x - cr, -c1h * z1[j][r].y - ci);
-                    z2[r] = make_double2(-c1h * z1[j][r].x + cr, -c1h * z1[j][r].y + ci);
-                    s_ah[j] += rdot(z1[j][r], qv[r]) + c2h * rdot(w1[r], u[j][r]);
+                    o[r] = make_double2(-c1h * z1[r].x - cr, -c1h * z1[r].y - ci);
+                    z2[r] = make_double2(-c1h * z1[r].x + cr, -c1h * z1[r].y + ci);
+                    s_ah[j] += rdot(z1[r], qv[r]) + c2h * rdot(w1[r], u[j][r]);
+#pragma unroll
+                    for (int i2 = 0; i2 < ND; ++i2) pz[j][i2] += rdot(z1[r], u[i2][r]);
                 }
                 put_H(QO_KA0 + j, o);
                 put_H(QO_KA1 + j, z2);
             }
+            double s_aa[NPAIR];
 #pragma unroll
             for (int j = 0, q = 0; j < ND; ++j)
 #pragma unroll
-                for (int i2 = 0; i2 <= j; ++i2, ++q) {
-                    s_aa[q] = 0.0;
-#pragma unroll
-                    for (int r = 0; r < N; ++r) s_aa[q] += rdot(z1[i2][r], u[j][r]) + rdot(z1[j][r], u[i2][r]);
-                }
+                for (int i2 = 0; i2 <= j; ++i2, ++q) s_aa[q] = pz[i2][j] + pz[j][i2];
             s_hh = gsum(s_hh);
             put_scalar(QO_HHH, s_hh * (1.0 / 6.0));
 #pragma unroll
@@ -2311,15 +2312,21 @@ __global__ void qck_aux_kernel(const QckLaunch p) {
     for (long long t = blockIdx.x; t < p.n_knots; t += gridDim.x) do_aux(p, t, threadIdx.x, blockDim.x);
 }
 
+// One warp per (knot, shared position): the lanes walk the contributors' partial columns in ascending order with stride 32,
+// then a shuffle tree combines the 32 partial sums.  The order of the additions is fixed (no atomics): bitwise reproducible.
 __global__ void qck_reduce_kernel(const QckReduce r, double* __restrict__ H, const double* __restrict__ partial,
                                   long long n_knots, long long nnzH, int npart) {
-    long long total = n_knots * r.n_shared;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i / r.n_shared;
-        int s = (int)(i - t * r.n_shared);
+    const int lane = threadIdx.x & 31;
+    const long long total = n_knots * r.n_shared;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += nwarps) {
+        const long long t = i / r.n_shared;
+        const int s = (int)(i - t * r.n_shared);
+        const int k0 = r.ptr[s], k1 = r.ptr[s + 1];
         double acc = 0.0;
-        for (int k = r.ptr[s]; k < r.ptr[s + 1]; ++k) acc += partial[t * npart + r.cols[k]];
-        H[t * nnzH + r.pos[s]] = acc;
+        for (int k = k0 + lane; k < k1; k += 32) acc += partial[t * npart + r.cols[k]];
+        acc = warp_sum(acc);
+        if (lane == 0) H[t * nnzH + r.pos[s]] = acc;
     }
 }
 
@@ -2561,8 +2568,8 @@ int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches) {
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,
                       int npart, cudaStream_t stream, int* launches) {
     if (R.n_shared == 0 || n_knots <= 0) return 0;
-    long long total = n_knots * R.n_shared;
-    long long grid = (total + 255) / 256;
+    long long total = n_knots * R.n_shared;  // one warp each
+    long long grid = (total + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
     qck_reduce_kernel<<<(unsigned)grid, 256, 0, stream>>>(R, H, partial, n_knots, nnzH, npart);
     if (launches) ++*launches;
