@@ -545,7 +545,7 @@ int build(qck_handle* h) {
         }
         // column kernel (levels <= 4): dense drive matrices A_j = -i H_j, row-major, and the per-member destinations
         c.dense_aj = nullptr; c.qdst = nullptr;
-        if (c.kind == QCK_UNITARY_PADE && c.order == 4 && N <= 4) {
+        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && N <= 4) {
             std::vector<double2> daj((size_t)nm * nd * N * N);
             for (int m2 = 0; m2 < nm; ++m2) {
                 const Integ& I = h->integ[C.members[m2]];

@@ -2039,12 +2039,13 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
 // (its column of an iso-vector; its two columns of every copy of a kron(I_N, .) block), so they leave as 16-byte stores
 // straight from registers: no staging image.  Destinations per member come from the host's placement pass.
 // ------------------------------------------------------------------------------------------------------------
-template <int N, int ND>
+// NC: columns of the state (N for unitaries, 1 for kets: QuantumStatePadeIntegrator = the same algebra on one column)
+template <int N, int ND, int NC>
 __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
-    constexpr int n2 = 2 * N, blk = n2 * n2, IPW = 32 / N, NPAIR = ND * (ND + 1) / 2;
+    constexpr int n2 = 2 * N, blk = n2 * n2, IPW = 32 / NC, NPAIR = ND * (ND + 1) / 2;
     const QckClassDev& c = p.c;
     const int lane = threadIdx.x & 31;
-    const int gi = lane / N, col = lane - gi * N;  // item slot inside the warp, column
+    const int gi = lane / NC, col = lane - gi * NC;  // item slot inside the warp, column
     const bool needF = p.mask & QCK_EVAL_F, needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
     const int nact = p.member_end - p.member_begin;
     const long long n_items = p.n_knots * nact;
@@ -2066,7 +2067,7 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
     auto gsum = [&](double v) {  // sum over the N lanes of this lane's item
         double r = v;
 #pragma unroll
-        for (int o = 1; o < N; ++o) r += __shfl_sync(0xffffffffu, v, (gi * N + (col + o) % N) & 31);
+        for (int o = 1; o < NC; ++o) r += __shfl_sync(0xffffffffu, v, (gi * NC + (col + o) % NC) & 31);
         return r;
     };
 
@@ -2189,36 +2190,49 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
         }
         // ---- -iso(F), +iso(B): this lane's columns (col, col + N) of the 2N x 2N block, into every one of the N copies -------------
         if (needJ && on && qd[QO_ISOF] >= 0) {
-            double2 acol[N], a2[N];
-#pragma unroll
-            for (int k = 0; k < N; ++k) {  // column `col` of A (a lane-dependent column: rebuilt from the constants)
-                double2 v = __ldg(A0g + k + N * col);
-#pragma unroll
-                for (int j = 0; j < ND; ++j) {
-                    const double2 w = __ldg(Ajg + (j * N + k) * N + col);
-                    v.x = fma(a[j], w.x, v.x);
-                    v.y = fma(a[j], w.y, v.y);
-                }
-                acol[k] = v;
-            }
-            mvA(a2, acol);
-            double f0[n2], f1[n2], b0[n2], b1[n2];
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                const double id = r == col ? 1.0 : 0.0;
-                const double fr = id + c1h * acol[r].x + c2h2 * a2[r].x, fi = c1h * acol[r].y + c2h2 * a2[r].y;
-                const double br = id - c1h * acol[r].x + c2h2 * a2[r].x, bi = -c1h * acol[r].y + c2h2 * a2[r].y;
-                f0[r] = -fr; f0[N + r] = -fi; f1[r] = fi; f1[N + r] = -fr;
-                b0[r] = br;  b0[N + r] = bi;  b1[r] = -bi; b1[N + r] = br;
-            }
             const int dF = qd[QO_ISOF], dB = qd[QO_ISOB];
+            auto block_columns = [&](int bc, const double2 (&acol)[N], int copy0, int copy1) {  // columns bc, bc + N of the block
+                double2 a2[N];
+                mvA(a2, acol);
+                double f0[n2], f1[n2], b0[n2], b1[n2];
 #pragma unroll
-            for (int cb = 0; cb < N; ++cb) {
-                store_run(oJ + dF + cb * blk + col * n2, f0);
-                store_run(oJ + dF + cb * blk + (col + N) * n2, f1);
-                if (dB >= 0) {
-                    store_run(oJ + dB + cb * blk + col * n2, b0);
-                    store_run(oJ + dB + cb * blk + (col + N) * n2, b1);
+                for (int r = 0; r < N; ++r) {
+                    const double id = r == bc ? 1.0 : 0.0;
+                    const double fr = id + c1h * acol[r].x + c2h2 * a2[r].x, fi = c1h * acol[r].y + c2h2 * a2[r].y;
+                    const double br = id - c1h * acol[r].x + c2h2 * a2[r].x, bi = -c1h * acol[r].y + c2h2 * a2[r].y;
+                    f0[r] = -fr; f0[N + r] = -fi; f1[r] = fi; f1[N + r] = -fr;
+                    b0[r] = br;  b0[N + r] = bi;  b1[r] = -bi; b1[N + r] = br;
+                }
+                for (int cb = copy0; cb < copy1; ++cb) {
+                    store_run(oJ + dF + cb * blk + bc * n2, f0);
+                    store_run(oJ + dF + cb * blk + (bc + N) * n2, f1);
+                    if (dB >= 0) {
+                        store_run(oJ + dB + cb * blk + bc * n2, b0);
+                        store_run(oJ + dB + cb * blk + (bc + N) * n2, b1);
+                    }
+                }
+            };
+            if constexpr (NC == N) {  // unitary: this lane's column pair, into every one of the N copies
+                double2 acol[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) {  // column `col` of A (a lane-dependent column: rebuilt from the constants)
+                    double2 v = __ldg(A0g + k + N * col);
+#pragma unroll
+                    for (int j = 0; j < ND; ++j) {
+                        const double2 w = __ldg(Ajg + (j * N + k) * N + col);
+                        v.x = fma(a[j], w.x, v.x);
+                        v.y = fma(a[j], w.y, v.y);
+                    }
+                    acol[k] = v;
+                }
+                block_columns(col, acol, 0, N);
+            } else {  // ket: the single lane writes all column pairs of the one block
+#pragma unroll
+                for (int bc = 0; bc < N; ++bc) {
+                    double2 acol[N];
+#pragma unroll
+                    for (int k = 0; k < N; ++k) acol[k] = A[k][bc];
+                    block_columns(bc, acol, 0, 1);
                 }
             }
         }
@@ -2304,7 +2318,7 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
 #pragma unroll
                 for (int i2 = 0; i2 <= j; ++i2, ++q) put_scalar(qo_haa(i2, j), c2h2 * gsum(s_aa[q]));
         }
-        if (mi == 0 && p.n_aux && on) do_aux(p, t, col, N);  // derivative-integrator entries of this knot
+        if (mi == 0 && p.n_aux && on) do_aux(p, t, col, NC);  // derivative-integrator entries of this knot
     }
 }
 
@@ -2445,18 +2459,21 @@ static int launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, 
     const QckClassDev& c = L.c;
     *done = false;
     static const int enabled = getenv("QCK_COLUMN") ? atoi(getenv("QCK_COLUMN")) : 1;
-    if (!enabled || c.kind != QCK_UNITARY_PADE || c.order != 4 || c.N < 2 || c.N > 4 || c.nd < 1 || c.nd > 4 || !c.dense_aj || !c.qdst) return 0;
+    const bool ket = c.kind == QCK_KET_PADE;
+    if (!enabled || (c.kind != QCK_UNITARY_PADE && !ket) || c.order != 4 || c.N < 2 || c.N > 4 || c.nd < 1 || c.nd > 4 || !c.dense_aj || !c.qdst) return 0;
     typedef void (*kern_t)(const QckLaunch);
     kern_t kern = nullptr;
-#define QCK_COL(N_) (c.nd == 1 ? qck_column_kernel<N_, 1> : (c.nd == 2 ? qck_column_kernel<N_, 2> : (c.nd == 3 ? qck_column_kernel<N_, 3> : qck_column_kernel<N_, 4>)))
+#define QCK_COL2(N_, NC_) (c.nd == 1 ? qck_column_kernel<N_, 1, NC_> : (c.nd == 2 ? qck_column_kernel<N_, 2, NC_> : (c.nd == 3 ? qck_column_kernel<N_, 3, NC_> : qck_column_kernel<N_, 4, NC_>)))
+#define QCK_COL(N_) (ket ? QCK_COL2(N_, 1) : QCK_COL2(N_, N_))
     kern = c.N == 2 ? QCK_COL(2) : (c.N == 3 ? QCK_COL(3) : QCK_COL(4));
 #undef QCK_COL
+#undef QCK_COL2
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return 0;
     const long long n_items = L.n_knots * (long long)(L.member_end - L.member_begin);
-    const int ipw = 32 / c.N;
+    const int ipw = 32 / (ket ? 1 : c.N);
     long long grid = (long long)sm_count * per_sm;
     const long long need = (n_items + 8LL * ipw - 1) / (8LL * ipw);
     if (grid > need) grid = need;

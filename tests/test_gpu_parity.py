@@ -146,7 +146,8 @@ print("variant ok")
 
 @pytest.mark.parametrize("name,kw,env", [("cz", {}, {"QCK_ROWSLICE": "0"}), ("cz", {}, {"QCK_ROWSLICE": "0", "QCK_DMMA": "1"}),
                                          ("cz", {}, {"QCK_ROWSLICE_DENSE": "1"}), ("cz", {}, {"QCK_ROWSLICE_WARPS": "3"}),
-                                         ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"})])
+                                         ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"}),
+                                         ("ket", {}, {"QCK_COLUMN": "0"})])
 def test_kernel_variants(name, kw, env):
     """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
     (QCK_ROWSLICE=0 / QCK_COLUMN=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives, a smaller CTA."""
