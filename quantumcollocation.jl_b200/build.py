@@ -5,13 +5,13 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/qck_kernels.cu", "csrc/qck_host.cpp"]
-HEADERS = ["csrc/qck_internal.h", "../include/qcknot.h"]
+SOURCES = ["csrc/qck_kernels.cu", "csrc/qck_rowslice.cu", "csrc/qck_column.cu", "csrc/qck_host.cpp"]
+HEADERS = ["csrc/qck_internal.h", "csrc/qck_device.cuh", "../include/qcknot.h"]
 LIB = os.path.join(HERE, "libqcknot.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177",
+    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177", "--threads", "4",
 ]
 
 

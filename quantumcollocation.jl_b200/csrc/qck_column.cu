@@ -1,0 +1,333 @@
+// Column kernel (2..4-level Pade-4 unitaries and kets, one lane per column) of libqcknot.so.  Compiled as its own translation unit so that the kernel families build in parallel.
+#include "qck_device.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// Column kernel: Pade-4, unitaries, 2..4 levels (Hadamard / sampling problems).  ONE LANE per column of the unitaries:
+// N lanes per (knot, integrator) work item, 32 / N items per warp, no shared memory, no barriers.
+//
+// A lane holds ALL of A = -i H(a) (N x N complex) and its own columns d, s, m of D = U1 - U0, S = U1 + U0, M in registers;
+// every product of the path is a local matrix-vector product (same matrix-vector form as the row-slice kernel), the scalar
+// second derivatives are dot products summed over the item's N lanes with shuffles.  The constant drives A_j are read
+// (dense, per member) through L1.  A lane's values of one output quantity are 2N consecutive doubles of the value arrays
+// (its column of an iso-vector; its two columns of every copy of a kron(I_N, .) block), so they leave as 16-byte stores
+// straight from registers: no staging image.  Destinations per member come from the host's placement pass.
+// ------------------------------------------------------------------------------------------------------------
+// NC: columns of the state (N for unitaries, 1 for kets: QuantumStatePadeIntegrator = the same algebra on one column)
+template <int N, int ND, int NC>
+__global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
+    constexpr int n2 = 2 * N, blk = n2 * n2, IPW = 32 / NC, NPAIR = ND * (ND + 1) / 2;
+    const QckClassDev& c = p.c;
+    const int lane = threadIdx.x & 31;
+    const int gi = lane / NC, col = lane - gi * NC;  // item slot inside the warp, column
+    const bool needF = p.mask & QCK_EVAL_F, needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
+    const int nact = p.member_end - p.member_begin;
+    const long long n_items = p.n_knots * nact;
+    const long long nslots = (long long)gridDim.x * (blockDim.x >> 5) * IPW;
+    const bool free_time = c.free_time;
+
+    auto store_run = [](double* dst, const double (&v)[n2]) {  // 2N consecutive doubles, 16-byte stores where aligned
+        if (reinterpret_cast<uintptr_t>(dst) & 8) {
+            dst[0] = v[0];
+#pragma unroll
+            for (int i = 0; i < N - 1; ++i) *reinterpret_cast<double2*>(dst + 1 + 2 * i) = make_double2(v[1 + 2 * i], v[2 + 2 * i]);
+            dst[n2 - 1] = v[n2 - 1];
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) *reinterpret_cast<double2*>(dst + 2 * i) = make_double2(v[2 * i], v[2 * i + 1]);
+        }
+    };
+    auto rdot = [](double2 x, double2 y) { return x.x * y.x + x.y * y.y; };  // Re <x, y>
+    auto gsum = [&](double v) {  // sum over the N lanes of this lane's item
+        double r = v;
+#pragma unroll
+        for (int o = 1; o < NC; ++o) r += __shfl_sync(0xffffffffu, v, (gi * NC + (col + o) % NC) & 31);
+        return r;
+    };
+
+    for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * IPW; base < n_items; base += nslots) {
+        const long long item = base + gi;
+        const bool on = gi < IPW && item < n_items;
+        const long long it = on ? item : base;  // idle lanes shadow a valid item (no stores)
+        const long long t = it / nact;
+        const int mi = (int)(it - t * nact), m = p.member_begin + mi;
+        const int soff = p.moff_global[3 * mi], coff = p.moff_global[3 * mi + 1], roff = p.moff_global[3 * mi + 2];
+        const double* zt = p.Z + t * c.zdim;
+        const int* qd = c.qdst + (size_t)m * QO_COUNT;
+        double* const oF = p.F + t * c.dyn;
+        double* const oJ = p.J + t * p.nnzJ;
+        // iso-vector quantity q: this lane's column (rows 0..N-1 real, then imaginary); arr0 = start of the knot block
+        auto put_vec = [&](double* arr0, int d0, int q, const double2 (&x)[N]) {
+            const int st = c.pl_stride[q];
+            if (st == 1) {
+                double v[n2];
+#pragma unroll
+                for (int r = 0; r < N; ++r) { v[r] = x[r].x; v[N + r] = x[r].y; }
+                store_run(arr0 + d0 + col * n2, v);
+            } else {
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    arr0[d0 + (col * n2 + r) * st] = x[r].x;
+                    arr0[d0 + (col * n2 + N + r) * st] = x[r].y;
+                }
+            }
+        };
+        auto put_J = [&](int q, const double2 (&x)[N]) {
+            const int d0 = qd[q];
+            if (d0 >= 0 && on) put_vec(oJ, d0, q, x);
+        };
+        auto put_H = [&](int q, const double2 (&x)[N]) {  // (>= nnzH: partial column of a shared position)
+            const int d0 = qd[q];
+            if (d0 < 0 || !on) return;
+            if (d0 < p.nnzH) put_vec(p.H + t * p.nnzH, d0, q, x);
+            else put_vec(p.partial + t * p.npart, d0 - (int)p.nnzH, q, x);
+        };
+        auto put_scalar = [&](int q, double v) {
+            const int d0 = qd[q];
+            if (d0 < 0 || !on || col != 0) return;
+            if (d0 < p.nnzH) p.H[t * p.nnzH + d0] = v;
+            else p.partial[t * p.npart + (d0 - p.nnzH)] = v;
+        };
+        // ---- inputs: this lane's column of U0, U1 and of the multipliers ------------------------------------------------------
+        double2 d[N], s[N], mm[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            const double u0r = zt[soff + col * n2 + r], u0i = zt[soff + col * n2 + N + r];
+            const double u1r = zt[c.zdim + soff + col * n2 + r], u1i = zt[c.zdim + soff + col * n2 + N + r];
+            d[r] = make_double2(u1r - u0r, u1i - u0i);
+            s[r] = make_double2(u1r + u0r, u1i + u0i);
+            mm[r] = needH ? make_double2(p.mu[t * c.dyn + roff + col * n2 + r], p.mu[t * c.dyn + roff + col * n2 + N + r]) : make_double2(0.0, 0.0);
+        }
+        const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
+        const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
+        double a[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) a[j] = zt[coff + j];
+        // ---- A = A0 + sum_j a_j A_j ---------------------------------------------------------------------------------------------
+        const double2* const A0g = c.cmat + (size_t)m * c.cmat_stride;  // column-major
+        const double2* const Ajg = c.dense_aj + (size_t)m * ND * N * N;  // [drive][row][column]
+        double2 A[N][N];
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                double2 v = __ldg(A0g + r + N * k);
+#pragma unroll
+                for (int j = 0; j < ND; ++j) {
+                    const double2 w = __ldg(Ajg + (j * N + r) * N + k);
+                    v.x = fma(a[j], w.x, v.x);
+                    v.y = fma(a[j], w.y, v.y);
+                }
+                A[r][k] = v;
+            }
+        auto mvA = [&](double2 (&y)[N], const double2 (&x)[N]) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                y[r] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < N; ++k) cfma(y[r], A[r][k], x[k]);
+            }
+        };
+        auto mvAH = [&](double2 (&y)[N], const double2 (&x)[N]) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                y[r] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < N; ++k) cfma(y[r], make_double2(A[k][r].x, -A[k][r].y), x[k]);
+            }
+        };
+
+        // ---- residual, d/dh; q = -1/2 s + h/6 A d and v = -h/2 s + h^2/12 A d for the drive terms ---------------------------------
+        double2 qv[N], vv[N];
+        double s_hh = 0.0;
+        {
+            double2 x1[N], x2[N], x3[N], o[N];
+            mvA(x1, s);
+            mvA(x2, d);
+            mvA(x3, x2);
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                qv[r] = make_double2(-0.5 * s[r].x + c2h * x2[r].x, -0.5 * s[r].y + c2h * x2[r].y);
+                vv[r] = make_double2(-c1h * s[r].x + c2h2 * x2[r].x, -c1h * s[r].y + c2h2 * x2[r].y);
+                s_hh += rdot(mm[r], x3[r]);
+            }
+            if (needF && on && qd[QO_R] >= 0) {
+#pragma unroll
+                for (int r = 0; r < N; ++r) o[r] = make_double2(d[r].x - c1h * x1[r].x + c2h2 * x3[r].x, d[r].y - c1h * x1[r].y + c2h2 * x3[r].y);
+                put_vec(oF, qd[QO_R], QO_R, o);
+            }
+            if (needJ) {
+#pragma unroll
+                for (int r = 0; r < N; ++r) o[r] = make_double2(-0.5 * x1[r].x + c2h * x3[r].x, -0.5 * x1[r].y + c2h * x3[r].y);
+                put_J(QO_TH, o);
+            }
+        }
+        // ---- -iso(F), +iso(B): this lane's columns (col, col + N) of the 2N x 2N block, into every one of the N copies -------------
+        if (needJ && on && qd[QO_ISOF] >= 0) {
+            const int dF = qd[QO_ISOF], dB = qd[QO_ISOB];
+            auto block_columns = [&](int bc, const double2 (&acol)[N], int copy0, int copy1) {  // columns bc, bc + N of the block
+                double2 a2[N];
+                mvA(a2, acol);
+                double f0[n2], f1[n2], b0[n2], b1[n2];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const double id = r == bc ? 1.0 : 0.0;
+                    const double fr = id + c1h * acol[r].x + c2h2 * a2[r].x, fi = c1h * acol[r].y + c2h2 * a2[r].y;
+                    const double br = id - c1h * acol[r].x + c2h2 * a2[r].x, bi = -c1h * acol[r].y + c2h2 * a2[r].y;
+                    f0[r] = -fr; f0[N + r] = -fi; f1[r] = fi; f1[N + r] = -fr;
+                    b0[r] = br;  b0[N + r] = bi;  b1[r] = -bi; b1[N + r] = br;
+                }
+                for (int cb = copy0; cb < copy1; ++cb) {
+                    store_run(oJ + dF + cb * blk + bc * n2, f0);
+                    store_run(oJ + dF + cb * blk + (bc + N) * n2, f1);
+                    if (dB >= 0) {
+                        store_run(oJ + dB + cb * blk + bc * n2, b0);
+                        store_run(oJ + dB + cb * blk + (bc + N) * n2, b1);
+                    }
+                }
+            };
+            if constexpr (NC == N) {  // unitary: this lane's column pair, into every one of the N copies
+                double2 acol[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) {  // column `col` of A (a lane-dependent column: rebuilt from the constants)
+                    double2 v = __ldg(A0g + k + N * col);
+#pragma unroll
+                    for (int j = 0; j < ND; ++j) {
+                        const double2 w = __ldg(Ajg + (j * N + k) * N + col);
+                        v.x = fma(a[j], w.x, v.x);
+                        v.y = fma(a[j], w.y, v.y);
+                    }
+                    acol[k] = v;
+                }
+                block_columns(col, acol, 0, N);
+            } else {  // ket: the single lane writes all column pairs of the one block
+#pragma unroll
+                for (int bc = 0; bc < N; ++bc) {
+                    double2 acol[N];
+#pragma unroll
+                    for (int k = 0; k < N; ++k) acol[k] = A[k][bc];
+                    block_columns(bc, acol, 0, 1);
+                }
+            }
+        }
+        // ---- drive terms -----------------------------------------------------------------------------------------------------------------
+        double2 u[ND][N];
+        if (needJ || needH) {
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                double2 y[N], y3[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    y[r] = u[j][r] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double2 w = __ldg(Ajg + (j * N + r) * N + k);
+                        cfma(y[r], w, vv[k]);
+                        cfma(u[j][r], w, d[k]);
+                    }
+                }
+                mvA(y3, u[j]);
+                if (needJ) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r) y[r] = make_double2(y[r].x + c2h2 * y3[r].x, y[r].y + c2h2 * y3[r].y);
+                    put_J(QO_TA + j, y);
+                }
+            }
+        }
+        if (needH) {
+            double2 w1[N];
+            double s_ah[ND], pz[ND][ND];  // pz[i][j] = Re <A_i^H m, A_j d> (this lane's column)
+            {
+                double2 w2[N], o[N];
+                mvAH(w1, mm);
+                mvAH(w2, w1);
+#pragma unroll
+                for (int r = 0; r < N; ++r) o[r] = make_double2(-0.5 * w1[r].x - c2h * w2[r].x, -0.5 * w1[r].y - c2h * w2[r].y);
+                put_H(QO_KH0, o);
+#pragma unroll
+                for (int r = 0; r < N; ++r) o[r] = make_double2(-0.5 * w1[r].x + c2h * w2[r].x, -0.5 * w1[r].y + c2h * w2[r].y);
+                put_H(QO_KH1, o);
+            }
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                double2 z1[N], z2[N], z3[N], o[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    z1[r] = z2[r] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        double2 w = __ldg(Ajg + (j * N + k) * N + r);  // conj(A_j[k][r])
+                        w.y = -w.y;
+                        cfma(z1[r], w, mm[k]);
+                        cfma(z2[r], w, w1[k]);
+                    }
+                }
+                mvAH(z3, z1);
+                s_ah[j] = 0.0;
+#pragma unroll
+                for (int i2 = 0; i2 < ND; ++i2) pz[j][i2] = 0.0;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const double cr = c2h2 * (z2[r].x + z3[r].x), ci = c2h2 * (z2[r].y + z3[r].y);
+                    o[r] = make_double2(-c1h * z1[r].x - cr, -c1h * z1[r].y - ci);
+                    z2[r] = make_double2(-c1h * z1[r].x + cr, -c1h * z1[r].y + ci);
+                    s_ah[j] += rdot(z1[r], qv[r]) + c2h * rdot(w1[r], u[j][r]);
+#pragma unroll
+                    for (int i2 = 0; i2 < ND; ++i2) pz[j][i2] += rdot(z1[r], u[i2][r]);
+                }
+                put_H(QO_KA0 + j, o);
+                put_H(QO_KA1 + j, z2);
+            }
+            double s_aa[NPAIR];
+#pragma unroll
+            for (int j = 0, q = 0; j < ND; ++j)
+#pragma unroll
+                for (int i2 = 0; i2 <= j; ++i2, ++q) s_aa[q] = pz[i2][j] + pz[j][i2];
+            s_hh = gsum(s_hh);
+            put_scalar(QO_HHH, s_hh * (1.0 / 6.0));
+#pragma unroll
+            for (int j = 0; j < ND; ++j) put_scalar(QO_HAH + j, gsum(s_ah[j]));
+#pragma unroll
+            for (int j = 0, q = 0; j < ND; ++j)
+#pragma unroll
+                for (int i2 = 0; i2 <= j; ++i2, ++q) put_scalar(qo_haa(i2, j), c2h2 * gsum(s_aa[q]));
+        }
+        if (mi == 0 && p.n_aux && on) do_aux(p, t, col, NC);  // derivative-integrator entries of this knot
+    }
+}
+
+
+}  // namespace
+
+// one lane per column, everything in registers (2..4-level Pade-4 unitaries, up to four drives, any number of members)
+int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done) {
+    const QckClassDev& c = L.c;
+    *done = false;
+    static const int enabled = getenv("QCK_COLUMN") ? atoi(getenv("QCK_COLUMN")) : 1;
+    const bool ket = c.kind == QCK_KET_PADE;
+    if (!enabled || (c.kind != QCK_UNITARY_PADE && !ket) || c.order != 4 || c.N < 2 || c.N > 4 || c.nd < 1 || c.nd > 4 || !c.dense_aj || !c.qdst) return 0;
+    typedef void (*kern_t)(const QckLaunch);
+    kern_t kern = nullptr;
+#define QCK_COL2(N_, NC_) (c.nd == 1 ? qck_column_kernel<N_, 1, NC_> : (c.nd == 2 ? qck_column_kernel<N_, 2, NC_> : (c.nd == 3 ? qck_column_kernel<N_, 3, NC_> : qck_column_kernel<N_, 4, NC_>)))
+#define QCK_COL(N_) (ket ? QCK_COL2(N_, 1) : QCK_COL2(N_, N_))
+    kern = c.N == 2 ? QCK_COL(2) : (c.N == 3 ? QCK_COL(3) : QCK_COL(4));
+#undef QCK_COL
+#undef QCK_COL2
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return 0;
+    const long long n_items = L.n_knots * (long long)(L.member_end - L.member_begin);
+    const int ipw = 32 / (ket ? 1 : c.N);
+    long long grid = (long long)sm_count * per_sm;
+    const long long need = (n_items + 8LL * ipw - 1) / (8LL * ipw);
+    if (grid > need) grid = need;
+    static const bool dbg = getenv("QCK_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "[qcknot] column kernel: N=%d nd=%d CTAs/SM=%d grid=%lld items=%lld\n", c.N, c.nd, per_sm, grid, n_items);
+    kern<<<(unsigned)grid, 256, 0, stream>>>(L);
+    if (launches) ++*launches;
+    *done = true;
+    return (int)cudaGetLastError();
+}
+

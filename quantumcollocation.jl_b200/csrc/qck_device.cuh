@@ -1,0 +1,237 @@
+// Device helpers shared by the kernel translation units of libqcknot.so (complex FMA, small tile products, cp.async / TMA
+// bulk-copy wrappers, derivative-integrator entries, the write-out of the output image).  Internal: not part of the C-ABI.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+
+#include "qck_internal.h"
+
+namespace {
+
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ void cfma(double2& c, double2 a, double2 b) {
+    c.x = fma(a.x, b.x, c.x);
+    c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y);
+    c.y = fma(a.y, b.x, c.y);
+}
+
+// acc[i][j] = sum_k opA(A)[r0+i, k] * opB(B)[k, c0+j],  k < K, 3 x TC complex register tile.
+// Operands are column-major with leading dimension ld.  opX = conj-transpose when tX is set, expressed through
+// runtime strides + a sign on the imaginary part so that every product of a stage runs the same instruction stream.
+template <int TC, bool ZERO = true>
+__device__ __forceinline__ void tile_mm(const double2* __restrict__ A, bool tA, const double2* __restrict__ B, bool tB,
+                                        int K, int ld, int r0, int c0, double2 (&acc)[QCK_TILE][TC]) {
+    if (ZERO) {
+#pragma unroll
+        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+            for (int j = 0; j < TC; ++j) acc[i][j] = make_double2(0.0, 0.0);
+    }
+    const int ar = tA ? ld : 1, ak = tA ? 1 : ld;  // A[(r0+i)*ar + k*ak]
+    const int bc = tB ? 1 : ld, bk = tB ? ld : 1;  // B[(c0+j)*bc + k*bk]
+    const double sa = tA ? -1.0 : 1.0, sb = tB ? -1.0 : 1.0;  // conjugation = sign of the imaginary part
+    const double2* a = A + r0 * ar;
+    const double2* b = B + c0 * bc;
+#pragma unroll 3
+    for (int k = 0; k < K; ++k) {
+        double2 av[QCK_TILE], bv[TC];
+#pragma unroll
+        for (int i = 0; i < QCK_TILE; ++i) {
+            av[i] = a[i * ar + k * ak];
+            av[i].y *= sa;
+        }
+#pragma unroll
+        for (int j = 0; j < TC; ++j) {
+            bv[j] = b[j * bc + k * bk];
+            bv[j].y *= sb;
+        }
+#pragma unroll
+        for (int i = 0; i < QCK_TILE; ++i)
+#pragma unroll
+            for (int j = 0; j < TC; ++j) cfma(acc[i][j], av[i], bv[j]);
+    }
+}
+
+// out[r, c] = sum_w val[r][w] * X[col[r][w], c]   (fixed-width sparse row format of a constant drive matrix)
+__device__ __forceinline__ double2 ell_row(const double2* __restrict__ val, const int* __restrict__ col, int W,
+                                           const double2* __restrict__ X, int ld, int r, int c) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int w = 0; w < W; ++w) {
+        double2 v = val[r * W + w];
+        int k = col[r * W + w];
+        cfma(acc, v, X[k + ld * c]);
+    }
+    return acc;
+}
+
+// FP64 tensor-core tile product: D(8x8) += A(8x4, row-major fragment) * B(4x8, column fragment).  Lane (g = lane/4,
+// t = lane%4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+__device__ __forceinline__ void do_aux(const QckLaunch& p, long long t, int tid, int nthreads) {
+    const QckClassDev& c = p.c;
+    const double* zt = p.Z + t * c.zdim;
+    for (int k = tid; k < p.n_aux; k += nthreads) {
+        QckAux a = p.aux[k];
+        if (!((p.mask >> a.out) & 1u)) continue;
+        double dt = c.free_time ? zt[c.dt_off] : c.dt_fixed;
+        double v;
+        switch (a.op) {
+            case QAUX_CONST: v = a.c; break;
+            case QAUX_NEG_DT: v = -dt; break;
+            case QAUX_NEG_Z: v = -zt[a.i0]; break;
+            case QAUX_NEG_MU: v = -p.mu[t * c.dyn + a.i0]; break;
+            default: v = zt[c.zdim + a.i0] - zt[a.i0] - dt * zt[a.i1]; break;
+        }
+        if (a.out == 0) p.F[t * c.dyn + a.pos] = v;
+        else if (a.out == 1) p.J[t * p.nnzJ + a.pos] = v;
+        else if (a.pos < p.nnzH) p.H[t * p.nnzH + a.pos] = v;
+        else p.partial[t * p.npart + (a.pos - p.nnzH)] = v;
+    }
+}
+
+// same entries, operands already staged in shared memory by the prefetch (fused path: no global load latency)
+__device__ __forceinline__ void do_aux_staged(const QckLaunch& p, const QckAux* auxs, const double* auxv, double dt,
+                                              long long t, int tid, int nthreads) {
+    const QckClassDev& c = p.c;
+    for (int k = tid; k < p.n_aux; k += nthreads) {
+        const QckAux a = auxs[k];
+        if (!((p.mask >> a.out) & 1u)) continue;
+        double v;
+        switch (a.op) {
+            case QAUX_CONST: v = a.c; break;
+            case QAUX_NEG_DT: v = -dt; break;
+            case QAUX_NEG_Z: v = -auxv[3 * k]; break;
+            case QAUX_NEG_MU: v = -auxv[3 * k + 2]; break;
+            default: v = auxv[3 * k + 1] - auxv[3 * k] - dt * auxv[3 * k + 2]; break;
+        }
+        if (a.out == 0) p.F[t * c.dyn + a.pos] = v;
+        else if (a.out == 1) p.J[t * p.nnzJ + a.pos] = v;
+        else if (a.pos < p.nnzH) p.H[t * p.nnzH + a.pos] = v;
+        else p.partial[t * p.npart + (a.pos - p.nnzH)] = v;
+    }
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// TMA bulk copy shared -> global (one thread issues; the copy engine drains the image while the CTA computes on)
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (the bulk copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// Write-out: every unit is nrep back-to-back contiguous copies image -> value array, owned by ONE warp (the host
+// balanced the units over the warps).  Consecutive lanes store consecutive positions with 16-byte stores; a destination
+// that sits at 8 mod 16 takes a scalar head/tail and pairs shifted by one double.  Repeated (kron(I_N, .)) blocks of
+// the compile-time size 2*HPC doubles are read ONCE into registers and stored nrep times (no loads, no index wrap in
+// the store loop); all loops are kept free of integer division and of per-element address arithmetic.
+#define QCK_BULK_STORE 1
+template <int HPC>
+__device__ __forceinline__ void write_units(const double* __restrict__ image, const QckSeg* __restrict__ segs, int s0, int s1,
+                                            const QckLaunch& p, long long t, int lane, unsigned mask) {
+    double* const baseF = p.F + t * p.c.dyn;
+    double* const baseJ = p.J + t * p.nnzJ;
+    double* const baseH = p.H + t * p.nnzH;
+    double* const baseP = p.partial + t * p.npart - p.nnzH;
+    for (int s = s0; s < s1; ++s) {
+        const QckSeg sg = segs[s];
+        const int arr = sg.arr & 255;
+        if (!((mask >> arr) & 1u)) continue;
+        double* dst = (arr == 0 ? baseF : (arr == 1 ? baseJ : ((long long)sg.dst < p.nnzH ? baseH : baseP))) + sg.dst;
+        const double* src = image + (sg.img_nrep & 0xffff);
+        const int nrep = sg.img_nrep >> 16, n = sg.n;
+        const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
+        if (nrep == 1 && !odd && !(n & 1) && QCK_BULK_STORE) {
+            if (lane == 0) bulk_store(dst, src, (unsigned)n * 8u);
+        } else if (nrep == 1) {
+            // plain run: scalar head (misaligned destination) / tail, 16-byte body
+            const int head = odd ? 1 : 0;
+            const int pairs = (n - head) >> 1;
+            if (lane == 31) {
+                if (head) dst[0] = src[0];
+                if (head + 2 * pairs < n) dst[n - 1] = src[n - 1];
+            }
+            double2* d2 = reinterpret_cast<double2*>(dst + head) + lane;
+            int k = lane;
+            if (!head) {
+                const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
+                for (; k + 96 < pairs; k += 128, s2 += 128, d2 += 128) {
+                    const double2 v0 = s2[0], v1 = s2[32], v2 = s2[64], v3 = s2[96];
+                    d2[0] = v0; d2[32] = v1; d2[64] = v2; d2[96] = v3;
+                }
+                for (; k < pairs; k += 32, s2 += 32, d2 += 32) *d2 = *s2;
+            } else {
+                const double* sh = src + 1 + 2 * lane;
+                for (; k + 32 < pairs; k += 64, sh += 128, d2 += 64) {
+                    const double a0 = sh[0], a1 = sh[1], b0 = sh[64], b1 = sh[65];
+                    d2[0] = make_double2(a0, a1); d2[32] = make_double2(b0, b1);
+                }
+                for (; k < pairs; k += 32, sh += 64, d2 += 32) *d2 = make_double2(sh[0], sh[1]);
+            }
+        } else if (!odd && !(n & 1) && QCK_BULK_STORE) {
+            if (lane == 0)
+                for (int r = 0; r < nrep; ++r) bulk_store(dst + (size_t)r * n, src, (unsigned)n * 8u);
+        } else if (!odd && !(n & 1)) {
+            const int hp = n >> 1;
+            const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
+            double2* d2 = reinterpret_cast<double2*>(dst) + lane;
+            if (HPC > 0 && hp == HPC) {
+                constexpr int NV = HPC > 0 ? (HPC + 31) / 32 : 1;
+                double2 v[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (32 * (i + 1) <= HPC || lane + 32 * i < HPC) v[i] = s2[32 * i];
+                for (int r = 0; r < nrep; ++r, d2 += HPC) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+                        if (32 * (i + 1) <= HPC || lane + 32 * i < HPC) d2[32 * i] = v[i];
+                }
+            } else {
+                for (int r = 0; r < nrep; ++r, d2 += hp) {
+#pragma unroll 2
+                    for (int k = lane; k < hp; k += 32) d2[k - lane] = s2[k - lane];
+                }
+            }
+        } else {
+            const int total = n * nrep, step = 32 % n;  // rare path (odd period or misaligned repeated block)
+            int k = lane % n;
+            for (int idx = lane; idx < total; idx += 32) {
+                dst[idx] = src[k];
+                k += step;
+                if (k >= n) k -= n;
+            }
+        }
+    }
+}
+
+
+}  // namespace

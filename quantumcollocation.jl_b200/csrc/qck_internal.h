@@ -136,6 +136,9 @@ struct QckReduce {  // fixed-order reduction of shared Hessian positions
 // kernel launchers (qck_kernels.cu).  Return cudaError_t as int.
 int qck_launch_quantum(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches);
 int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches);
+// specialised kernels (own translation units); *done tells whether the class was taken
+int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 int qck_fused_aux_limit(void);
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,

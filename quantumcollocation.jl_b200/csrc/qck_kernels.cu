@@ -21,233 +21,9 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "qck_internal.h"
+#include "qck_device.cuh"
 
 namespace {
-
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ void cfma(double2& c, double2 a, double2 b) {
-    c.x = fma(a.x, b.x, c.x);
-    c.x = fma(-a.y, b.y, c.x);
-    c.y = fma(a.x, b.y, c.y);
-    c.y = fma(a.y, b.x, c.y);
-}
-
-// acc[i][j] = sum_k opA(A)[r0+i, k] * opB(B)[k, c0+j],  k < K, 3 x TC complex register tile.
-// Operands are column-major with leading dimension ld.  opX = conj-transpose when tX is set, expressed through
-// runtime strides + a sign on the imaginary part so that every product of a stage runs the same instruction stream.
-template <int TC, bool ZERO = true>
-__device__ __forceinline__ void tile_mm(const double2* __restrict__ A, bool tA, const double2* __restrict__ B, bool tB,
-                                        int K, int ld, int r0, int c0, double2 (&acc)[QCK_TILE][TC]) {
-    if (ZERO) {
-#pragma unroll
-        for (int i = 0; i < QCK_TILE; ++i)
-#pragma unroll
-            for (int j = 0; j < TC; ++j) acc[i][j] = make_double2(0.0, 0.0);
-    }
-    const int ar = tA ? ld : 1, ak = tA ? 1 : ld;  // A[(r0+i)*ar + k*ak]
-    const int bc = tB ? 1 : ld, bk = tB ? ld : 1;  // B[(c0+j)*bc + k*bk]
-    const double sa = tA ? -1.0 : 1.0, sb = tB ? -1.0 : 1.0;  // conjugation = sign of the imaginary part
-    const double2* a = A + r0 * ar;
-    const double2* b = B + c0 * bc;
-#pragma unroll 3
-    for (int k = 0; k < K; ++k) {
-        double2 av[QCK_TILE], bv[TC];
-#pragma unroll
-        for (int i = 0; i < QCK_TILE; ++i) {
-            av[i] = a[i * ar + k * ak];
-            av[i].y *= sa;
-        }
-#pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            bv[j] = b[j * bc + k * bk];
-            bv[j].y *= sb;
-        }
-#pragma unroll
-        for (int i = 0; i < QCK_TILE; ++i)
-#pragma unroll
-            for (int j = 0; j < TC; ++j) cfma(acc[i][j], av[i], bv[j]);
-    }
-}
-
-// out[r, c] = sum_w val[r][w] * X[col[r][w], c]   (fixed-width sparse row format of a constant drive matrix)
-__device__ __forceinline__ double2 ell_row(const double2* __restrict__ val, const int* __restrict__ col, int W,
-                                           const double2* __restrict__ X, int ld, int r, int c) {
-    double2 acc = make_double2(0.0, 0.0);
-    for (int w = 0; w < W; ++w) {
-        double2 v = val[r * W + w];
-        int k = col[r * W + w];
-        cfma(acc, v, X[k + ld * c]);
-    }
-    return acc;
-}
-
-// FP64 tensor-core tile product: D(8x8) += A(8x4, row-major fragment) * B(4x8, column fragment).  Lane (g = lane/4,
-// t = lane%4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t+1].
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ double warp_sum(double s) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return s;
-}
-
-__device__ __forceinline__ void do_aux(const QckLaunch& p, long long t, int tid, int nthreads) {
-    const QckClassDev& c = p.c;
-    const double* zt = p.Z + t * c.zdim;
-    for (int k = tid; k < p.n_aux; k += nthreads) {
-        QckAux a = p.aux[k];
-        if (!((p.mask >> a.out) & 1u)) continue;
-        double dt = c.free_time ? zt[c.dt_off] : c.dt_fixed;
-        double v;
-        switch (a.op) {
-            case QAUX_CONST: v = a.c; break;
-            case QAUX_NEG_DT: v = -dt; break;
-            case QAUX_NEG_Z: v = -zt[a.i0]; break;
-            case QAUX_NEG_MU: v = -p.mu[t * c.dyn + a.i0]; break;
-            default: v = zt[c.zdim + a.i0] - zt[a.i0] - dt * zt[a.i1]; break;
-        }
-        if (a.out == 0) p.F[t * c.dyn + a.pos] = v;
-        else if (a.out == 1) p.J[t * p.nnzJ + a.pos] = v;
-        else if (a.pos < p.nnzH) p.H[t * p.nnzH + a.pos] = v;
-        else p.partial[t * p.npart + (a.pos - p.nnzH)] = v;
-    }
-}
-
-// same entries, operands already staged in shared memory by the prefetch (fused path: no global load latency)
-__device__ __forceinline__ void do_aux_staged(const QckLaunch& p, const QckAux* auxs, const double* auxv, double dt,
-                                              long long t, int tid, int nthreads) {
-    const QckClassDev& c = p.c;
-    for (int k = tid; k < p.n_aux; k += nthreads) {
-        const QckAux a = auxs[k];
-        if (!((p.mask >> a.out) & 1u)) continue;
-        double v;
-        switch (a.op) {
-            case QAUX_CONST: v = a.c; break;
-            case QAUX_NEG_DT: v = -dt; break;
-            case QAUX_NEG_Z: v = -auxv[3 * k]; break;
-            case QAUX_NEG_MU: v = -auxv[3 * k + 2]; break;
-            default: v = auxv[3 * k + 1] - auxv[3 * k] - dt * auxv[3 * k + 2]; break;
-        }
-        if (a.out == 0) p.F[t * c.dyn + a.pos] = v;
-        else if (a.out == 1) p.J[t * p.nnzJ + a.pos] = v;
-        else if (a.pos < p.nnzH) p.H[t * p.nnzH + a.pos] = v;
-        else p.partial[t * p.npart + (a.pos - p.nnzH)] = v;
-    }
-}
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-// TMA bulk copy shared -> global (one thread issues; the copy engine drains the image while the CTA computes on)
-__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-// generic-proxy writes to shared memory -> visible to the async proxy (the bulk copy engine)
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-// Write-out: every unit is nrep back-to-back contiguous copies image -> value array, owned by ONE warp (the host
-// balanced the units over the warps).  Consecutive lanes store consecutive positions with 16-byte stores; a destination
-// that sits at 8 mod 16 takes a scalar head/tail and pairs shifted by one double.  Repeated (kron(I_N, .)) blocks of
-// the compile-time size 2*HPC doubles are read ONCE into registers and stored nrep times (no loads, no index wrap in
-// the store loop); all loops are kept free of integer division and of per-element address arithmetic.
-#define QCK_BULK_STORE 1
-template <int HPC>
-__device__ __forceinline__ void write_units(const double* __restrict__ image, const QckSeg* __restrict__ segs, int s0, int s1,
-                                            const QckLaunch& p, long long t, int lane, unsigned mask) {
-    double* const baseF = p.F + t * p.c.dyn;
-    double* const baseJ = p.J + t * p.nnzJ;
-    double* const baseH = p.H + t * p.nnzH;
-    double* const baseP = p.partial + t * p.npart - p.nnzH;
-    for (int s = s0; s < s1; ++s) {
-        const QckSeg sg = segs[s];
-        const int arr = sg.arr & 255;
-        if (!((mask >> arr) & 1u)) continue;
-        double* dst = (arr == 0 ? baseF : (arr == 1 ? baseJ : ((long long)sg.dst < p.nnzH ? baseH : baseP))) + sg.dst;
-        const double* src = image + (sg.img_nrep & 0xffff);
-        const int nrep = sg.img_nrep >> 16, n = sg.n;
-        const bool odd = (reinterpret_cast<uintptr_t>(dst) & 15) != 0;
-        if (nrep == 1 && !odd && !(n & 1) && QCK_BULK_STORE) {
-            if (lane == 0) bulk_store(dst, src, (unsigned)n * 8u);
-        } else if (nrep == 1) {
-            // plain run: scalar head (misaligned destination) / tail, 16-byte body
-            const int head = odd ? 1 : 0;
-            const int pairs = (n - head) >> 1;
-            if (lane == 31) {
-                if (head) dst[0] = src[0];
-                if (head + 2 * pairs < n) dst[n - 1] = src[n - 1];
-            }
-            double2* d2 = reinterpret_cast<double2*>(dst + head) + lane;
-            int k = lane;
-            if (!head) {
-                const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
-                for (; k + 96 < pairs; k += 128, s2 += 128, d2 += 128) {
-                    const double2 v0 = s2[0], v1 = s2[32], v2 = s2[64], v3 = s2[96];
-                    d2[0] = v0; d2[32] = v1; d2[64] = v2; d2[96] = v3;
-                }
-                for (; k < pairs; k += 32, s2 += 32, d2 += 32) *d2 = *s2;
-            } else {
-                const double* sh = src + 1 + 2 * lane;
-                for (; k + 32 < pairs; k += 64, sh += 128, d2 += 64) {
-                    const double a0 = sh[0], a1 = sh[1], b0 = sh[64], b1 = sh[65];
-                    d2[0] = make_double2(a0, a1); d2[32] = make_double2(b0, b1);
-                }
-                for (; k < pairs; k += 32, sh += 64, d2 += 32) *d2 = make_double2(sh[0], sh[1]);
-            }
-        } else if (!odd && !(n & 1) && QCK_BULK_STORE) {
-            if (lane == 0)
-                for (int r = 0; r < nrep; ++r) bulk_store(dst + (size_t)r * n, src, (unsigned)n * 8u);
-        } else if (!odd && !(n & 1)) {
-            const int hp = n >> 1;
-            const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
-            double2* d2 = reinterpret_cast<double2*>(dst) + lane;
-            if (HPC > 0 && hp == HPC) {
-                constexpr int NV = HPC > 0 ? (HPC + 31) / 32 : 1;
-                double2 v[NV];
-#pragma unroll
-                for (int i = 0; i < NV; ++i)
-                    if (32 * (i + 1) <= HPC || lane + 32 * i < HPC) v[i] = s2[32 * i];
-                for (int r = 0; r < nrep; ++r, d2 += HPC) {
-#pragma unroll
-                    for (int i = 0; i < NV; ++i)
-                        if (32 * (i + 1) <= HPC || lane + 32 * i < HPC) d2[32 * i] = v[i];
-                }
-            } else {
-                for (int r = 0; r < nrep; ++r, d2 += hp) {
-#pragma unroll 2
-                    for (int k = lane; k < hp; k += 32) d2[k - lane] = s2[k - lane];
-                }
-            }
-        } else {
-            const int total = n * nrep, step = 32 % n;  // rare path (odd period or misaligned repeated block)
-            int k = lane % n;
-            for (int idx = lane; idx < total; idx += 32) {
-                dst[idx] = src[k];
-                k += step;
-                if (k >= n) k -= n;
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Pade-4 integrators (UnitaryPadeIntegrator / QuantumStatePadeIntegrator, order 4).
@@ -1622,706 +1398,6 @@ qck_quantum_kernel(const QckLaunch p) {
 #undef GSYNC
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Row-slice kernel: Pade-4, unitaries, 9 levels (the two-transmon CZ problem).  ONE WARP per knot, no block barriers.
-//
-// The columns of the unitaries are independent under every product of the path (R[:,c] = D[:,c] - h/2 A S[:,c] + ...), so
-// lane (c, k) of a warp owns rows 3k .. 3k+2 of column c (27 lanes) and keeps ITS THREE ROWS OF A = -i H(a) IN REGISTERS
-// for the whole knot.  Every dense product of the path becomes a row-slice matrix-vector product
-//     y[3k + i] = sum_j A[3k + i][j] x[j],     x = a full column read from shared memory (all lanes of a column read the
-// same address: broadcast), 27 complex FMAs per lane, no operand re-load from shared memory for A.  Products with the
-// constant drives A_j, with A_j^H and with A^H read their matrix from shared memory the same way.  In matrix-vector form
-//     R = d - h/2 A s + h^2/12 A (A d)                    d/dh = -1/2 A s + h/6 A (A d)
-//     d/da_j = A_j (-h/2 s + h^2/12 A d) + h^2/12 A (A_j d)
-//     state x dt:  -(1/2 w1 + h/6 A^H w1),  w1 = A^H m     state x a_j:  -(h/2 z1 + h^2/12 (A_j^H w1 + A^H z1)),  z1 = A_j^H m
-//     dt x dt = 1/6 sum Re<m, A A d>      a_j x dt = sum -1/2 Re<z1_j, s> + h/6 (Re<z1_j, A d> + Re<w1, A_j d>)
-//     a_i x a_j = h^2/12 sum (Re<z1_i, A_j d> + Re<z1_j, A_i d>)          (sums over rows and columns = one warp reduction)
-// 13 + 4 n_d row-slice products per knot.  Values go into the warp's own output image (same host placement and write-out
-// units as the tiled kernel), which the warp then copies out.
-// ------------------------------------------------------------------------------------------------------------
-// WC: compile-time width of the sparse rows of the drives (loops fully unrolled); 0 = dense drive matrices
-// AH: A is anti-Hermitian (Hermitian Hamiltonians): A^H x = -(A x) runs on the register-resident rows of A
-template <int ND, int WC, bool AH>
-__global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p) {
-    constexpr int N = 9, NN = 81, n2 = 18, dim = 162;
-    extern __shared__ __align__(16) unsigned char smem_all[];
-    const QckClassDev& c = p.c;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const bool act = lane < 3 * N;
-    const int cc = act ? lane / 3 : 0, k3 = act ? 3 * (lane - 3 * (lane / 3)) : 0;  // column, first row of this lane
-    const bool needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
-    const bool needT = needJ || needH;
-    const bool free_time = c.free_time;
-    const int m = p.member_begin;
-    // CTA-wide tables: the member's constant block [A0 | sparse rows of A_j, A_j^H | anticommutator lists | contributor
-    // lists of A] (same layout as the tiled kernel's) and the write-out units
-    const int W = WC > 0 ? WC : c.W, elln = c.ell_stride, kkc = c.kk_cap, acn = c.ac_cap;
-    double2* const conv = reinterpret_cast<double2*>(smem_all);
-    const int nconv = NN + elln + kkc + acn;
-    int* const coni = reinterpret_cast<int*>(conv + nconv);
-    const int nrec = QCK_SEG_HDR / 4 + c.nseg;
-    QckSeg* const segtab = reinterpret_cast<QckSeg*>(smem_all + (((size_t)nconv * 16 + (size_t)c.icon_stride * 4 + 15) & ~(size_t)15));
-    // output staging: the F + J part of the image first, flushed, then the Hessian part in the same space
-    const int hoff = p.hoff, stage_doubles = hoff > c.img_doubles - hoff ? hoff : c.img_doubles - hoff;
-    const int img_bytes = ((stage_doubles + 1) & ~1) * 8;
-    double2* const cAj = reinterpret_cast<double2*>(segtab + nrec);  // WC == 0: dense A_j, row-major
-    unsigned char* const wbase = reinterpret_cast<unsigned char*>(cAj + (WC > 0 ? 0 : ND * NN)) + (size_t)warp * (img_bytes + 8 * NN * 16);
-    double* const imgJ = reinterpret_cast<double*>(wbase);
-    double* const imgH = imgJ - hoff;
-    double2* const vD = reinterpret_cast<double2*>(wbase + img_bytes);  // columns of D = U1 - U0: element [c * 9 + r]
-    double2* const vS = vD + NN;       // S = U1 + U0
-    double2* const vM = vS + NN;       // multipliers
-    double2* const vX2 = vM + NN;      // A D
-    double2* const vW1 = vX2 + NN;     // A^H M
-    double2* const vU = vW1 + NN;      // A_j D (current drive)
-    double2* const vZ1 = vU + NN;      // A_j^H M (current drive)
-    double2* const mA = vZ1 + NN;      // A, row-major (for A^H products and column access)
-    {
-        const double2* gv = c.cmat + (size_t)m * c.cmat_stride;
-        const int* gc = c.ell_col + (size_t)m * c.icon_stride;
-        for (int e = threadIdx.x; e < nconv; e += blockDim.x) conv[e] = gv[e];
-        for (int e = threadIdx.x; e < c.icon_stride; e += blockDim.x) coni[e] = gc[e];
-        const QckSeg* gs = c.segs + (size_t)m * nrec;
-        for (int i = threadIdx.x; i < nrec; i += blockDim.x) segtab[i] = gs[i];
-        for (int i = lane; i < img_bytes / 8; i += 32) imgJ[i] = 0.0;
-        if (WC == 0) {
-            for (int e = threadIdx.x; e < ND * NN; e += blockDim.x) cAj[e] = make_double2(0.0, 0.0);
-            __syncthreads();
-            for (int w = threadIdx.x; w < ND * N * W; w += blockDim.x) {  // dense A_j from the fixed-width sparse rows
-                const int j = w / (N * W), rem = w - j * N * W, r = rem / W, u = rem - r * W;
-                const int o = ((j * 2) * N + r) * W + u;
-                const double2 v = gv[NN + o];
-                if (v.x != 0.0 || v.y != 0.0) cAj[j * NN + r * N + gc[o]] = v;
-            }
-        }
-        __syncthreads();
-    }
-    const double2* const A0 = conv;
-    const double2* const ellv = conv + NN;
-    const double2* const kkv = ellv + elln;
-    const double2* const acv = kkv + kkc;
-    const int* const ellc = coni;
-    const int* const kkptr = coni + elln;
-    const int* const kkrc = kkptr + ND * (ND + 1) / 2 + 1;
-    const int* const acptr = kkrc + kkc;
-    const int* const acj = acptr + NN + 1;
-    const int* seghdr = reinterpret_cast<const int*>(segtab);
-    const QckSeg* segs = segtab + QCK_SEG_HDR / 4;
-    const int soff = p.moff_global[0], coff = p.moff_global[1], roff = p.moff_global[2];
-    const int xo = cc * N;  // this lane's column inside the vector buffers
-
-    for (long long t = (long long)blockIdx.x * nwarps + warp; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
-        const double* zt = p.Z + t * c.zdim;
-        // ---- inputs: coalesced loads of the two state vectors and the multipliers, unpacked into complex columns ----------
-        constexpr int NLD = (dim + 31) / 32;
-        double in0[NLD], in1[NLD], inm[NLD];  // all global loads of the knot are issued before the first use
-        {
-            const double* mut = p.mu + t * c.dyn + roff;
-#pragma unroll
-            for (int q = 0; q < NLD; ++q) {
-                const int idx = lane + 32 * q;
-                const bool ok = idx < dim;
-                in0[q] = ok ? zt[soff + idx] : 0.0;
-                in1[q] = ok ? zt[c.zdim + soff + idx] : 0.0;
-                inm[q] = ok && needH ? mut[idx] : 0.0;
-            }
-        }
-        const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
-        if (t + (long long)gridDim.x * nwarps < p.n_knots) {  // pull the next knot of this warp into L2 meanwhile
-            const double* zn = zt + (long long)gridDim.x * nwarps * c.zdim;
-            const double* mn = p.mu + (t + (long long)gridDim.x * nwarps) * c.dyn + roff;
-            for (int b = lane * 16; b < 2 * c.zdim; b += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(zn + b));
-            if (needH)
-                for (int b = lane * 16; b < dim; b += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(mn + b));
-        }
-        const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
-#pragma unroll
-        for (int q = 0; q < NLD; ++q) {
-            const int idx = lane + 32 * q;
-            if (idx < dim) {
-                const int col = idx / n2, qq = idx - col * n2, im = qq >= N, r = qq - im * N;
-                const int o = 2 * (col * N + r) + im;
-                reinterpret_cast<double*>(vD)[o] = in1[q] - in0[q];
-                reinterpret_cast<double*>(vS)[o] = in1[q] + in0[q];
-                if (needH) reinterpret_cast<double*>(vM)[o] = inm[q];
-            }
-        }
-        // ---- A = A0 + sum_j a_j A_j (per-element contributor lists) into shared memory, this lane's three rows into registers
-        for (int e = lane; e < NN; e += 32) {
-            double2 v = A0[e];
-            for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
-                const double aj = __ldg(zt + coff + acj[u]);  // (L1 hit: the controls were just loaded)
-                const double2 d = acv[u];
-                v.x = fma(aj, d.x, v.x);
-                v.y = fma(aj, d.y, v.y);
-            }
-            mA[(e % N) * N + e / N] = v;  // A0 is column-major
-        }
-        __syncwarp();
-        double2 Ar[3][N];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < N; ++j) Ar[i][j] = mA[(k3 + i) * N + j];
-        // row-slice products: y[i] = sum_j Mat[3k + i][j] x[j]
-        auto mv_reg = [&](double2 (&y)[3], const double2* x) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) y[i] = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 xv = x[j];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) cfma(y[i], Ar[i][j], xv);
-            }
-        };
-        auto mvH = [&](double2 (&y)[3], const double2* Mat, const double2* x) {  // y = Mat^H x
-#pragma unroll
-            for (int i = 0; i < 3; ++i) y[i] = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 xv = x[j];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    double2 mv = Mat[j * N + k3 + i];
-                    mv.y = -mv.y;
-                    cfma(y[i], mv, xv);
-                }
-            }
-        };
-        auto put = [&](double* image, int q, int i, double2 v) {  // element (row k3 + i, column cc) of an iso-vector quantity
-            const int b = c.pl_base[q], s = c.pl_stride[q], ire = cc * n2 + k3 + i;
-            if (b >= 0 && act) { image[b + ire * s] = v.x; image[b + (ire + N) * s] = v.y; }
-        };
-        auto rdot = [](double2 x, double2 y) { return x.x * y.x + x.y * y.y; };  // Re <x, y>
-        auto mvAH = [&](double2 (&y)[3], const double2* x) {  // y = A^H x
-            if constexpr (AH) {
-                mv_reg(y, x);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) y[i] = make_double2(-y[i].x, -y[i].y);
-            } else {
-                mvH(y, mA, x);
-            }
-        };
-
-        double s_hh = 0.0, s_ah[ND];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) s_ah[j] = 0.0;
-        double2 w1[3];
-        {
-            double2 x1[3], x2[3], x3[3];
-            mv_reg(x1, vS + xo);
-            mv_reg(x2, vD + xo);
-            if (act) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) vX2[xo + k3 + i] = x2[i];
-            }
-            if (needH) {
-                mvAH(w1, vM + xo);
-                if (act) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) vW1[xo + k3 + i] = w1[i];
-                }
-            }
-            __syncwarp();
-            mv_reg(x3, vX2 + xo);
-            if (needH && act) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) s_hh += rdot(vM[xo + k3 + i], x3[i]);
-            }
-            if (QCK_BULK_STORE) {
-                if (lane == 0) bulk_wait_read();  // the copy engine has finished reading the previous knot's staging buffer
-                __syncwarp();
-            }
-            // ---- phase 1: residual and Jacobian values ---------------------------------------------------------------------------
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double2 d = vD[xo + k3 + i];
-                put(imgJ, QO_R, i, make_double2(d.x - c1h * x1[i].x + c2h2 * x3[i].x, d.y - c1h * x1[i].y + c2h2 * x3[i].y));
-                put(imgJ, QO_TH, i, make_double2(-0.5 * x1[i].x + c2h * x3[i].x, -0.5 * x1[i].y + c2h * x3[i].y));
-            }
-        }
-        if (needJ) {  // column cc of A^2 -> -iso(F), +iso(B)
-            double2 a2[3], acol[N];
-#pragma unroll
-            for (int j = 0; j < N; ++j) acol[j] = mA[j * N + cc];
-            mv_reg(a2, acol);
-            if (act) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int r = k3 + i;
-                    const double2 av = mA[r * N + cc];
-                    const double id = r == cc ? 1.0 : 0.0;
-                    const double fr = id + c1h * av.x + c2h2 * a2[i].x, fi = c1h * av.y + c2h2 * a2[i].y;
-                    const double br = id - c1h * av.x + c2h2 * a2[i].x, bi = -c1h * av.y + c2h2 * a2[i].y;
-                    const int k00 = r + n2 * cc, k01 = r + n2 * (cc + N);
-                    const int bF = c.pl_base[QO_ISOF], sF = c.pl_stride[QO_ISOF], bB = c.pl_base[QO_ISOB], sB = c.pl_stride[QO_ISOB];
-                    imgJ[bF + k00 * sF] = -fr; imgJ[bF + (k00 + N) * sF] = -fi; imgJ[bF + k01 * sF] = fi; imgJ[bF + (k01 + N) * sF] = -fr;
-                    imgJ[bB + k00 * sB] = br;  imgJ[bB + (k00 + N) * sB] = bi;  imgJ[bB + k01 * sB] = -bi; imgJ[bB + (k01 + N) * sB] = br;
-                }
-            }
-        }
-        if (needT) {
-#pragma unroll
-            for (int j = 0; j < ND; ++j) {
-                double2 y[3], u[3], y3[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) y[i] = u[i] = make_double2(0.0, 0.0);
-                // y = A_j (-h/2 s + h^2/12 A d),  u = A_j d
-                if constexpr (WC > 0) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int o0 = ((j * 2) * N + k3 + i) * WC;
-#pragma unroll
-                        for (int w = 0; w < WC; ++w) {
-                            const double2 av = ellv[o0 + w];
-                            const int col = xo + ellc[o0 + w];
-                            const double2 sv = vS[col], xv = vX2[col];
-                            cfma(y[i], av, make_double2(-c1h * sv.x + c2h2 * xv.x, -c1h * sv.y + c2h2 * xv.y));
-                            cfma(u[i], av, vD[col]);
-                        }
-                    }
-                } else {
-                    const double2* Aj = cAj + j * NN;
-#pragma unroll
-                    for (int jj = 0; jj < N; ++jj) {
-                        const double2 sv = vS[xo + jj], xv = vX2[xo + jj], dv = vD[xo + jj];
-                        const double2 vv = make_double2(-c1h * sv.x + c2h2 * xv.x, -c1h * sv.y + c2h2 * xv.y);
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            const double2 aij = Aj[(k3 + i) * N + jj];
-                            cfma(y[i], aij, vv);
-                            cfma(u[i], aij, dv);
-                        }
-                    }
-                }
-                __syncwarp();  // the previous drive's readers of vU are done
-                if (act) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) vU[xo + k3 + i] = u[i];
-                }
-                __syncwarp();
-                mv_reg(y3, vU + xo);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    put(imgJ, QO_TA + j, i, make_double2(y[i].x + c2h2 * y3[i].x, y[i].y + c2h2 * y3[i].y));
-                    if (needH && act) s_ah[j] += c2h * rdot(w1[i], u[i]);
-                }
-            }
-        }
-        if (p.n_aux) do_aux(p, t, lane, 32);  // derivative-integrator entries of this knot
-        if (QCK_BULK_STORE) fence_async_smem();
-        __syncwarp();
-        write_units<2 * NN>(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
-        if (QCK_BULK_STORE && lane == 0) bulk_commit();
-        __syncwarp();
-        // ---- phase 2: Hessian-of-Lagrangian values, staged in the same buffer ------------------------------------------------------
-        if (needH) {
-            double2 w2[3];
-            mvAH(w2, vW1 + xo);
-            if (QCK_BULK_STORE) {
-                if (lane == 0) bulk_wait_read();  // phase-1 copies have left the buffer
-                __syncwarp();
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                put(imgH, QO_KH0, i, make_double2(-0.5 * w1[i].x - c2h * w2[i].x, -0.5 * w1[i].y - c2h * w2[i].y));
-                put(imgH, QO_KH1, i, make_double2(-0.5 * w1[i].x + c2h * w2[i].x, -0.5 * w1[i].y + c2h * w2[i].y));
-            }
-#pragma unroll
-            for (int j = 0; j < ND; ++j) {
-                double2 z1[3], z2[3], z3[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) z1[i] = z2[i] = make_double2(0.0, 0.0);
-                // z1 = A_j^H m,  z2 = A_j^H w1
-                if constexpr (WC > 0) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int o1 = ((j * 2 + 1) * N + k3 + i) * WC;  // (the table holds the rows of A_j^H)
-#pragma unroll
-                        for (int w = 0; w < WC; ++w) {
-                            const double2 av = ellv[o1 + w];
-                            const int col = xo + ellc[o1 + w];
-                            cfma(z1[i], av, vM[col]);
-                            cfma(z2[i], av, vW1[col]);
-                        }
-                    }
-                } else {
-                    const double2* Aj = cAj + j * NN;
-#pragma unroll
-                    for (int jj = 0; jj < N; ++jj) {
-                        const double2 mv = vM[xo + jj], wv = vW1[xo + jj];
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            double2 aji = Aj[jj * N + k3 + i];
-                            aji.y = -aji.y;
-                            cfma(z1[i], aji, mv);
-                            cfma(z2[i], aji, wv);
-                        }
-                    }
-                }
-                __syncwarp();  // the previous drive's readers of vZ1 are done
-                if (act) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) vZ1[xo + k3 + i] = z1[i];
-                }
-                __syncwarp();
-                mvAH(z3, vZ1 + xo);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double cr = c2h2 * (z2[i].x + z3[i].x), ci = c2h2 * (z2[i].y + z3[i].y);
-                    put(imgH, QO_KA0 + j, i, make_double2(-c1h * z1[i].x - cr, -c1h * z1[i].y - ci));
-                    put(imgH, QO_KA1 + j, i, make_double2(-c1h * z1[i].x + cr, -c1h * z1[i].y + ci));
-                    if (act) s_ah[j] += -0.5 * rdot(z1[i], vS[xo + k3 + i]) + c2h * rdot(z1[i], vX2[xo + k3 + i]);
-                }
-            }
-            // a_i x a_j = h^2/12 Re tr({A_i, A_j} G),  G = D M^H (one more row-slice product, into the idle A_j D buffer);
-            // the constant sparse anticommutators come as (row, column, value) lists, three lanes per pair
-            double2 gr[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) gr[i] = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int jj = 0; jj < N; ++jj) {
-                double2 mv = vM[jj * N + cc];  // conj(M[cc][jj])
-                mv.y = -mv.y;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) cfma(gr[i], vD[jj * N + k3 + i], mv);
-            }
-            if (act) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) vU[(k3 + i) * N + cc] = gr[i];  // G[row][column]  (vU: its last reader ran before phase 1's flush)
-            }
-            __syncwarp();
-            constexpr int NPAIR = ND * (ND + 1) / 2;
-            const int pr = lane / 3, sub = lane - 3 * pr;
-            double val = 0.0;
-            if (pr < NPAIR)
-                for (int u = kkptr[pr] + sub, u1 = kkptr[pr + 1]; u < u1; u += 3) {
-                    const int rc = kkrc[u];
-                    const double2 kv = kkv[u];
-                    const double2 gv = vU[(rc & 255) * N + (rc >> 8)];  // K[r, k] G[k, r]
-                    val = fma(kv.x, gv.x, val);
-                    val = fma(-kv.y, gv.y, val);
-                }
-            const double v1 = __shfl_down_sync(0xffffffffu, val, 1), v2 = __shfl_down_sync(0xffffffffu, val, 2);
-            if (pr < NPAIR && sub == 0) {
-                int j = 0, rem = pr;
-                while (rem > j) { rem -= j + 1; ++j; }
-                const int q = qo_haa(rem, j);
-                if (c.pl_base[q] >= 0) imgH[c.pl_base[q]] = c2h2 * (val + v1 + v2);
-            }
-            s_hh = warp_sum(s_hh);
-#pragma unroll
-            for (int j = 0; j < ND; ++j) s_ah[j] = warp_sum(s_ah[j]);
-            if (lane == 0) {
-                if (c.pl_base[QO_HHH] >= 0) imgH[c.pl_base[QO_HHH]] = s_hh * (1.0 / 6.0);
-#pragma unroll
-                for (int j = 0; j < ND; ++j)
-                    if (c.pl_base[QO_HAH + j] >= 0) imgH[c.pl_base[QO_HAH + j]] = s_ah[j];
-            }
-            if (QCK_BULK_STORE) fence_async_smem();
-            __syncwarp();
-            write_units<2 * NN>(imgH, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & QCK_EVAL_H);
-            if (QCK_BULK_STORE && lane == 0) bulk_commit();
-            __syncwarp();
-        }
-    }
-    if (QCK_BULK_STORE && lane == 0) bulk_wait_all();
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Column kernel: Pade-4, unitaries, 2..4 levels (Hadamard / sampling problems).  ONE LANE per column of the unitaries:
-// N lanes per (knot, integrator) work item, 32 / N items per warp, no shared memory, no barriers.
-//
-// A lane holds ALL of A = -i H(a) (N x N complex) and its own columns d, s, m of D = U1 - U0, S = U1 + U0, M in registers;
-// every product of the path is a local matrix-vector product (same matrix-vector form as the row-slice kernel), the scalar
-// second derivatives are dot products summed over the item's N lanes with shuffles.  The constant drives A_j are read
-// (dense, per member) through L1.  A lane's values of one output quantity are 2N consecutive doubles of the value arrays
-// (its column of an iso-vector; its two columns of every copy of a kron(I_N, .) block), so they leave as 16-byte stores
-// straight from registers: no staging image.  Destinations per member come from the host's placement pass.
-// ------------------------------------------------------------------------------------------------------------
-// NC: columns of the state (N for unitaries, 1 for kets: QuantumStatePadeIntegrator = the same algebra on one column)
-template <int N, int ND, int NC>
-__global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
-    constexpr int n2 = 2 * N, blk = n2 * n2, IPW = 32 / NC, NPAIR = ND * (ND + 1) / 2;
-    const QckClassDev& c = p.c;
-    const int lane = threadIdx.x & 31;
-    const int gi = lane / NC, col = lane - gi * NC;  // item slot inside the warp, column
-    const bool needF = p.mask & QCK_EVAL_F, needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
-    const int nact = p.member_end - p.member_begin;
-    const long long n_items = p.n_knots * nact;
-    const long long nslots = (long long)gridDim.x * (blockDim.x >> 5) * IPW;
-    const bool free_time = c.free_time;
-
-    auto store_run = [](double* dst, const double (&v)[n2]) {  // 2N consecutive doubles, 16-byte stores where aligned
-        if (reinterpret_cast<uintptr_t>(dst) & 8) {
-            dst[0] = v[0];
-#pragma unroll
-            for (int i = 0; i < N - 1; ++i) *reinterpret_cast<double2*>(dst + 1 + 2 * i) = make_double2(v[1 + 2 * i], v[2 + 2 * i]);
-            dst[n2 - 1] = v[n2 - 1];
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) *reinterpret_cast<double2*>(dst + 2 * i) = make_double2(v[2 * i], v[2 * i + 1]);
-        }
-    };
-    auto rdot = [](double2 x, double2 y) { return x.x * y.x + x.y * y.y; };  // Re <x, y>
-    auto gsum = [&](double v) {  // sum over the N lanes of this lane's item
-        double r = v;
-#pragma unroll
-        for (int o = 1; o < NC; ++o) r += __shfl_sync(0xffffffffu, v, (gi * NC + (col + o) % NC) & 31);
-        return r;
-    };
-
-    for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * IPW; base < n_items; base += nslots) {
-        const long long item = base + gi;
-        const bool on = gi < IPW && item < n_items;
-        const long long it = on ? item : base;  // idle lanes shadow a valid item (no stores)
-        const long long t = it / nact;
-        const int mi = (int)(it - t * nact), m = p.member_begin + mi;
-        const int soff = p.moff_global[3 * mi], coff = p.moff_global[3 * mi + 1], roff = p.moff_global[3 * mi + 2];
-        const double* zt = p.Z + t * c.zdim;
-        const int* qd = c.qdst + (size_t)m * QO_COUNT;
-        double* const oF = p.F + t * c.dyn;
-        double* const oJ = p.J + t * p.nnzJ;
-        // iso-vector quantity q: this lane's column (rows 0..N-1 real, then imaginary); arr0 = start of the knot block
-        auto put_vec = [&](double* arr0, int d0, int q, const double2 (&x)[N]) {
-            const int st = c.pl_stride[q];
-            if (st == 1) {
-                double v[n2];
-#pragma unroll
-                for (int r = 0; r < N; ++r) { v[r] = x[r].x; v[N + r] = x[r].y; }
-                store_run(arr0 + d0 + col * n2, v);
-            } else {
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    arr0[d0 + (col * n2 + r) * st] = x[r].x;
-                    arr0[d0 + (col * n2 + N + r) * st] = x[r].y;
-                }
-            }
-        };
-        auto put_J = [&](int q, const double2 (&x)[N]) {
-            const int d0 = qd[q];
-            if (d0 >= 0 && on) put_vec(oJ, d0, q, x);
-        };
-        auto put_H = [&](int q, const double2 (&x)[N]) {  // (>= nnzH: partial column of a shared position)
-            const int d0 = qd[q];
-            if (d0 < 0 || !on) return;
-            if (d0 < p.nnzH) put_vec(p.H + t * p.nnzH, d0, q, x);
-            else put_vec(p.partial + t * p.npart, d0 - (int)p.nnzH, q, x);
-        };
-        auto put_scalar = [&](int q, double v) {
-            const int d0 = qd[q];
-            if (d0 < 0 || !on || col != 0) return;
-            if (d0 < p.nnzH) p.H[t * p.nnzH + d0] = v;
-            else p.partial[t * p.npart + (d0 - p.nnzH)] = v;
-        };
-        // ---- inputs: this lane's column of U0, U1 and of the multipliers ------------------------------------------------------
-        double2 d[N], s[N], mm[N];
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            const double u0r = zt[soff + col * n2 + r], u0i = zt[soff + col * n2 + N + r];
-            const double u1r = zt[c.zdim + soff + col * n2 + r], u1i = zt[c.zdim + soff + col * n2 + N + r];
-            d[r] = make_double2(u1r - u0r, u1i - u0i);
-            s[r] = make_double2(u1r + u0r, u1i + u0i);
-            mm[r] = needH ? make_double2(p.mu[t * c.dyn + roff + col * n2 + r], p.mu[t * c.dyn + roff + col * n2 + N + r]) : make_double2(0.0, 0.0);
-        }
-        const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
-        const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
-        double a[ND];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) a[j] = zt[coff + j];
-        // ---- A = A0 + sum_j a_j A_j ---------------------------------------------------------------------------------------------
-        const double2* const A0g = c.cmat + (size_t)m * c.cmat_stride;  // column-major
-        const double2* const Ajg = c.dense_aj + (size_t)m * ND * N * N;  // [drive][row][column]
-        double2 A[N][N];
-#pragma unroll
-        for (int r = 0; r < N; ++r)
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                double2 v = __ldg(A0g + r + N * k);
-#pragma unroll
-                for (int j = 0; j < ND; ++j) {
-                    const double2 w = __ldg(Ajg + (j * N + r) * N + k);
-                    v.x = fma(a[j], w.x, v.x);
-                    v.y = fma(a[j], w.y, v.y);
-                }
-                A[r][k] = v;
-            }
-        auto mvA = [&](double2 (&y)[N], const double2 (&x)[N]) {
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                y[r] = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int k = 0; k < N; ++k) cfma(y[r], A[r][k], x[k]);
-            }
-        };
-        auto mvAH = [&](double2 (&y)[N], const double2 (&x)[N]) {
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                y[r] = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int k = 0; k < N; ++k) cfma(y[r], make_double2(A[k][r].x, -A[k][r].y), x[k]);
-            }
-        };
-
-        // ---- residual, d/dh; q = -1/2 s + h/6 A d and v = -h/2 s + h^2/12 A d for the drive terms ---------------------------------
-        double2 qv[N], vv[N];
-        double s_hh = 0.0;
-        {
-            double2 x1[N], x2[N], x3[N], o[N];
-            mvA(x1, s);
-            mvA(x2, d);
-            mvA(x3, x2);
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                qv[r] = make_double2(-0.5 * s[r].x + c2h * x2[r].x, -0.5 * s[r].y + c2h * x2[r].y);
-                vv[r] = make_double2(-c1h * s[r].x + c2h2 * x2[r].x, -c1h * s[r].y + c2h2 * x2[r].y);
-                s_hh += rdot(mm[r], x3[r]);
-            }
-            if (needF && on && qd[QO_R] >= 0) {
-#pragma unroll
-                for (int r = 0; r < N; ++r) o[r] = make_double2(d[r].x - c1h * x1[r].x + c2h2 * x3[r].x, d[r].y - c1h * x1[r].y + c2h2 * x3[r].y);
-                put_vec(oF, qd[QO_R], QO_R, o);
-            }
-            if (needJ) {
-#pragma unroll
-                for (int r = 0; r < N; ++r) o[r] = make_double2(-0.5 * x1[r].x + c2h * x3[r].x, -0.5 * x1[r].y + c2h * x3[r].y);
-                put_J(QO_TH, o);
-            }
-        }
-        // ---- -iso(F), +iso(B): this lane's columns (col, col + N) of the 2N x 2N block, into every one of the N copies -------------
-        if (needJ && on && qd[QO_ISOF] >= 0) {
-            const int dF = qd[QO_ISOF], dB = qd[QO_ISOB];
-            auto block_columns = [&](int bc, const double2 (&acol)[N], int copy0, int copy1) {  // columns bc, bc + N of the block
-                double2 a2[N];
-                mvA(a2, acol);
-                double f0[n2], f1[n2], b0[n2], b1[n2];
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    const double id = r == bc ? 1.0 : 0.0;
-                    const double fr = id + c1h * acol[r].x + c2h2 * a2[r].x, fi = c1h * acol[r].y + c2h2 * a2[r].y;
-                    const double br = id - c1h * acol[r].x + c2h2 * a2[r].x, bi = -c1h * acol[r].y + c2h2 * a2[r].y;
-                    f0[r] = -fr; f0[N + r] = -fi; f1[r] = fi; f1[N + r] = -fr;
-                    b0[r] = br;  b0[N + r] = bi;  b1[r] = -bi; b1[N + r] = br;
-                }
-                for (int cb = copy0; cb < copy1; ++cb) {
-                    store_run(oJ + dF + cb * blk + bc * n2, f0);
-                    store_run(oJ + dF + cb * blk + (bc + N) * n2, f1);
-                    if (dB >= 0) {
-                        store_run(oJ + dB + cb * blk + bc * n2, b0);
-                        store_run(oJ + dB + cb * blk + (bc + N) * n2, b1);
-                    }
-                }
-            };
-            if constexpr (NC == N) {  // unitary: this lane's column pair, into every one of the N copies
-                double2 acol[N];
-#pragma unroll
-                for (int k = 0; k < N; ++k) {  // column `col` of A (a lane-dependent column: rebuilt from the constants)
-                    double2 v = __ldg(A0g + k + N * col);
-#pragma unroll
-                    for (int j = 0; j < ND; ++j) {
-                        const double2 w = __ldg(Ajg + (j * N + k) * N + col);
-                        v.x = fma(a[j], w.x, v.x);
-                        v.y = fma(a[j], w.y, v.y);
-                    }
-                    acol[k] = v;
-                }
-                block_columns(col, acol, 0, N);
-            } else {  // ket: the single lane writes all column pairs of the one block
-#pragma unroll
-                for (int bc = 0; bc < N; ++bc) {
-                    double2 acol[N];
-#pragma unroll
-                    for (int k = 0; k < N; ++k) acol[k] = A[k][bc];
-                    block_columns(bc, acol, 0, 1);
-                }
-            }
-        }
-        // ---- drive terms -----------------------------------------------------------------------------------------------------------------
-        double2 u[ND][N];
-        if (needJ || needH) {
-#pragma unroll
-            for (int j = 0; j < ND; ++j) {
-                double2 y[N], y3[N];
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    y[r] = u[j][r] = make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        const double2 w = __ldg(Ajg + (j * N + r) * N + k);
-                        cfma(y[r], w, vv[k]);
-                        cfma(u[j][r], w, d[k]);
-                    }
-                }
-                mvA(y3, u[j]);
-                if (needJ) {
-#pragma unroll
-                    for (int r = 0; r < N; ++r) y[r] = make_double2(y[r].x + c2h2 * y3[r].x, y[r].y + c2h2 * y3[r].y);
-                    put_J(QO_TA + j, y);
-                }
-            }
-        }
-        if (needH) {
-            double2 w1[N];
-            double s_ah[ND], pz[ND][ND];  // pz[i][j] = Re <A_i^H m, A_j d> (this lane's column)
-            {
-                double2 w2[N], o[N];
-                mvAH(w1, mm);
-                mvAH(w2, w1);
-#pragma unroll
-                for (int r = 0; r < N; ++r) o[r] = make_double2(-0.5 * w1[r].x - c2h * w2[r].x, -0.5 * w1[r].y - c2h * w2[r].y);
-                put_H(QO_KH0, o);
-#pragma unroll
-                for (int r = 0; r < N; ++r) o[r] = make_double2(-0.5 * w1[r].x + c2h * w2[r].x, -0.5 * w1[r].y + c2h * w2[r].y);
-                put_H(QO_KH1, o);
-            }
-#pragma unroll
-            for (int j = 0; j < ND; ++j) {
-                double2 z1[N], z2[N], z3[N], o[N];
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    z1[r] = z2[r] = make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        double2 w = __ldg(Ajg + (j * N + k) * N + r);  // conj(A_j[k][r])
-                        w.y = -w.y;
-                        cfma(z1[r], w, mm[k]);
-                        cfma(z2[r], w, w1[k]);
-                    }
-                }
-                mvAH(z3, z1);
-                s_ah[j] = 0.0;
-#pragma unroll
-                for (int i2 = 0; i2 < ND; ++i2) pz[j][i2] = 0.0;
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    const double cr = c2h2 * (z2[r].x + z3[r].x), ci = c2h2 * (z2[r].y + z3[r].y);
-                    o[r] = make_double2(-c1h * z1[r].x - cr, -c1h * z1[r].y - ci);
-                    z2[r] = make_double2(-c1h * z1[r].x + cr, -c1h * z1[r].y + ci);
-                    s_ah[j] += rdot(z1[r], qv[r]) + c2h * rdot(w1[r], u[j][r]);
-#pragma unroll
-                    for (int i2 = 0; i2 < ND; ++i2) pz[j][i2] += rdot(z1[r], u[i2][r]);
-                }
-                put_H(QO_KA0 + j, o);
-                put_H(QO_KA1 + j, z2);
-            }
-            double s_aa[NPAIR];
-#pragma unroll
-            for (int j = 0, q = 0; j < ND; ++j)
-#pragma unroll
-                for (int i2 = 0; i2 <= j; ++i2, ++q) s_aa[q] = pz[i2][j] + pz[j][i2];
-            s_hh = gsum(s_hh);
-            put_scalar(QO_HHH, s_hh * (1.0 / 6.0));
-#pragma unroll
-            for (int j = 0; j < ND; ++j) put_scalar(QO_HAH + j, gsum(s_ah[j]));
-#pragma unroll
-            for (int j = 0, q = 0; j < ND; ++j)
-#pragma unroll
-                for (int i2 = 0; i2 <= j; ++i2, ++q) put_scalar(qo_haa(i2, j), c2h2 * gsum(s_aa[q]));
-        }
-        if (mi == 0 && p.n_aux && on) do_aux(p, t, col, NC);  // derivative-integrator entries of this knot
-    }
-}
-
 __global__ void qck_aux_kernel(const QckLaunch p) {
     for (long long t = blockIdx.x; t < p.n_knots; t += gridDim.x) do_aux(p, t, threadIdx.x, blockDim.x);
 }
@@ -2408,83 +1484,6 @@ static qck_kernel_t kernel_for(int N, bool multi) {
 
 #define QCK_MAX_FUSED_AUX 256
 
-// one warp per knot, A rows in registers (9-level Pade-4 unitaries, one active member, up to four drives)
-static int launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done) {
-    const QckClassDev& c = L.c;
-    *done = false;
-    static const int enabled = getenv("QCK_ROWSLICE") ? atoi(getenv("QCK_ROWSLICE")) : 1;
-    if (!enabled || c.kind != QCK_UNITARY_PADE || c.order != 4 || c.N != 9 || L.member_end - L.member_begin != 1 || c.nd < 1 || c.nd > 4) return 0;
-    typedef void (*kern_t)(const QckLaunch);
-    static const int sparse_ok = getenv("QCK_ROWSLICE_DENSE") ? 0 : 1;
-    const int wc = sparse_ok && c.W <= 2 ? c.W : 0;  // sparse drive rows of width 1 or 2 are unrolled; wider ones run dense
-    kern_t kern;
-#define QCK_RS(ND_) (c.antiherm ? (wc == 1 ? qck_rowslice9_kernel<ND_, 1, true> : (wc == 2 ? qck_rowslice9_kernel<ND_, 2, true> : qck_rowslice9_kernel<ND_, 0, true>)) \
-                                 : (wc == 1 ? qck_rowslice9_kernel<ND_, 1, false> : (wc == 2 ? qck_rowslice9_kernel<ND_, 2, false> : qck_rowslice9_kernel<ND_, 0, false>)))
-    kern = c.nd == 1 ? QCK_RS(1) : (c.nd == 2 ? QCK_RS(2) : (c.nd == 3 ? QCK_RS(3) : QCK_RS(4)));
-#undef QCK_RS
-    const int nrec = QCK_SEG_HDR / 4 + c.nseg;
-    // staging: F + J part and Hessian part of the output image share one buffer (the Hessian part starts at hoff)
-    int hoff = c.img_doubles;
-    for (int q = 0; q < QO_COUNT; ++q) {
-        const bool hq = q == QO_KH0 || q == QO_KH1 || (q >= QO_KA0 && q < QO_ONE);
-        if (hq && c.pl_base[q] >= 0 && c.pl_base[q] < hoff) hoff = c.pl_base[q];
-    }
-    hoff &= ~1;
-    const int stage_doubles = hoff > c.img_doubles - hoff ? hoff : c.img_doubles - hoff;
-    const size_t per_warp = (size_t)((stage_doubles + 1) & ~1) * 8 + 8 * 81 * 16;
-    const size_t shared = ((((size_t)(81 + c.ell_stride + c.kk_cap + c.ac_cap) * 16 + (size_t)c.icon_stride * 4) + 15) & ~(size_t)15) + (size_t)nrec * 16 +
-                          (wc > 0 ? 0 : (size_t)c.nd * 81 * 16);
-    int nwarps = 8;
-    static const int knob = getenv("QCK_ROWSLICE_WARPS") ? atoi(getenv("QCK_ROWSLICE_WARPS")) : 0;
-    if (knob >= 1 && knob <= 8) nwarps = knob;
-    while (nwarps > 1 && shared + nwarps * per_warp > 227 * 1024) --nwarps;
-    const size_t smem = shared + nwarps * per_warp;
-    if (smem > 227 * 1024) return 0;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    long long grid = sm_count;
-    if (grid * nwarps > L.n_knots) grid = (L.n_knots + nwarps - 1) / nwarps;
-    static const bool dbg = getenv("QCK_DEBUG") != nullptr;
-    if (dbg) fprintf(stderr, "[qcknot] row-slice kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d\n", c.nd, nwarps, smem, grid, c.nseg);
-    QckLaunch L2 = L;
-    L2.hoff = hoff;
-    kern<<<(unsigned)grid, nwarps * 32, smem, stream>>>(L2);
-    if (launches) ++*launches;
-    *done = true;
-    return (int)cudaGetLastError();
-}
-
-// one lane per column, everything in registers (2..4-level Pade-4 unitaries, up to four drives, any number of members)
-static int launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done) {
-    const QckClassDev& c = L.c;
-    *done = false;
-    static const int enabled = getenv("QCK_COLUMN") ? atoi(getenv("QCK_COLUMN")) : 1;
-    const bool ket = c.kind == QCK_KET_PADE;
-    if (!enabled || (c.kind != QCK_UNITARY_PADE && !ket) || c.order != 4 || c.N < 2 || c.N > 4 || c.nd < 1 || c.nd > 4 || !c.dense_aj || !c.qdst) return 0;
-    typedef void (*kern_t)(const QckLaunch);
-    kern_t kern = nullptr;
-#define QCK_COL2(N_, NC_) (c.nd == 1 ? qck_column_kernel<N_, 1, NC_> : (c.nd == 2 ? qck_column_kernel<N_, 2, NC_> : (c.nd == 3 ? qck_column_kernel<N_, 3, NC_> : qck_column_kernel<N_, 4, NC_>)))
-#define QCK_COL(N_) (ket ? QCK_COL2(N_, 1) : QCK_COL2(N_, N_))
-    kern = c.N == 2 ? QCK_COL(2) : (c.N == 3 ? QCK_COL(3) : QCK_COL(4));
-#undef QCK_COL
-#undef QCK_COL2
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return 0;
-    const long long n_items = L.n_knots * (long long)(L.member_end - L.member_begin);
-    const int ipw = 32 / (ket ? 1 : c.N);
-    long long grid = (long long)sm_count * per_sm;
-    const long long need = (n_items + 8LL * ipw - 1) / (8LL * ipw);
-    if (grid > need) grid = need;
-    static const bool dbg = getenv("QCK_DEBUG") != nullptr;
-    if (dbg) fprintf(stderr, "[qcknot] column kernel: N=%d nd=%d CTAs/SM=%d grid=%lld items=%lld\n", c.N, c.nd, per_sm, grid, n_items);
-    kern<<<(unsigned)grid, 256, 0, stream>>>(L);
-    if (launches) ++*launches;
-    *done = true;
-    return (int)cudaGetLastError();
-}
-
 int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, int* launches) {
     QckLaunch L = L0;
     const QckClassDev& c = L.c;
@@ -2492,9 +1491,9 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     if (n_items <= 0) return 0;
     {
         bool done = false;
-        int rc = launch_rowslice9(L, sm_count, stream, launches, &done);
+        int rc = qck_launch_rowslice9(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
-        rc = launch_column(L, sm_count, stream, launches, &done);
+        rc = qck_launch_column(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
     }
     const bool unitary = c.kind == QCK_UNITARY_PADE || c.kind == QCK_UNITARY_EXP;

@@ -1,0 +1,460 @@
+// Row-slice kernel (9-level Pade-4 unitaries, one warp per knot) of libqcknot.so.  Compiled as its own translation unit so that the kernel families build in parallel.
+#include "qck_device.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// Row-slice kernel: Pade-4, unitaries, 9 levels (the two-transmon CZ problem).  ONE WARP per knot, no block barriers.
+//
+// The columns of the unitaries are independent under every product of the path (R[:,c] = D[:,c] - h/2 A S[:,c] + ...), so
+// lane (c, k) of a warp owns rows 3k .. 3k+2 of column c (27 lanes) and keeps ITS THREE ROWS OF A = -i H(a) IN REGISTERS
+// for the whole knot.  Every dense product of the path becomes a row-slice matrix-vector product
+//     y[3k + i] = sum_j A[3k + i][j] x[j],     x = a full column read from shared memory (all lanes of a column read the
+// same address: broadcast), 27 complex FMAs per lane, no operand re-load from shared memory for A.  Products with the
+// constant drives A_j, with A_j^H and with A^H read their matrix from shared memory the same way.  In matrix-vector form
+//     R = d - h/2 A s + h^2/12 A (A d)                    d/dh = -1/2 A s + h/6 A (A d)
+//     d/da_j = A_j (-h/2 s + h^2/12 A d) + h^2/12 A (A_j d)
+//     state x dt:  -(1/2 w1 + h/6 A^H w1),  w1 = A^H m     state x a_j:  -(h/2 z1 + h^2/12 (A_j^H w1 + A^H z1)),  z1 = A_j^H m
+//     dt x dt = 1/6 sum Re<m, A A d>      a_j x dt = sum -1/2 Re<z1_j, s> + h/6 (Re<z1_j, A d> + Re<w1, A_j d>)
+//     a_i x a_j = h^2/12 sum (Re<z1_i, A_j d> + Re<z1_j, A_i d>)          (sums over rows and columns = one warp reduction)
+// 13 + 4 n_d row-slice products per knot.  Values go into the warp's own output image (same host placement and write-out
+// units as the tiled kernel), which the warp then copies out.
+// ------------------------------------------------------------------------------------------------------------
+// WC: compile-time width of the sparse rows of the drives (loops fully unrolled); 0 = dense drive matrices
+// AH: A is anti-Hermitian (Hermitian Hamiltonians): A^H x = -(A x) runs on the register-resident rows of A
+template <int ND, int WC, bool AH>
+__global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p) {
+    constexpr int N = 9, NN = 81, n2 = 18, dim = 162;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const QckClassDev& c = p.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool act = lane < 3 * N;
+    const int cc = act ? lane / 3 : 0, k3 = act ? 3 * (lane - 3 * (lane / 3)) : 0;  // column, first row of this lane
+    const bool needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
+    const bool needT = needJ || needH;
+    const bool free_time = c.free_time;
+    const int m = p.member_begin;
+    // CTA-wide tables: the member's constant block [A0 | sparse rows of A_j, A_j^H | anticommutator lists | contributor
+    // lists of A] (same layout as the tiled kernel's) and the write-out units
+    const int W = WC > 0 ? WC : c.W, elln = c.ell_stride, kkc = c.kk_cap, acn = c.ac_cap;
+    double2* const conv = reinterpret_cast<double2*>(smem_all);
+    const int nconv = NN + elln + kkc + acn;
+    int* const coni = reinterpret_cast<int*>(conv + nconv);
+    const int nrec = QCK_SEG_HDR / 4 + c.nseg;
+    QckSeg* const segtab = reinterpret_cast<QckSeg*>(smem_all + (((size_t)nconv * 16 + (size_t)c.icon_stride * 4 + 15) & ~(size_t)15));
+    // output staging: the F + J part of the image first, flushed, then the Hessian part in the same space
+    const int hoff = p.hoff, stage_doubles = hoff > c.img_doubles - hoff ? hoff : c.img_doubles - hoff;
+    const int img_bytes = ((stage_doubles + 1) & ~1) * 8;
+    double2* const cAj = reinterpret_cast<double2*>(segtab + nrec);  // WC == 0: dense A_j, row-major
+    unsigned char* const wbase = reinterpret_cast<unsigned char*>(cAj + (WC > 0 ? 0 : ND * NN)) + (size_t)warp * (img_bytes + 8 * NN * 16);
+    double* const imgJ = reinterpret_cast<double*>(wbase);
+    double* const imgH = imgJ - hoff;
+    double2* const vD = reinterpret_cast<double2*>(wbase + img_bytes);  // columns of D = U1 - U0: element [c * 9 + r]
+    double2* const vS = vD + NN;       // S = U1 + U0
+    double2* const vM = vS + NN;       // multipliers
+    double2* const vX2 = vM + NN;      // A D
+    double2* const vW1 = vX2 + NN;     // A^H M
+    double2* const vU = vW1 + NN;      // A_j D (current drive)
+    double2* const vZ1 = vU + NN;      // A_j^H M (current drive)
+    double2* const mA = vZ1 + NN;      // A, row-major (for A^H products and column access)
+    {
+        const double2* gv = c.cmat + (size_t)m * c.cmat_stride;
+        const int* gc = c.ell_col + (size_t)m * c.icon_stride;
+        for (int e = threadIdx.x; e < nconv; e += blockDim.x) conv[e] = gv[e];
+        for (int e = threadIdx.x; e < c.icon_stride; e += blockDim.x) coni[e] = gc[e];
+        const QckSeg* gs = c.segs + (size_t)m * nrec;
+        for (int i = threadIdx.x; i < nrec; i += blockDim.x) segtab[i] = gs[i];
+        for (int i = lane; i < img_bytes / 8; i += 32) imgJ[i] = 0.0;
+        if (WC == 0) {
+            for (int e = threadIdx.x; e < ND * NN; e += blockDim.x) cAj[e] = make_double2(0.0, 0.0);
+            __syncthreads();
+            for (int w = threadIdx.x; w < ND * N * W; w += blockDim.x) {  // dense A_j from the fixed-width sparse rows
+                const int j = w / (N * W), rem = w - j * N * W, r = rem / W, u = rem - r * W;
+                const int o = ((j * 2) * N + r) * W + u;
+                const double2 v = gv[NN + o];
+                if (v.x != 0.0 || v.y != 0.0) cAj[j * NN + r * N + gc[o]] = v;
+            }
+        }
+        __syncthreads();
+    }
+    const double2* const A0 = conv;
+    const double2* const ellv = conv + NN;
+    const double2* const kkv = ellv + elln;
+    const double2* const acv = kkv + kkc;
+    const int* const ellc = coni;
+    const int* const kkptr = coni + elln;
+    const int* const kkrc = kkptr + ND * (ND + 1) / 2 + 1;
+    const int* const acptr = kkrc + kkc;
+    const int* const acj = acptr + NN + 1;
+    const int* seghdr = reinterpret_cast<const int*>(segtab);
+    const QckSeg* segs = segtab + QCK_SEG_HDR / 4;
+    const int soff = p.moff_global[0], coff = p.moff_global[1], roff = p.moff_global[2];
+    const int xo = cc * N;  // this lane's column inside the vector buffers
+
+    for (long long t = (long long)blockIdx.x * nwarps + warp; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
+        const double* zt = p.Z + t * c.zdim;
+        // ---- inputs: coalesced loads of the two state vectors and the multipliers, unpacked into complex columns ----------
+        constexpr int NLD = (dim + 31) / 32;
+        double in0[NLD], in1[NLD], inm[NLD];  // all global loads of the knot are issued before the first use
+        {
+            const double* mut = p.mu + t * c.dyn + roff;
+#pragma unroll
+            for (int q = 0; q < NLD; ++q) {
+                const int idx = lane + 32 * q;
+                const bool ok = idx < dim;
+                in0[q] = ok ? zt[soff + idx] : 0.0;
+                in1[q] = ok ? zt[c.zdim + soff + idx] : 0.0;
+                inm[q] = ok && needH ? mut[idx] : 0.0;
+            }
+        }
+        const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
+        if (t + (long long)gridDim.x * nwarps < p.n_knots) {  // pull the next knot of this warp into L2 meanwhile
+            const double* zn = zt + (long long)gridDim.x * nwarps * c.zdim;
+            const double* mn = p.mu + (t + (long long)gridDim.x * nwarps) * c.dyn + roff;
+            for (int b = lane * 16; b < 2 * c.zdim; b += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(zn + b));
+            if (needH)
+                for (int b = lane * 16; b < dim; b += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(mn + b));
+        }
+        const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int idx = lane + 32 * q;
+            if (idx < dim) {
+                const int col = idx / n2, qq = idx - col * n2, im = qq >= N, r = qq - im * N;
+                const int o = 2 * (col * N + r) + im;
+                reinterpret_cast<double*>(vD)[o] = in1[q] - in0[q];
+                reinterpret_cast<double*>(vS)[o] = in1[q] + in0[q];
+                if (needH) reinterpret_cast<double*>(vM)[o] = inm[q];
+            }
+        }
+        // ---- A = A0 + sum_j a_j A_j (per-element contributor lists) into shared memory, this lane's three rows into registers
+        for (int e = lane; e < NN; e += 32) {
+            double2 v = A0[e];
+            for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
+                const double aj = __ldg(zt + coff + acj[u]);  // (L1 hit: the controls were just loaded)
+                const double2 d = acv[u];
+                v.x = fma(aj, d.x, v.x);
+                v.y = fma(aj, d.y, v.y);
+            }
+            mA[(e % N) * N + e / N] = v;  // A0 is column-major
+        }
+        __syncwarp();
+        double2 Ar[3][N];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) Ar[i][j] = mA[(k3 + i) * N + j];
+        // row-slice products: y[i] = sum_j Mat[3k + i][j] x[j]
+        auto mv_reg = [&](double2 (&y)[3], const double2* x) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) y[i] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 xv = x[j];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cfma(y[i], Ar[i][j], xv);
+            }
+        };
+        auto mvH = [&](double2 (&y)[3], const double2* Mat, const double2* x) {  // y = Mat^H x
+#pragma unroll
+            for (int i = 0; i < 3; ++i) y[i] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 xv = x[j];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    double2 mv = Mat[j * N + k3 + i];
+                    mv.y = -mv.y;
+                    cfma(y[i], mv, xv);
+                }
+            }
+        };
+        auto put = [&](double* image, int q, int i, double2 v) {  // element (row k3 + i, column cc) of an iso-vector quantity
+            const int b = c.pl_base[q], s = c.pl_stride[q], ire = cc * n2 + k3 + i;
+            if (b >= 0 && act) { image[b + ire * s] = v.x; image[b + (ire + N) * s] = v.y; }
+        };
+        auto rdot = [](double2 x, double2 y) { return x.x * y.x + x.y * y.y; };  // Re <x, y>
+        auto mvAH = [&](double2 (&y)[3], const double2* x) {  // y = A^H x
+            if constexpr (AH) {
+                mv_reg(y, x);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) y[i] = make_double2(-y[i].x, -y[i].y);
+            } else {
+                mvH(y, mA, x);
+            }
+        };
+
+        double s_hh = 0.0, s_ah[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s_ah[j] = 0.0;
+        double2 w1[3];
+        {
+            double2 x1[3], x2[3], x3[3];
+            mv_reg(x1, vS + xo);
+            mv_reg(x2, vD + xo);
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) vX2[xo + k3 + i] = x2[i];
+            }
+            if (needH) {
+                mvAH(w1, vM + xo);
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) vW1[xo + k3 + i] = w1[i];
+                }
+            }
+            __syncwarp();
+            mv_reg(x3, vX2 + xo);
+            if (needH && act) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) s_hh += rdot(vM[xo + k3 + i], x3[i]);
+            }
+            if (QCK_BULK_STORE) {
+                if (lane == 0) bulk_wait_read();  // the copy engine has finished reading the previous knot's staging buffer
+                __syncwarp();
+            }
+            // ---- phase 1: residual and Jacobian values ---------------------------------------------------------------------------
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double2 d = vD[xo + k3 + i];
+                put(imgJ, QO_R, i, make_double2(d.x - c1h * x1[i].x + c2h2 * x3[i].x, d.y - c1h * x1[i].y + c2h2 * x3[i].y));
+                put(imgJ, QO_TH, i, make_double2(-0.5 * x1[i].x + c2h * x3[i].x, -0.5 * x1[i].y + c2h * x3[i].y));
+            }
+        }
+        if (needJ) {  // column cc of A^2 -> -iso(F), +iso(B)
+            double2 a2[3], acol[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) acol[j] = mA[j * N + cc];
+            mv_reg(a2, acol);
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int r = k3 + i;
+                    const double2 av = mA[r * N + cc];
+                    const double id = r == cc ? 1.0 : 0.0;
+                    const double fr = id + c1h * av.x + c2h2 * a2[i].x, fi = c1h * av.y + c2h2 * a2[i].y;
+                    const double br = id - c1h * av.x + c2h2 * a2[i].x, bi = -c1h * av.y + c2h2 * a2[i].y;
+                    const int k00 = r + n2 * cc, k01 = r + n2 * (cc + N);
+                    const int bF = c.pl_base[QO_ISOF], sF = c.pl_stride[QO_ISOF], bB = c.pl_base[QO_ISOB], sB = c.pl_stride[QO_ISOB];
+                    imgJ[bF + k00 * sF] = -fr; imgJ[bF + (k00 + N) * sF] = -fi; imgJ[bF + k01 * sF] = fi; imgJ[bF + (k01 + N) * sF] = -fr;
+                    imgJ[bB + k00 * sB] = br;  imgJ[bB + (k00 + N) * sB] = bi;  imgJ[bB + k01 * sB] = -bi; imgJ[bB + (k01 + N) * sB] = br;
+                }
+            }
+        }
+        if (needT) {
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                double2 y[3], u[3], y3[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) y[i] = u[i] = make_double2(0.0, 0.0);
+                // y = A_j (-h/2 s + h^2/12 A d),  u = A_j d
+                if constexpr (WC > 0) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int o0 = ((j * 2) * N + k3 + i) * WC;
+#pragma unroll
+                        for (int w = 0; w < WC; ++w) {
+                            const double2 av = ellv[o0 + w];
+                            const int col = xo + ellc[o0 + w];
+                            const double2 sv = vS[col], xv = vX2[col];
+                            cfma(y[i], av, make_double2(-c1h * sv.x + c2h2 * xv.x, -c1h * sv.y + c2h2 * xv.y));
+                            cfma(u[i], av, vD[col]);
+                        }
+                    }
+                } else {
+                    const double2* Aj = cAj + j * NN;
+#pragma unroll
+                    for (int jj = 0; jj < N; ++jj) {
+                        const double2 sv = vS[xo + jj], xv = vX2[xo + jj], dv = vD[xo + jj];
+                        const double2 vv = make_double2(-c1h * sv.x + c2h2 * xv.x, -c1h * sv.y + c2h2 * xv.y);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const double2 aij = Aj[(k3 + i) * N + jj];
+                            cfma(y[i], aij, vv);
+                            cfma(u[i], aij, dv);
+                        }
+                    }
+                }
+                __syncwarp();  // the previous drive's readers of vU are done
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) vU[xo + k3 + i] = u[i];
+                }
+                __syncwarp();
+                mv_reg(y3, vU + xo);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    put(imgJ, QO_TA + j, i, make_double2(y[i].x + c2h2 * y3[i].x, y[i].y + c2h2 * y3[i].y));
+                    if (needH && act) s_ah[j] += c2h * rdot(w1[i], u[i]);
+                }
+            }
+        }
+        if (p.n_aux) do_aux(p, t, lane, 32);  // derivative-integrator entries of this knot
+        if (QCK_BULK_STORE) fence_async_smem();
+        __syncwarp();
+        write_units<2 * NN>(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
+        if (QCK_BULK_STORE && lane == 0) bulk_commit();
+        __syncwarp();
+        // ---- phase 2: Hessian-of-Lagrangian values, staged in the same buffer ------------------------------------------------------
+        if (needH) {
+            double2 w2[3];
+            mvAH(w2, vW1 + xo);
+            if (QCK_BULK_STORE) {
+                if (lane == 0) bulk_wait_read();  // phase-1 copies have left the buffer
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                put(imgH, QO_KH0, i, make_double2(-0.5 * w1[i].x - c2h * w2[i].x, -0.5 * w1[i].y - c2h * w2[i].y));
+                put(imgH, QO_KH1, i, make_double2(-0.5 * w1[i].x + c2h * w2[i].x, -0.5 * w1[i].y + c2h * w2[i].y));
+            }
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                double2 z1[3], z2[3], z3[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) z1[i] = z2[i] = make_double2(0.0, 0.0);
+                // z1 = A_j^H m,  z2 = A_j^H w1
+                if constexpr (WC > 0) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int o1 = ((j * 2 + 1) * N + k3 + i) * WC;  // (the table holds the rows of A_j^H)
+#pragma unroll
+                        for (int w = 0; w < WC; ++w) {
+                            const double2 av = ellv[o1 + w];
+                            const int col = xo + ellc[o1 + w];
+                            cfma(z1[i], av, vM[col]);
+                            cfma(z2[i], av, vW1[col]);
+                        }
+                    }
+                } else {
+                    const double2* Aj = cAj + j * NN;
+#pragma unroll
+                    for (int jj = 0; jj < N; ++jj) {
+                        const double2 mv = vM[xo + jj], wv = vW1[xo + jj];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            double2 aji = Aj[jj * N + k3 + i];
+                            aji.y = -aji.y;
+                            cfma(z1[i], aji, mv);
+                            cfma(z2[i], aji, wv);
+                        }
+                    }
+                }
+                __syncwarp();  // the previous drive's readers of vZ1 are done
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) vZ1[xo + k3 + i] = z1[i];
+                }
+                __syncwarp();
+                mvAH(z3, vZ1 + xo);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double cr = c2h2 * (z2[i].x + z3[i].x), ci = c2h2 * (z2[i].y + z3[i].y);
+                    put(imgH, QO_KA0 + j, i, make_double2(-c1h * z1[i].x - cr, -c1h * z1[i].y - ci));
+                    put(imgH, QO_KA1 + j, i, make_double2(-c1h * z1[i].x + cr, -c1h * z1[i].y + ci));
+                    if (act) s_ah[j] += -0.5 * rdot(z1[i], vS[xo + k3 + i]) + c2h * rdot(z1[i], vX2[xo + k3 + i]);
+                }
+            }
+            // a_i x a_j = h^2/12 Re tr({A_i, A_j} G),  G = D M^H (one more row-slice product, into the idle A_j D buffer);
+            // the constant sparse anticommutators come as (row, column, value) lists, three lanes per pair
+            double2 gr[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) gr[i] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int jj = 0; jj < N; ++jj) {
+                double2 mv = vM[jj * N + cc];  // conj(M[cc][jj])
+                mv.y = -mv.y;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cfma(gr[i], vD[jj * N + k3 + i], mv);
+            }
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) vU[(k3 + i) * N + cc] = gr[i];  // G[row][column]  (vU: its last reader ran before phase 1's flush)
+            }
+            __syncwarp();
+            constexpr int NPAIR = ND * (ND + 1) / 2;
+            const int pr = lane / 3, sub = lane - 3 * pr;
+            double val = 0.0;
+            if (pr < NPAIR)
+                for (int u = kkptr[pr] + sub, u1 = kkptr[pr + 1]; u < u1; u += 3) {
+                    const int rc = kkrc[u];
+                    const double2 kv = kkv[u];
+                    const double2 gv = vU[(rc & 255) * N + (rc >> 8)];  // K[r, k] G[k, r]
+                    val = fma(kv.x, gv.x, val);
+                    val = fma(-kv.y, gv.y, val);
+                }
+            const double v1 = __shfl_down_sync(0xffffffffu, val, 1), v2 = __shfl_down_sync(0xffffffffu, val, 2);
+            if (pr < NPAIR && sub == 0) {
+                int j = 0, rem = pr;
+                while (rem > j) { rem -= j + 1; ++j; }
+                const int q = qo_haa(rem, j);
+                if (c.pl_base[q] >= 0) imgH[c.pl_base[q]] = c2h2 * (val + v1 + v2);
+            }
+            s_hh = warp_sum(s_hh);
+#pragma unroll
+            for (int j = 0; j < ND; ++j) s_ah[j] = warp_sum(s_ah[j]);
+            if (lane == 0) {
+                if (c.pl_base[QO_HHH] >= 0) imgH[c.pl_base[QO_HHH]] = s_hh * (1.0 / 6.0);
+#pragma unroll
+                for (int j = 0; j < ND; ++j)
+                    if (c.pl_base[QO_HAH + j] >= 0) imgH[c.pl_base[QO_HAH + j]] = s_ah[j];
+            }
+            if (QCK_BULK_STORE) fence_async_smem();
+            __syncwarp();
+            write_units<2 * NN>(imgH, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & QCK_EVAL_H);
+            if (QCK_BULK_STORE && lane == 0) bulk_commit();
+            __syncwarp();
+        }
+    }
+    if (QCK_BULK_STORE && lane == 0) bulk_wait_all();
+}
+
+
+}  // namespace
+
+// one warp per knot, A rows in registers (9-level Pade-4 unitaries, one active member, up to four drives)
+int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done) {
+    const QckClassDev& c = L.c;
+    *done = false;
+    static const int enabled = getenv("QCK_ROWSLICE") ? atoi(getenv("QCK_ROWSLICE")) : 1;
+    if (!enabled || c.kind != QCK_UNITARY_PADE || c.order != 4 || c.N != 9 || L.member_end - L.member_begin != 1 || c.nd < 1 || c.nd > 4) return 0;
+    typedef void (*kern_t)(const QckLaunch);
+    static const int sparse_ok = getenv("QCK_ROWSLICE_DENSE") ? 0 : 1;
+    const int wc = sparse_ok && c.W <= 2 ? c.W : 0;  // sparse drive rows of width 1 or 2 are unrolled; wider ones run dense
+    kern_t kern;
+#define QCK_RS(ND_) (c.antiherm ? (wc == 1 ? qck_rowslice9_kernel<ND_, 1, true> : (wc == 2 ? qck_rowslice9_kernel<ND_, 2, true> : qck_rowslice9_kernel<ND_, 0, true>)) \
+                                 : (wc == 1 ? qck_rowslice9_kernel<ND_, 1, false> : (wc == 2 ? qck_rowslice9_kernel<ND_, 2, false> : qck_rowslice9_kernel<ND_, 0, false>)))
+    kern = c.nd == 1 ? QCK_RS(1) : (c.nd == 2 ? QCK_RS(2) : (c.nd == 3 ? QCK_RS(3) : QCK_RS(4)));
+#undef QCK_RS
+    const int nrec = QCK_SEG_HDR / 4 + c.nseg;
+    // staging: F + J part and Hessian part of the output image share one buffer (the Hessian part starts at hoff)
+    int hoff = c.img_doubles;
+    for (int q = 0; q < QO_COUNT; ++q) {
+        const bool hq = q == QO_KH0 || q == QO_KH1 || (q >= QO_KA0 && q < QO_ONE);
+        if (hq && c.pl_base[q] >= 0 && c.pl_base[q] < hoff) hoff = c.pl_base[q];
+    }
+    hoff &= ~1;
+    const int stage_doubles = hoff > c.img_doubles - hoff ? hoff : c.img_doubles - hoff;
+    const size_t per_warp = (size_t)((stage_doubles + 1) & ~1) * 8 + 8 * 81 * 16;
+    const size_t shared = ((((size_t)(81 + c.ell_stride + c.kk_cap + c.ac_cap) * 16 + (size_t)c.icon_stride * 4) + 15) & ~(size_t)15) + (size_t)nrec * 16 +
+                          (wc > 0 ? 0 : (size_t)c.nd * 81 * 16);
+    int nwarps = 8;
+    static const int knob = getenv("QCK_ROWSLICE_WARPS") ? atoi(getenv("QCK_ROWSLICE_WARPS")) : 0;
+    if (knob >= 1 && knob <= 8) nwarps = knob;
+    while (nwarps > 1 && shared + nwarps * per_warp > 227 * 1024) --nwarps;
+    const size_t smem = shared + nwarps * per_warp;
+    if (smem > 227 * 1024) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    long long grid = sm_count;
+    if (grid * nwarps > L.n_knots) grid = (L.n_knots + nwarps - 1) / nwarps;
+    static const bool dbg = getenv("QCK_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "[qcknot] row-slice kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d\n", c.nd, nwarps, smem, grid, c.nseg);
+    QckLaunch L2 = L;
+    L2.hoff = hoff;
+    kern<<<(unsigned)grid, nwarps * 32, smem, stream>>>(L2);
+    if (launches) ++*launches;
+    *done = true;
+    return (int)cudaGetLastError();
+}
+
