@@ -16,9 +16,10 @@ namespace {
 //     d/da_j = A_j (-h/2 s + h^2/12 A d) + h^2/12 A (A_j d)
 //     state x dt:  -(1/2 w1 + h/6 A^H w1),  w1 = A^H m     state x a_j:  -(h/2 z1 + h^2/12 (A_j^H w1 + A^H z1)),  z1 = A_j^H m
 //     dt x dt = 1/6 sum Re<m, A A d>      a_j x dt = sum -1/2 Re<z1_j, s> + h/6 (Re<z1_j, A d> + Re<w1, A_j d>)
-//     a_i x a_j = h^2/12 sum (Re<z1_i, A_j d> + Re<z1_j, A_i d>)          (sums over rows and columns = one warp reduction)
-// 13 + 4 n_d row-slice products per knot.  Values go into the warp's own output image (same host placement and write-out
-// units as the tiled kernel), which the warp then copies out.
+//     a_i x a_j = h^2/12 Re tr({A_i, A_j} G),  G = D M^H     (sums over rows and columns = one warp reduction each)
+// 8 + 2 n_d dense row-slice products and 4 n_d products with the (sparse) drives per knot.  Values go into the warp's
+// staging buffer in the solver's structure order (same host placement and write-out units as the tiled kernel): first the
+// residual + Jacobian part, flushed, then the Hessian part in the same space.
 // ------------------------------------------------------------------------------------------------------------
 // WC: compile-time width of the sparse rows of the drives (loops fully unrolled); 0 = dense drive matrices
 // AH: A is anti-Hermitian (Hermitian Hamiltonians): A^H x = -(A x) runs on the register-resident rows of A
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
     const int soff = p.moff_global[0], coff = p.moff_global[1], roff = p.moff_global[2];
     const int xo = cc * N;  // this lane's column inside the vector buffers
 
-    for (long long t = (long long)blockIdx.x * nwarps + warp; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
+    // warp-major slots: the last, partially filled round spreads over all SMs (fewer active warps per SM run faster each)
+    for (long long t = (long long)warp * gridDim.x + blockIdx.x; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
         const double* zt = p.Z + t * c.zdim;
         // ---- inputs: coalesced loads of the two state vectors and the multipliers, unpacked into complex columns ----------
         constexpr int NLD = (dim + 31) / 32;
