@@ -4,7 +4,7 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------------------
-// Column kernel: Pade-4, unitaries, 2..4 levels (Hadamard / sampling problems).  ONE LANE per column of the unitaries:
+// Column kernel: Pade-4, unitaries and kets, 2..4 levels (Hadamard / sampling / quantum-state problems).  ONE LANE per column:
 // N lanes per (knot, integrator) work item, 32 / N items per warp, no shared memory, no barriers.
 //
 // A lane holds ALL of A = -i H(a) (N x N complex) and its own columns d, s, m of D = U1 - U0, S = U1 + U0, M in registers;
