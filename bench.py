@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--integrator", default="pade", choices=["pade", "exponential"])
     ap.add_argument("--T", type=int, default=10000, help="knot points per GPU")
     ap.add_argument("--systems", type=int, default=None, help="sampled systems (sampling workload)")
+    ap.add_argument("--shard", default="knot", choices=["knot", "ensemble"],
+                    help="knot: every GPU evaluates T knots (weak scaling); ensemble (sampling workload): the sampled systems are "
+                         "split over the GPUs, shared-control Hessian entries are summed with one NCCL all-reduce (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget (bounded sample)")
     return ap.parse_args()
@@ -52,6 +55,8 @@ def workload_name(args, n):
          "hadamard": "single-qubit Hadamard UnitarySmoothPulseProblem, N=2, 2 drives",
          "sampling": f"UnitarySamplingProblem 4-level transmon, {args.systems or 256} systems",
          "ket": "QuantumStateSmoothPulseProblem, N=2, 2 drives"}[args.workload]
+    if getattr(args, "shard", "knot") == "ensemble":
+        return f"{d}, {args.integrator} integrator, free dt, T={args.T} knots, systems split over {n} GPU(s) (ensemble-sharded)"
     return f"{d}, {args.integrator} integrator, free dt, T={args.T} knots/GPU x {n} GPU(s), knot-sharded"
 
 
@@ -193,13 +198,26 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
-    systems, traj, integrators = build_problem(args, n_gpus)
-    nbp = args.T - 1
-    t0k, t1k = rank * nbp, (rank + 1) * nbp
-    D = qcknot.QuantumDynamics(integrators, traj, device=local_rank, knot_range=(t0k, t1k))
-    nb = D.n_blocks
-    Zh = np.ascontiguousarray(traj.datavec[t0k * D.zdim:(t1k + 1) * D.zdim])
-    muh = wl.random_multipliers(nb * D.dyn, seed=1234 + rank)
+    ensemble = args.shard == "ensemble"
+    if ensemble and args.workload != "sampling":
+        raise SystemExit("--shard ensemble needs --workload sampling")
+    if ensemble:
+        # strong scaling: the same T knots on every GPU, each GPU owns a slice of the sampled systems
+        from qcknot.sharding import integrator_shard
+        systems, traj, integrators = build_problem(args, 1)
+        q0, q1 = integrator_shard(len(systems), len(integrators), rank, n_gpus)
+        D = qcknot.QuantumDynamics(integrators, traj, device=local_rank, integrator_range=(q0, q1))
+        nb = D.n_blocks
+        Zh = np.ascontiguousarray(traj.datavec[: (nb + 1) * D.zdim])
+        muh = wl.random_multipliers(nb * D.dyn, seed=1234)
+    else:
+        systems, traj, integrators = build_problem(args, n_gpus)
+        nbp = args.T - 1
+        t0k, t1k = rank * nbp, (rank + 1) * nbp
+        D = qcknot.QuantumDynamics(integrators, traj, device=local_rank, knot_range=(t0k, t1k))
+        nb = D.n_blocks
+        Zh = np.ascontiguousarray(traj.datavec[t0k * D.zdim:(t1k + 1) * D.zdim])
+        muh = wl.random_multipliers(nb * D.dyn, seed=1234 + rank)
 
     # ---- device-resident arm ------------------------------------------------------------------------------------------
     stream = torch.cuda.Stream(device=dev)
@@ -211,8 +229,17 @@ def main():
     H = torch.empty(nb * max(D.nnzH, 1), dtype=torch.float64, device=dev)
     st = stream.cuda_stream
 
+    shared_idx = None
+    if ensemble and world > 1:
+        pos = torch.from_numpy(D.shared_hessian_positions()).to(dev)
+        shared_idx = (torch.arange(nb, device=dev)[:, None] * D.nnzH + pos[None, :]).reshape(-1)
+
     def step():
         D.eval_device(7, Z.data_ptr(), mu.data_ptr(), F.data_ptr(), J.data_ptr(), H.data_ptr(), st)
+        if shared_idx is not None:  # the one data-path collective: partial sums of the entries on the shared controls
+            buf = H[shared_idx]
+            dist.all_reduce(buf)
+            H[shared_idx] = buf
 
     def barrier():
         torch.cuda.synchronize()
@@ -254,14 +281,14 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
-    total_evals_per_step = nb * n_gpus
+    total_evals_per_step = nb if ensemble else nb * n_gpus
     value = total_evals_per_step * args.steps / (ms * 1e-3)
     e2e_value = total_evals_per_step * e2e_steps / (e2e_ms * 1e-3)
 
     if rank == 0:
         bpe = algorithmic_bytes(D.zdim, D.dyn, D.nnzJ, D.nnzH)
         kernel_s = ms * 1e-3 / args.steps
-        achieved = bpe * nb / kernel_s * 1e-9
+        achieved = bpe * nb / kernel_s * 1e-9 / (n_gpus if ensemble else 1)  # per GPU
         peak, peak_src = 6650.0, "fallback"
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -280,7 +307,7 @@ def main():
         out = {
             "metric": "knot-pt constraint+Jac+Hess evals/s", "value": value, "unit": "evals/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if ensemble else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, n_gpus), "seed": 1234, "evals_per_step": total_evals_per_step,
                        "l2": "outputs per step exceed L2 (inputs+outputs larger than L2, no flush needed)"
                        if bpe * nb > 2 * 126e6 else "working set fits L2; flush not applied"},
