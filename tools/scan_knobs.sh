@@ -1,10 +1,11 @@
 #!/bin/bash
-# development scan of the launch knobs (QCK_DMMA, QCK_TMA_MIN) over the benchmark workloads
-for d in 0 1; do for m in 0 2048 4096 16384 1000000000; do
-  echo "cz dmma=$d tma_min=$m: $(QCK_DMMA=$d QCK_TMA_MIN=$m python tools/quick_bench.py cz 10000 pade 2>&1 | grep 'F+J+H')"
-done; done
-for m in 0 512 2048 1000000000; do
-  echo "sampling tma_min=$m: $(QCK_TMA_MIN=$m python tools/quick_bench.py sampling 200 pade 256 2>&1 | grep 'F+J+H')"
-  echo "hadamard tma_min=$m: $(QCK_TMA_MIN=$m python tools/quick_bench.py hadamard 100000 pade 2>&1 | grep 'F+J+H')"
-  echo "cz-exp tma_min=$m: $(QCK_TMA_MIN=$m python tools/quick_bench.py cz 10000 exponential 2>&1 | grep 'F+J+H')"
+# development scan of the launch knobs over the benchmark workloads (each knob is read once per process)
+for env in "" "QCK_ROWSLICE=0" "QCK_ROWSLICE=0 QCK_DMMA=1" "QCK_ROWSLICE_DENSE=1" "QCK_ROWSLICE_WARPS=6" "QCK_ROWSLICE_WARPS=7"; do
+  echo "cz [$env]: $(env $env python tools/quick_bench.py cz 10000 pade 2>&1 | grep 'F+J+H')"
 done
+for env in "" "QCK_COLUMN=0"; do
+  echo "sampling [$env]: $(env $env python tools/quick_bench.py sampling 200 pade 256 2>&1 | grep 'F+J+H')"
+  echo "hadamard [$env]: $(env $env python tools/quick_bench.py hadamard 100000 pade 2>&1 | grep 'F+J+H')"
+  echo "ket [$env]: $(env $env python tools/quick_bench.py ket 100000 pade 2>&1 | grep 'F+J+H')"
+done
+echo "cz-exp: $(python tools/quick_bench.py cz 10000 exponential 2>&1 | grep 'F+J+H')"
