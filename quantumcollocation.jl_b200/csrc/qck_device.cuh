@@ -236,5 +236,71 @@ __device__ __forceinline__ void write_units(const double* __restrict__ image, co
     }
 }
 
+// Lane-parallel variant for a warp that writes a whole knot on its own (row-slice kernel): lane u decodes unit u; units whose
+// copies are 16-byte aligned leave through the copy engine right from that lane (every issuing lane commits / waits for its
+// own bulk group), the others are broadcast one by one and copied by the whole warp.
+__device__ __forceinline__ void write_units_lanes(const double* __restrict__ image, const QckSeg* __restrict__ segs, int s0, int s1,
+                                                  const QckLaunch& p, long long t, int lane, unsigned mask) {
+    double* const baseF = p.F + t * p.c.dyn;
+    double* const baseJ = p.J + t * p.nnzJ;
+    double* const baseH = p.H + t * p.nnzH;
+    double* const baseP = p.partial + t * p.npart - p.nnzH;
+    for (int sb = s0; sb < s1; sb += 32) {
+        const int s = sb + lane;
+        bool todo = false;
+        double* dst = nullptr;
+        int img = 0, n = 0, nrep = 0;
+        if (s < s1) {
+            const QckSeg sg = segs[s];
+            const int arr = sg.arr & 255;
+            if ((mask >> arr) & 1u) {
+                dst = (arr == 0 ? baseF : (arr == 1 ? baseJ : ((long long)sg.dst < p.nnzH ? baseH : baseP))) + sg.dst;
+                img = sg.img_nrep & 0xffff; nrep = sg.img_nrep >> 16; n = sg.n;
+                if (!(reinterpret_cast<uintptr_t>(dst) & 15) && !(n & 1)) {
+                    for (int r = 0; r < nrep; ++r) bulk_store(dst + (size_t)r * n, image + img, (unsigned)n * 8u);
+                } else {
+                    todo = true;
+                }
+            }
+        }
+        unsigned rem = __ballot_sync(0xffffffffu, todo);
+        while (rem) {
+            const int l = __ffs(rem) - 1;
+            rem &= rem - 1;
+            double* const d = reinterpret_cast<double*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
+            const double* const src = image + __shfl_sync(0xffffffffu, img, l);
+            const int nn = __shfl_sync(0xffffffffu, n, l), nr = __shfl_sync(0xffffffffu, nrep, l);
+            if (nr == 1) {  // plain run: scalar head (misaligned destination) / tail, 16-byte body
+                const int head = (reinterpret_cast<uintptr_t>(d) & 15) ? 1 : 0;
+                const int pairs = (nn - head) >> 1;
+                if (lane == 31) {
+                    if (head) d[0] = src[0];
+                    if (head + 2 * pairs < nn) d[nn - 1] = src[nn - 1];
+                }
+                double2* d2 = reinterpret_cast<double2*>(d + head) + lane;
+                int k = lane;
+                if (!head) {
+                    const double2* s2 = reinterpret_cast<const double2*>(src) + lane;
+                    for (; k < pairs; k += 32, s2 += 32, d2 += 32) *d2 = *s2;
+                } else {
+                    const double* sh = src + 1 + 2 * lane;
+                    for (; k + 32 < pairs; k += 64, sh += 128, d2 += 64) {
+                        const double a0 = sh[0], a1 = sh[1], b0 = sh[64], b1 = sh[65];
+                        d2[0] = make_double2(a0, a1); d2[32] = make_double2(b0, b1);
+                    }
+                    for (; k < pairs; k += 32, sh += 64, d2 += 32) *d2 = make_double2(sh[0], sh[1]);
+                }
+            } else {  // rare: odd period or misaligned repeated block
+                const int total = nn * nr, step = 32 % nn;
+                int k = lane % nn;
+                for (int idx = lane; idx < total; idx += 32) {
+                    d[idx] = src[k];
+                    k += step;
+                    if (k >= nn) k -= nn;
+                }
+            }
+        }
+    }
+}
 
 }  // namespace

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 for (int i = 0; i < 3; ++i) s_hh += rdot(vM[xo + k3 + i], x3[i]);
             }
             if (QCK_BULK_STORE) {
-                if (lane == 0) bulk_wait_read();  // the copy engine has finished reading the previous knot's staging buffer
+                bulk_wait_read();  // the copy engine has finished reading the previous knot's staging buffer
                 __syncwarp();
             }
             // ---- phase 1: residual and Jacobian values ---------------------------------------------------------------------------
@@ -294,15 +294,18 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
         if (p.n_aux) do_aux(p, t, lane, 32);  // derivative-integrator entries of this knot
         if (QCK_BULK_STORE) fence_async_smem();
         __syncwarp();
-        write_units<2 * NN>(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
-        if (QCK_BULK_STORE && lane == 0) bulk_commit();
+        // (when the Hessian phase follows at once, its first image write would wait for these copies anyway: one lane issues
+        //  them in order; as the knot's last flush they are issued from all lanes and drain behind the next knot's first products)
+        if (needH) write_units<2 * NN>(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
+        else write_units_lanes(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
+        if (QCK_BULK_STORE) bulk_commit();
         __syncwarp();
         // ---- phase 2: Hessian-of-Lagrangian values, staged in the same buffer ------------------------------------------------------
         if (needH) {
             double2 w2[3];
             mvAH(w2, vW1 + xo);
             if (QCK_BULK_STORE) {
-                if (lane == 0) bulk_wait_read();  // phase-1 copies have left the buffer
+                bulk_wait_read();  // phase-1 copies have left the buffer
                 __syncwarp();
             }
 #pragma unroll
@@ -403,12 +406,12 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
             }
             if (QCK_BULK_STORE) fence_async_smem();
             __syncwarp();
-            write_units<2 * NN>(imgH, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & QCK_EVAL_H);
-            if (QCK_BULK_STORE && lane == 0) bulk_commit();
+            write_units_lanes(imgH, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & QCK_EVAL_H);
+            if (QCK_BULK_STORE) bulk_commit();
             __syncwarp();
         }
     }
-    if (QCK_BULK_STORE && lane == 0) bulk_wait_all();
+    if (QCK_BULK_STORE) bulk_wait_all();
 }
 
 
