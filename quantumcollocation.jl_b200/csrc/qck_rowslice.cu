@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 }
             }
         }
-        if (needT) {
+        if (needJ) {  // (a Hessian-only call gets its A_j d inside the Hessian loop and skips this one)
 #pragma unroll
             for (int j = 0; j < ND; ++j) {
                 double2 y[3], u[3], y3[3];
@@ -343,6 +343,31 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                             cfma(z1[i], aji, mv);
                             cfma(z2[i], aji, wv);
                         }
+                    }
+                }
+                if (!needJ) {  // Hessian-only call: the a_j x dt entry's Re <w1, A_j d> term (otherwise taken in phase 1)
+                    double2 u[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) u[i] = make_double2(0.0, 0.0);
+                    if constexpr (WC > 0) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int o0 = ((j * 2) * N + k3 + i) * WC;
+#pragma unroll
+                            for (int w = 0; w < WC; ++w) cfma(u[i], ellv[o0 + w], vD[xo + ellc[o0 + w]]);
+                        }
+                    } else {
+                        const double2* Aj2 = cAj + j * NN;
+#pragma unroll
+                        for (int jj = 0; jj < N; ++jj) {
+                            const double2 dv = vD[xo + jj];
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) cfma(u[i], Aj2[(k3 + i) * N + jj], dv);
+                        }
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) s_ah[j] += c2h * rdot(w1[i], u[i]);
                     }
                 }
                 __syncwarp();  // the previous drive's readers of vZ1 are done
