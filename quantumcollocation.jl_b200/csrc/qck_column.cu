@@ -223,12 +223,12 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
                         const double2 w = __ldg(Ajg + (j * N + r) * N + k);
-                        cfma(y[r], w, vv[k]);
+                        if (needJ) cfma(y[r], w, vv[k]);
                         cfma(u[j][r], w, d[k]);
                     }
                 }
-                mvA(y3, u[j]);
-                if (needJ) {
+                if (needJ) {  // (a Hessian-only call needs A_j d only)
+                    mvA(y3, u[j]);
 #pragma unroll
                     for (int r = 0; r < N; ++r) y[r] = make_double2(y[r].x + c2h2 * y3[r].x, y[r].y + c2h2 * y3[r].y);
                     put_J(QO_TA + j, y);
