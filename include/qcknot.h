@@ -23,9 +23,19 @@
  *  - data layout is the reference's: Z = vec(data), data is zdim x T column-major, z_t = Z[t*zdim : (t+1)*zdim]
  *    (test/test_utils.jl:52-118); unitary iso-vec = vec(vcat(real(U), imag(U))) (trajectory_initialization.jl:137);
  *    ket iso = [Re psi; Im psi] (trajectory_initialization.jl:469-470); all values are Float64, indices Int64.
- *  - a handle describes `T` consecutive knot points = T-1 constraint blocks.  Knot-range sharding over GPUs is
- *    pointer arithmetic on the caller's side: shard g creates a handle with T = t1-t0+1 (one-knot halo) and
- *    passes Z + t0*zdim, F + t0*dyn, J + t0*nnzJ, H + t0*nnzH (values are knot-major, so shards are contiguous).
+ *  - a handle describes `T` consecutive knot points = T-1 constraint blocks.
+ *  - multi-GPU: n_gpus > 1 makes ONE handle drive n_gpus devices from the one serial
+ *    caller (Ipopt).  shard_mode KNOT splits the knot blocks into contiguous ranges (one-knot halo; values are
+ *    knot-major, so every GPU owns a contiguous segment of F, J and H), shard_mode ENSEMBLE splits the quantum
+ *    integrators (the sampled systems of unitary_sampling_problem.jl:134-155).  The host-buffer entry points take and
+ *    fill the caller's single arrays exactly as with one GPU: every GPU copies its own part over its own PCIe link.
+ *    NCCL (dlopen'ed libnccl.so.2, single-process communicator) is used only by qck_gather_device (all-gather of the
+ *    device-resident segments) and for the all-reduce of the Hessian entries that several systems share.
+ *  - host-buffer calls stage through library-owned page-locked memory, in knot chunks that overlap H2D, kernels, D2H
+ *    and the host-side expansion; the caller's arrays can be ordinary pageable memory.  kron(I_N, B) blocks cross
+ *    PCIe once and are written N times into the caller's array by the library's host threads.
+ *  - the same Z presented to qck_eval_residual / _jacobian / _hessian in succession (what Ipopt does within one
+ *    iteration) is uploaded once: the handle compares Z with its staged copy and reuses device-resident results.
  */
 #ifndef QCKNOT_H
 #define QCKNOT_H
@@ -49,12 +59,18 @@ extern "C" {
 #define QCK_EVAL_J 2u
 #define QCK_EVAL_H 4u
 
+/* multi-GPU partitioning */
+#define QCK_SHARD_KNOT 0
+#define QCK_SHARD_ENSEMBLE 1
+
 /* error codes */
 #define QCK_OK 0
 #define QCK_EINVAL 1    /* bad argument / unsupported configuration */
 #define QCK_ENODEVICE 2 /* no usable sm_100 CUDA device */
 #define QCK_ECUDA 3     /* a CUDA runtime call or kernel failed */
 #define QCK_ENOMEM 4
+#define QCK_ERANGE 5    /* an input is outside the range the kernels support (reported by the device after the pass) */
+#define QCK_ENCCL 6     /* libnccl could not be loaded or a collective failed */
 
 /* One entry of the reference's `integrators` vector.
  * Quantum kinds: state component = [state_off, state_off+state_len), drive component = [ctrl_off, ctrl_off+n_drives);
@@ -81,11 +97,14 @@ typedef struct qck_problem_desc {
     double dt_fixed;  /* used when dt_off < 0 */
     int32_t n_integrators;
     int32_t eval_hessian; /* 0: no Hessian structure/values (PiccoloOptions.eval_hessian=false) */
-    int32_t device;       /* CUDA device ordinal; -1 = structure-only handle (sizes + structures, every eval fails) */
-    int32_t integ_begin;  /* ensemble sharding: this handle evaluates integrators [integ_begin, integ_end);  */
-    int32_t integ_end;    /* 0,0 = all.  Structures always describe the whole problem.                        */
-    int32_t reserved;
+    int32_t device;       /* (first) CUDA device ordinal; -1 = structure-only handle (sizes + structures, every eval fails) */
+    int32_t integ_begin;  /* manual ensemble sharding: this handle evaluates integrators [integ_begin, integ_end);      */
+    int32_t integ_end;    /* integ_end < 0 = all integrators; begin == end = none.  Structures describe the whole problem. */
+    int32_t n_gpus;       /* 0 or 1: one GPU.  N > 1: this handle drives devices device .. device+N-1 (or `devices`)  */
     const qck_integrator_desc* integrators;
+    int32_t shard_mode;   /* QCK_SHARD_KNOT | QCK_SHARD_ENSEMBLE (n_gpus > 1) */
+    int32_t host_threads; /* host threads for staging / expansion of the value arrays; 0 = all hardware threads (max 32) */
+    const int32_t* devices; /* optional: explicit device ordinals, n_gpus entries (NULL = consecutive from `device`) */
 } qck_problem_desc;
 
 typedef struct qck_handle qck_handle;
@@ -106,8 +125,9 @@ int qck_jacobian_structure(const qck_handle* h, int64_t knot_offset, int64_t* ro
 int qck_hessian_structure(const qck_handle* h, int64_t knot_offset, int64_t* rows, int64_t* cols);
 
 /* Host-buffer entry points: what the MOI callbacks bind (eval_constraint, eval_constraint_jacobian,
- * eval_hessian_lagrangian).  Z has T*zdim doubles, mu and F have (T-1)*dyn, J (T-1)*nnzJ, H (T-1)*nnzH.
- * H2D copy of the inputs, one kernel pass, D2H copy of the value array; synchronous on return. */
+ * eval_hessian_lagrangian).  Z has T*zdim doubles, mu and F have (T-1)*dyn, J (T-1)*nnzJ, H (T-1)*nnzH; plain (pageable)
+ * host memory is fine.  Chunked H2D / kernels / compact D2H / host-side expansion, overlapped; synchronous on return.
+ * An unchanged Z (compared with the staged copy) is not uploaded again and its device-resident results are reused. */
 int qck_eval_residual(qck_handle* h, const double* Z, double* F);
 int qck_eval_jacobian(qck_handle* h, const double* Z, double* J);
 int qck_eval_hessian(qck_handle* h, const double* Z, const double* mu, double* H);
@@ -127,9 +147,42 @@ int qck_synchronize(qck_handle* h);
  * there and the caller all-reduces exactly these positions.  pos may be NULL to query the count. */
 int qck_shared_hessian_positions(const qck_handle* h, int64_t* count, int64_t* pos);
 
-/* page-lock / unlock a caller array (e.g. Ipopt's value buffers) so the D2H copy runs at full PCIe speed */
+/* page-lock / unlock a caller array (kept for callers that run their own copies from qck_device_buffers; the host-buffer
+ * entry points stage through library-owned page-locked memory and do not need it) */
 int qck_host_register(void* p, size_t bytes);
 int qck_host_unregister(void* p);
+
+/* ---- multi-GPU handles (n_gpus > 1); every function also accepts a single-GPU handle (one shard) ------------------------- */
+/* number of shards (GPUs) behind the handle, and what shard g covers: its device, its block range [block_begin, block_end)
+ * (KNOT: a contiguous part of 0 .. T-1; ENSEMBLE: everything) and its integrator range (ENSEMBLE: a part; KNOT: everything) */
+int qck_shard_count(const qck_handle* h, int32_t* n);
+int qck_shard_info(const qck_handle* h, int32_t g, int32_t* device, int64_t* block_begin, int64_t* block_end,
+                   int32_t* integ_begin, int32_t* integ_end);
+/* shard g's own device buffers (its knots of Z / mu, its segments of F / J / H) */
+int qck_shard_device_buffers(qck_handle* h, int32_t g, double** dZ, double** dmu, double** dF, double** dJ, double** dH);
+/* device-resident evaluation on every GPU: qck_upload copies the caller's Z (and mu, may be NULL) into the shards' buffers
+ * (synchronous), qck_eval_resident enqueues one pass per GPU on the shards' streams (asynchronous; qck_synchronize waits).
+ * ENSEMBLE: the Hessian entries on the shared controls are summed over the GPUs with ncclAllReduce. */
+int qck_upload(qck_handle* h, const double* Z, const double* mu);
+int qck_eval_resident(qck_handle* h, uint32_t mask);
+/* KNOT: assemble the device-resident value arrays on EVERY GPU (NCCL over NVLink, all-gather of the segments; asynchronous
+ * on the shards' streams); qck_gathered_buffers returns GPU g's assembled arrays (allocated by the first gather). */
+int qck_gather_device(qck_handle* h, uint32_t mask);
+int qck_gathered_buffers(qck_handle* h, int32_t g, double** dF, double** dJ, double** dH);
+/* NCCL version the library loaded (dlopen) and the size of its communicator; initialises NCCL for a multi-GPU handle */
+int qck_nccl_version(qck_handle* h, int32_t* version, int32_t* nranks);
+
+/* bytes the last host-buffer call moved over PCIe (all GPUs) and the number of calls served from device-resident results
+ * of an unchanged Z since creation */
+int qck_transfer_stats(const qck_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* cache_hits);
+/* Introspection of the host-buffer path.  qck_compact_map: the runs of value array `arr` (0 F, 1 J, 2 H) that this handle
+ * writes, per knot block, as (offset in the block, offset in the compact layout, length, repeats) quadruples -- repeats > 1 is
+ * a kron(I_N, B) block that crosses PCIe once.  segs may be NULL to query the count.  qck_expand_host runs the host half of the
+ * path alone (compact layout -> structure-order array; no device involved, works on structure-only handles). */
+int qck_compact_map(const qck_handle* h, int32_t arr, int64_t* count, int32_t* segs);
+int qck_expand_host(const qck_handle* h, int32_t arr, const double* compact, double* out, int64_t nk);
+/* forget the staged inputs / device-resident results (e.g. after writing into the handle's device buffers directly) */
+int qck_invalidate(qck_handle* h);
 
 /* kernels launched on this handle since creation (bench.py's gpu_launches) */
 int qck_launch_count(const qck_handle* h, int64_t* launches);

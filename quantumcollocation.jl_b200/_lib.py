@@ -9,12 +9,16 @@ LIB_PATH = os.environ.get("QCK_LIB") or os.path.join(HERE, "libqcknot.so")  # QC
 
 QCK_UNITARY_PADE, QCK_UNITARY_EXP, QCK_KET_PADE, QCK_KET_EXP, QCK_DERIVATIVE = range(5)
 QCK_EVAL_F, QCK_EVAL_J, QCK_EVAL_H = 1, 2, 4
+QCK_SHARD_KNOT, QCK_SHARD_ENSEMBLE = 0, 1
 
 EXPORTS = [
     "qck_create", "qck_destroy", "qck_last_error", "qck_sizes", "qck_jacobian_structure", "qck_hessian_structure",
     "qck_eval_residual", "qck_eval_jacobian", "qck_eval_hessian", "qck_eval_all", "qck_eval_device",
     "qck_device_buffers", "qck_synchronize", "qck_shared_hessian_positions", "qck_host_register",
     "qck_host_unregister", "qck_launch_count", "qck_version",
+    "qck_shard_count", "qck_shard_info", "qck_shard_device_buffers", "qck_upload", "qck_eval_resident",
+    "qck_gather_device", "qck_gathered_buffers", "qck_nccl_version", "qck_transfer_stats", "qck_invalidate",
+    "qck_compact_map", "qck_expand_host",
 ]
 
 
@@ -30,8 +34,9 @@ class ProblemDesc(C.Structure):
     _fields_ = [
         ("T", C.c_int64), ("zdim", C.c_int32), ("dt_off", C.c_int32), ("dt_fixed", C.c_double),
         ("n_integrators", C.c_int32), ("eval_hessian", C.c_int32), ("device", C.c_int32),
-        ("integ_begin", C.c_int32), ("integ_end", C.c_int32), ("reserved", C.c_int32),
+        ("integ_begin", C.c_int32), ("integ_end", C.c_int32), ("n_gpus", C.c_int32),
         ("integrators", C.POINTER(IntegratorDesc)),
+        ("shard_mode", C.c_int32), ("host_threads", C.c_int32), ("devices", C.POINTER(C.c_int32)),
     ]
 
 
@@ -70,5 +75,18 @@ def load() -> C.CDLL:
     lib.qck_host_unregister.argtypes = [vp]
     lib.qck_launch_count.argtypes = [vp, i64p]
     lib.qck_version.restype = C.c_char_p
+    i32p = C.POINTER(C.c_int32)
+    lib.qck_shard_count.argtypes = [vp, i32p]
+    lib.qck_shard_info.argtypes = [vp, C.c_int32, i32p, i64p, i64p, i32p, i32p]
+    lib.qck_shard_device_buffers.argtypes = [vp, C.c_int32] + [C.POINTER(vp)] * 5
+    lib.qck_upload.argtypes = [vp, vp, vp]
+    lib.qck_eval_resident.argtypes = [vp, C.c_uint32]
+    lib.qck_gather_device.argtypes = [vp, C.c_uint32]
+    lib.qck_gathered_buffers.argtypes = [vp, C.c_int32] + [C.POINTER(vp)] * 3
+    lib.qck_nccl_version.argtypes = [vp, i32p, i32p]
+    lib.qck_transfer_stats.argtypes = [vp, i64p, i64p, i64p]
+    lib.qck_invalidate.argtypes = [vp]
+    lib.qck_compact_map.argtypes = [vp, C.c_int32, i64p, vp]
+    lib.qck_expand_host.argtypes = [vp, C.c_int32, vp, vp, C.c_int64]
     _lib = lib
     return lib

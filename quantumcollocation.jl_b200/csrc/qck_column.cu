@@ -315,8 +315,13 @@ int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int
 #undef QCK_COL
 #undef QCK_COL2
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
-    if (e != cudaSuccess) return (int)e;
+    if (L.plan && L.plan->kern == (const void*)kern) {
+        per_sm = L.plan->per_sm;
+    } else {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+        if (e != cudaSuccess) return (int)e;
+        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = 0; L.plan->per_sm = per_sm; }
+    }
     if (per_sm < 1) return 0;
     const long long n_items = L.n_knots * (long long)(L.member_end - L.member_begin);
     const int ipw = 32 / (ket ? 1 : c.N);

@@ -15,35 +15,20 @@
 #include <string>
 #include <vector>
 
-#include "qck_internal.h"
+#include "qck_handle.h"
 
 namespace {
 
 thread_local std::string g_create_error;
 
-struct Integ {
-    int kind = 0, order = 0, N = 0, nd = 0, state_off = 0, state_len = 0, ctrl_off = 0;
-    int row_off = 0, dim = 0, nc = 0;
-    std::vector<std::complex<double>> Hdrift, Hdrives;
-    bool quantum() const { return kind != QCK_DERIVATIVE; }
-    bool unitary() const { return kind == QCK_UNITARY_PADE || kind == QCK_UNITARY_EXP; }
-    bool pade() const { return kind == QCK_UNITARY_PADE || kind == QCK_KET_PADE; }
-};
+typedef QckInteg Integ;
+typedef QckClassHost ClassHost;
 
-struct ClassHost {
-    QckClassDev dev{};
-    std::vector<int> members;  // integrator indices, ascending
-    int member_begin = 0, member_end = 0;
-    // device allocations owned by the class
-    std::vector<void*> allocs;
-};
-
-bool g_structure_only = false;  // set while building a device-less (structure-only) handle
-
+// structure-only handles (device < 0) never touch the device: their tables stay on the host
 template <class T>
-cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& allocs) {
+cudaError_t upload(const qck_handle* h, const std::vector<T>& v, const T** out, std::vector<void*>& allocs) {
     *out = nullptr;
-    if (v.empty() || g_structure_only) return cudaSuccess;
+    if (v.empty() || h->device < 0) return cudaSuccess;
     void* d = nullptr;
     cudaError_t e = cudaMalloc(&d, v.size() * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -55,32 +40,7 @@ cudaError_t upload(const std::vector<T>& v, const T** out, std::vector<void*>& a
 
 }  // namespace
 
-struct qck_handle {
-    std::string err;
-    int device = 0, sm_count = 148;
-    cudaStream_t stream = nullptr;
-    long long T = 0;
-    int zdim = 0, dt_off = -1, eval_hessian = 1, ib = 0, ie = 0;
-    double dt_fixed = 0.0;
-    std::vector<Integ> integ;
-    int dyn = 0;
-    long long nnzJ = 0, nnzH = 0;
-    std::vector<int32_t> Jr, Jc, Hr, Hc;  // per-knot structure, 0-based, CSC order
-    std::vector<ClassHost> classes;
-    std::vector<QckAux> aux;
-    const QckAux* d_aux = nullptr;
-    std::vector<int> sh_pos, sh_ptr, sh_cols;      // active contributors only (reduce kernel)
-    std::vector<long long> shared_positions;       // globally shared positions
-    QckReduce red{};
-    int npart = 0;
-    std::vector<void*> allocs;
-    double *dZ = nullptr, *dmu = nullptr, *dF = nullptr, *dJ = nullptr, *dH = nullptr, *dpartial = nullptr;
-    long long launches = 0;
-};
-
-namespace {
-
-int fail(qck_handle* h, int code, const char* fmt, ...) {
+int qck_fail(qck_handle* h, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -91,11 +51,10 @@ int fail(qck_handle* h, int code, const char* fmt, ...) {
     return code;
 }
 
-#define CUDA_TRY(h, call)                                                                          \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(h, QCK_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
+namespace {
+
+#define fail qck_fail
+#define CUDA_TRY QCK_CUDA_TRY
 
 // One structural nonzero of the per-knot Jacobian / Hessian block.
 struct Ent {
@@ -409,6 +368,12 @@ int build(qck_handle* h) {
                     !place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why, d0) ||
                     !place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why, d0))
                     return fail(h, QCK_EINVAL, "unsupported trajectory layout: %s", why.c_str());
+                for (int arr = 0; arr < 3; ++arr)
+                    for (auto& r : runs[arr]) {
+                        if (arr == 2 && r.dst >= h->nnzH) continue;  // partial column: the reduce kernel writes the shared position
+                        if (r.period < r.len) h->own[arr].push_back({r.dst, 0, r.period, r.len / r.period});
+                        else h->own[arr].push_back({r.dst, 0, r.len, 1});
+                    }
                 per_member[m2] = balance_units(runs, nwarps, hdrs[m2].data());
                 if (first) {
                     memcpy(c.pl_base, base, sizeof base); memcpy(c.pl_stride, stride, sizeof stride);
@@ -557,32 +522,34 @@ int build(qck_handle* h) {
                         }
             }
             cudaError_t e2;
-            if ((e2 = upload(daj, &c.dense_aj, C.allocs)) != cudaSuccess || (e2 = upload(qdst, &c.qdst, C.allocs)) != cudaSuccess)
+            if ((e2 = upload(h, daj, &c.dense_aj, C.allocs)) != cudaSuccess || (e2 = upload(h, qdst, &c.qdst, C.allocs)) != cudaSuccess)
                 return fail(h, QCK_ECUDA, "uploading column-kernel tables: %s", cudaGetErrorString(e2));
         }
         cudaError_t e;
-        if ((e = upload(segs, &c.segs, C.allocs)) != cudaSuccess ||
-            (e = upload(cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(icon, &c.ell_col, C.allocs)) != cudaSuccess ||
-            (e = upload(moff, &c.moff, C.allocs)) != cudaSuccess)
+        if ((e = upload(h, segs, &c.segs, C.allocs)) != cudaSuccess ||
+            (e = upload(h, cmat, &c.cmat, C.allocs)) != cudaSuccess || (e = upload(h, icon, &c.ell_col, C.allocs)) != cudaSuccess ||
+            (e = upload(h, moff, &c.moff, C.allocs)) != cudaSuccess)
             return fail(h, QCK_ECUDA, "uploading class constants: %s", cudaGetErrorString(e));
         c.tape = nullptr; c.tape_stride = 0; c.tape_levels = 0; c.max_ctas = 0;
-        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order != 4 && h->eval_hessian && !g_structure_only) {
+        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order != 4 && h->eval_hessian && h->device >= 0) {
             // reverse-sweep tape of the general-order Pade Hessian: (m-1) Horner levels x (P + nd + 1 tangents) per group
             c.tape_stride = (long long)(c.pade_m - 1) * (2 + nd) * N * N;
             c.max_ctas = h->sm_count * 4;
             void* tp = nullptr;
-            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas)) != cudaSuccess)
+            // (QCK_TAPE_SLOTS copies: launches on the handle's own stream and on the two pipeline streams may overlap)
+            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas * QCK_TAPE_SLOTS)) != cudaSuccess)
                 return fail(h, QCK_ENOMEM, "tape allocation failed: %s", cudaGetErrorString(e));
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
         }
-        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && !g_structure_only) {
+        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0) {
             // reverse-sweep tape of the exponential Hessian: 7 Horner steps x nd jets + 16 squaring levels x (1 + nd) matrices per CTA
             c.tape_levels = 16;
             c.tape_stride = (long long)(7 * nd + c.tape_levels * (1 + nd)) * N * N;
             c.max_ctas = h->sm_count * 4;
             void* tp = nullptr;
-            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas)) != cudaSuccess)
+            // (QCK_TAPE_SLOTS copies: launches on the handle's own stream and on the two pipeline streams may overlap)
+            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas * QCK_TAPE_SLOTS)) != cudaSuccess)
                 return fail(h, QCK_ENOMEM, "tape allocation failed: %s", cudaGetErrorString(e));
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
@@ -602,38 +569,73 @@ int build(qck_handle* h) {
     for (size_t k = 0; k < HE.size(); ++k)
         if (HE[k].cls < 0 && hdst[k] >= 0 && HE[k].contrib >= h->ib && HE[k].contrib < h->ie)
             h->aux.push_back({2, HE[k].aux_op, (int32_t)hdst[k], HE[k].aux_i0, 0, 0, 0.0});
+    // ---- positions this handle writes (host-buffer path: what crosses PCIe, and how it expands into the caller's arrays) ------
+    for (auto& a : h->aux)
+        if (a.out != 2 || a.pos < h->nnzH) h->own[a.out].push_back({a.pos, 0, 1, 1});
+    if (!h->exclude_shared)
+        for (size_t i = 0; i < h->sh_pos.size(); ++i)
+            if (h->sh_ptr[i + 1] > h->sh_ptr[i]) h->own[2].push_back({h->sh_pos[i], 0, 1, 1});
+    for (int arr = 0; arr < 3; ++arr) {
+        auto& v = h->own[arr];
+        std::sort(v.begin(), v.end(), [](const QckOwnSeg& a, const QckOwnSeg& b) { return a.full < b.full; });
+        std::vector<QckOwnSeg> merged;
+        for (auto& sgm : v) {
+            if (!merged.empty()) {
+                QckOwnSeg& b = merged.back();
+                const int bend = b.full + b.len * b.nrep;
+                if (sgm.full < bend) return fail(h, QCK_EINVAL, "internal: overlapping output runs");
+                if (sgm.full == bend && b.nrep == 1 && sgm.nrep == 1) { b.len += sgm.len; continue; }
+            }
+            merged.push_back(sgm);
+        }
+        int comp = 0;
+        for (auto& sgm : merged) { sgm.comp = comp; comp += sgm.len; }
+        v.swap(merged);
+    }
     cudaError_t e;
-    if ((e = upload(h->aux, &h->d_aux, h->allocs)) != cudaSuccess) return fail(h, QCK_ECUDA, "uploading aux entries: %s", cudaGetErrorString(e));
+    if ((e = upload(h, h->aux, &h->d_aux, h->allocs)) != cudaSuccess) return fail(h, QCK_ECUDA, "uploading aux entries: %s", cudaGetErrorString(e));
     h->red.n_shared = (int)h->sh_pos.size();
-    if ((e = upload(h->sh_pos, &h->red.pos, h->allocs)) != cudaSuccess || (e = upload(h->sh_ptr, &h->red.ptr, h->allocs)) != cudaSuccess ||
-        (e = upload(h->sh_cols, &h->red.cols, h->allocs)) != cudaSuccess)
+    if ((e = upload(h, h->sh_pos, &h->red.pos, h->allocs)) != cudaSuccess || (e = upload(h, h->sh_ptr, &h->red.ptr, h->allocs)) != cudaSuccess ||
+        (e = upload(h, h->sh_cols, &h->red.cols, h->allocs)) != cudaSuccess)
         return fail(h, QCK_ECUDA, "uploading reduction tables: %s", cudaGetErrorString(e));
     return QCK_OK;
 }
 
-int run(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, double* dF, double* dJ, double* dH, cudaStream_t st) {
+}  // namespace
+
+int qck_run(qck_handle* h, uint32_t mask, long long k0, long long nk, const double* dZ, const double* dmu, double* dF, double* dJ,
+            double* dH, cudaStream_t st, int slot) {
     if (!h->eval_hessian) mask &= ~QCK_EVAL_H;
     if (!dF) mask &= ~QCK_EVAL_F;
     if (!dJ) mask &= ~QCK_EVAL_J;
     if (!dH) mask &= ~QCK_EVAL_H;
-    if (!mask) return QCK_OK;
+    if (!mask || nk <= 0) return QCK_OK;
     if ((mask & QCK_EVAL_H) && !dmu) return fail(h, QCK_EINVAL, "the Hessian needs the multipliers mu");
     QckLaunch L{};
-    L.Z = dZ; L.mu = dmu; L.F = dF; L.J = dJ; L.H = dH; L.partial = h->dpartial;
-    L.n_knots = h->T - 1; L.nnzJ = h->nnzJ; L.nnzH = h->nnzH; L.npart = h->npart; L.mask = mask;
+    L.Z = dZ + k0 * h->zdim;
+    L.mu = dmu ? dmu + k0 * h->dyn : nullptr;
+    L.F = dF ? dF + k0 * h->dyn : nullptr;
+    L.J = dJ ? dJ + k0 * h->nnzJ : nullptr;
+    L.H = dH ? dH + k0 * h->nnzH : nullptr;
+    L.partial = h->dpartial + k0 * h->npart;
+    L.n_knots = nk; L.nnzJ = h->nnzJ; L.nnzH = h->nnzH; L.npart = h->npart; L.mask = mask;
+    L.status = h->d_status;
     bool aux_done = h->aux.empty();
     const bool fuse_aux = (int)h->aux.size() <= qck_fused_aux_limit();
     int launches = 0;
     for (auto& C : h->classes) {
         if (C.member_end <= C.member_begin) continue;
         L.c = C.dev; L.member_begin = C.member_begin; L.member_end = C.member_end;
+        if (L.c.tape) L.c.tape += (size_t)slot * (size_t)L.c.tape_stride * (size_t)L.c.max_ctas;  // this stream's scratch tape
         L.moff_global = C.dev.moff ? C.dev.moff + 3 * C.member_begin : nullptr;
+        L.plan = &C.plan;
         const bool take_aux = !aux_done && fuse_aux;
         L.aux = take_aux ? h->d_aux : nullptr; L.n_aux = take_aux ? (int)h->aux.size() : 0;
         if (take_aux) aux_done = true;
         int rc = qck_launch_quantum(L, h->sm_count, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "quantum kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }
+    L.plan = nullptr;
     if (!aux_done) {
         L.c = QckClassDev{};
         L.c.free_time = h->dt_off >= 0; L.c.dt_off = h->dt_off; L.c.zdim = h->zdim; L.c.dyn = h->dyn; L.c.dt_fixed = h->dt_fixed;
@@ -641,48 +643,50 @@ int run(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, doubl
         int rc = qck_launch_aux(L, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "aux kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }
-    if ((mask & QCK_EVAL_H) && h->red.n_shared) {
-        int rc = qck_launch_reduce(h->red, dH, h->dpartial, h->T - 1, h->nnzH, h->npart, st, &launches);
+    if ((mask & QCK_EVAL_H) && h->red.n_shared && h->npart > 0) {
+        int rc = qck_launch_reduce(h->red, L.H, L.partial, nk, h->nnzH, h->npart, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "reduce kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }
     h->launches += launches;
     return QCK_OK;
 }
 
+int qck_check_status(qck_handle* h) {
+    if (!h->d_status) return QCK_OK;
+    int st = 0;
+    QCK_CUDA_TRY(h, cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));
+    if (!st) return QCK_OK;
+    cudaMemset(h->d_status, 0, sizeof st);
+    if (st & QCK_ST_EXP_RANGE)
+        return fail(h, QCK_ERANGE, "exponential integrator: ||dt*G(a)||_1 exceeds 4096 at some knot (more squaring levels than the Hessian tape holds); results of this call are not exp(dt*G)");
+    return fail(h, QCK_ERANGE, "device reported status 0x%x", st);
+}
+
+namespace {
+
 int eval_host(qck_handle* h, const double* Z, const double* mu, double* F, double* J, double* H) {
     if (!h) return QCK_EINVAL;
     if (!Z) return fail(h, QCK_EINVAL, "Z is NULL");
+    if (!h->children.empty()) return qck_multi_eval(h, Z, mu, F, J, H);
     if (h->device < 0) return fail(h, QCK_ENODEVICE, "structure-only handle (device=-1): libqcknot has no CPU evaluation path");
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    const long long nk = h->T - 1;
-    uint32_t mask = (F ? QCK_EVAL_F : 0) | (J ? QCK_EVAL_J : 0) | ((H && h->eval_hessian) ? QCK_EVAL_H : 0);
-    if ((mask & QCK_EVAL_H) && !mu) return fail(h, QCK_EINVAL, "the Hessian needs the multipliers mu");
-    CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * h->T * h->zdim, cudaMemcpyHostToDevice, h->stream));
-    if (mask & QCK_EVAL_H) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * nk * h->dyn, cudaMemcpyHostToDevice, h->stream));
-    int rc = run(h, mask, h->dZ, h->dmu, h->dF, h->dJ, h->dH, h->stream);
-    if (rc) return rc;
-    if (mask & QCK_EVAL_F) CUDA_TRY(h, cudaMemcpyAsync(F, h->dF, sizeof(double) * nk * h->dyn, cudaMemcpyDeviceToHost, h->stream));
-    if (mask & QCK_EVAL_J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * nk * h->nnzJ, cudaMemcpyDeviceToHost, h->stream));
-    if (mask & QCK_EVAL_H) CUDA_TRY(h, cudaMemcpyAsync(H, h->dH, sizeof(double) * nk * h->nnzH, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return QCK_OK;
+    if (H && h->eval_hessian && !mu) return fail(h, QCK_EINVAL, "the Hessian needs the multipliers mu");
+    return qck_pipe_eval(h, Z, mu, F, J, H);
 }
 
 }  // namespace
 
 extern "C" {
 
-const char* qck_version(void) { return "qcknot 0.1 (sm_100a)"; }
+const char* qck_version(void) { return "qcknot 0.2 (sm_100a)"; }
 
 const char* qck_last_error(const qck_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int qck_create(const qck_problem_desc* d, qck_handle** out) {
-    if (!out) return fail(nullptr, QCK_EINVAL, "out is NULL");
+}  // extern "C"
+
+// One GPU (or structure-only): parses the description, builds structures and device tables, allocates the value buffers.
+int qck_create_single(const qck_problem_desc* d, qck_handle** out, bool exclude_shared) {
     *out = nullptr;
-    if (!d || !d->integrators || d->n_integrators <= 0) return fail(nullptr, QCK_EINVAL, "empty problem description");
-    if (d->T < 2) return fail(nullptr, QCK_EINVAL, "T must be >= 2 (got %lld)", (long long)d->T);
-    if (d->zdim <= 0 || d->dt_off >= d->zdim) return fail(nullptr, QCK_EINVAL, "bad zdim/dt_off");
-    const bool structure_only = d->device == -1;  // sizes + structures only (what Ipopt asks for at set-up); every eval fails
+    const bool structure_only = d->device < 0;  // sizes + structures only (what Ipopt asks for at set-up); every eval fails
     int ndev = 0;
     cudaError_t ce = cudaSuccess;
     cudaDeviceProp prop{};
@@ -691,7 +695,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
         ce = cudaGetDeviceCount(&ndev);
         if (ce != cudaSuccess || ndev == 0)
             return fail(nullptr, QCK_ENODEVICE, "no CUDA device (%s); libqcknot has no CPU fallback", ce == cudaSuccess ? "count=0" : cudaGetErrorString(ce));
-        if (d->device < 0 || d->device >= ndev) return fail(nullptr, QCK_ENODEVICE, "device %d out of range (%d devices)", d->device, ndev);
+        if (d->device >= ndev) return fail(nullptr, QCK_ENODEVICE, "device %d out of range (%d devices)", d->device, ndev);
         if ((ce = cudaGetDeviceProperties(&prop, d->device)) != cudaSuccess) return fail(nullptr, QCK_ECUDA, "%s", cudaGetErrorString(ce));
         if (prop.major != 10) return fail(nullptr, QCK_ENODEVICE, "device %d is sm_%d%d; libqcknot is built for sm_100a only", d->device, prop.major, prop.minor);
     }
@@ -699,11 +703,13 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
     qck_handle* h = new (std::nothrow) qck_handle();
     if (!h) return fail(nullptr, QCK_ENOMEM, "out of host memory");
     auto bail = [&](int code) { g_create_error = h->err; qck_destroy(h); return code; };
-    h->device = d->device; h->sm_count = prop.multiProcessorCount;
+    h->device = structure_only ? -1 : d->device; h->sm_count = prop.multiProcessorCount;
     h->T = d->T; h->zdim = d->zdim; h->dt_off = d->dt_off < 0 ? -1 : d->dt_off; h->dt_fixed = d->dt_fixed;
     h->eval_hessian = d->eval_hessian ? 1 : 0;
+    h->exclude_shared = exclude_shared;
+    h->host_threads = d->host_threads;
     h->ib = d->integ_begin; h->ie = d->integ_end;
-    if (h->ib == 0 && h->ie == 0) h->ie = d->n_integrators;
+    if (h->ie < 0) { h->ie = d->n_integrators; }  // integ_end < 0: every integrator; begin == end: none (an empty shard launches nothing)
     if (h->ib < 0 || h->ie > d->n_integrators || h->ib > h->ie) { fail(h, QCK_EINVAL, "bad integrator range [%d,%d)", h->ib, h->ie); return bail(QCK_EINVAL); }
     int row = 0;
     for (int q = 0; q < d->n_integrators; ++q) {
@@ -738,9 +744,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
     if (!structure_only && ((ce = cudaSetDevice(h->device)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)) {
         fail(h, QCK_ECUDA, "%s", cudaGetErrorString(ce)); return bail(QCK_ECUDA);
     }
-    g_structure_only = structure_only;
     int rc = build(h);
-    g_structure_only = false;
     if (rc) return bail(rc);
     if (structure_only) { *out = h; return QCK_OK; }
     const long long nk = h->T - 1;
@@ -754,15 +758,52 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
         cudaMemset(p, 0, sizeof(double) * (size_t)b.n);
         *b.p = static_cast<double*>(p);
     }
+    {
+        void* p = nullptr;
+        if ((ce = cudaMalloc(&p, 16)) != cudaSuccess) { fail(h, QCK_ENOMEM, "%s", cudaGetErrorString(ce)); return bail(QCK_ENOMEM); }
+        h->allocs.push_back(p);
+        cudaMemset(p, 0, 16);
+        h->d_status = static_cast<int*>(p);
+    }
+    for (auto& C : h->classes) h->uses_status = h->uses_status || (C.dev.tape != nullptr && C.dev.tape_levels > 0);
     if ((ce = cudaDeviceSynchronize()) != cudaSuccess) { fail(h, QCK_ECUDA, "%s", cudaGetErrorString(ce)); return bail(QCK_ECUDA); }
     *out = h;
     return QCK_OK;
 }
 
+extern "C" {
+
+int qck_create(const qck_problem_desc* d, qck_handle** out) {
+    if (!out) return fail(nullptr, QCK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!d || !d->integrators || d->n_integrators <= 0) return fail(nullptr, QCK_EINVAL, "empty problem description");
+    if (d->T < 2) return fail(nullptr, QCK_EINVAL, "T must be >= 2 (got %lld)", (long long)d->T);
+    if (d->zdim <= 0 || d->dt_off >= d->zdim) return fail(nullptr, QCK_EINVAL, "bad zdim/dt_off");
+    if (d->n_gpus < 0 || d->n_gpus > 64) return fail(nullptr, QCK_EINVAL, "bad n_gpus %d", d->n_gpus);
+    if (d->n_gpus <= 1) {
+        qck_problem_desc d1 = *d;
+        if (d->devices && d->n_gpus == 1 && d->device >= 0) d1.device = d->devices[0];
+        return qck_create_single(&d1, out, false);
+    }
+    if (d->shard_mode != QCK_SHARD_KNOT && d->shard_mode != QCK_SHARD_ENSEMBLE) return fail(nullptr, QCK_EINVAL, "unknown shard_mode %d", d->shard_mode);
+    // the parent holds sizes + structures of the whole problem; one child per GPU does the work
+    qck_problem_desc dp = *d;
+    dp.device = -1; dp.n_gpus = 1; dp.integ_begin = 0; dp.integ_end = -1;
+    qck_handle* parent = nullptr;
+    int rc = qck_create_single(&dp, &parent, false);
+    if (rc) return rc;
+    rc = qck_multi_create(d, parent);
+    if (rc) { g_create_error = parent->err; qck_destroy(parent); return rc; }
+    *out = parent;
+    return QCK_OK;
+}
+
 void qck_destroy(qck_handle* h) {
     if (!h) return;
+    if (!h->children.empty() || h->nccl) qck_multi_destroy(h);
     if (h->device < 0) { delete h; return; }
     cudaSetDevice(h->device);
+    qck_pipe_destroy(h);
     for (auto& C : h->classes) for (void* p : C.allocs) cudaFree(p);
     for (void* p : h->allocs) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -807,6 +848,7 @@ int qck_eval_all(qck_handle* h, const double* Z, const double* mu, double* F, do
 
 int qck_eval_device(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, double* dF, double* dJ, double* dH, void* stream) {
     if (!h) return QCK_EINVAL;
+    if (!h->children.empty()) return fail(h, QCK_EINVAL, "multi-GPU handle: use qck_upload + qck_eval_resident (device pointers belong to one GPU)");
     if (!dZ) return fail(h, QCK_EINVAL, "dZ is NULL");
     if (h->device < 0) return fail(h, QCK_ENODEVICE, "structure-only handle (device=-1): libqcknot has no CPU evaluation path");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -814,25 +856,35 @@ int qck_eval_device(qck_handle* h, uint32_t mask, const double* dZ, const double
     if (!(m & QCK_EVAL_F)) dF = nullptr;
     if (!(m & QCK_EVAL_J)) dJ = nullptr;
     if (!(m & QCK_EVAL_H)) dH = nullptr;
-    return run(h, m, dZ, dmu, dF, dJ, dH, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+    if (dZ == h->dZ || dmu == h->dmu || dF == h->dF || dJ == h->dJ || dH == h->dH) { h->pipe.valid_mask = 0; h->pipe.z_on_device = false; h->pipe.mu_on_device = false; }
+    return qck_run(h, m, 0, h->T - 1, dZ, dmu, dF, dJ, dH, stream ? static_cast<cudaStream_t>(stream) : h->stream, 0);
 }
 
 int qck_device_buffers(qck_handle* h, double** dZ, double** dmu, double** dF, double** dJ, double** dH) {
     if (!h) return QCK_EINVAL;
+    if (!h->children.empty()) return fail(h, QCK_EINVAL, "multi-GPU handle: use qck_shard_device_buffers");
     if (dZ) *dZ = h->dZ;
     if (dmu) *dmu = h->dmu;
     if (dF) *dF = h->dF;
     if (dJ) *dJ = h->dJ;
     if (dH) *dH = h->dH;
+    h->pipe.valid_mask = 0; h->pipe.z_on_device = false; h->pipe.mu_on_device = false;  // the caller may overwrite them
     return QCK_OK;
 }
 
 int qck_synchronize(qck_handle* h) {
     if (!h) return QCK_EINVAL;
+    if (!h->children.empty()) {
+        for (qck_handle* c : h->children) {
+            int rc = qck_synchronize(c);
+            if (rc) { h->err = c->err; return rc; }
+        }
+        return QCK_OK;
+    }
     if (h->device < 0) return QCK_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return QCK_OK;
+    return h->uses_status ? qck_check_status(h) : QCK_OK;
 }
 
 int qck_shared_hessian_positions(const qck_handle* h, int64_t* count, int64_t* pos) {
@@ -856,7 +908,26 @@ int qck_host_unregister(void* p) {
 
 int qck_launch_count(const qck_handle* h, int64_t* launches) {
     if (!h || !launches) return QCK_EINVAL;
-    *launches = h->launches;
+    long long n = h->launches;
+    for (const qck_handle* c : h->children) n += c->launches;
+    *launches = n;
+    return QCK_OK;
+}
+
+int qck_transfer_stats(const qck_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* cache_hits) {
+    if (!h) return QCK_EINVAL;
+    long long a = h->pipe.h2d_bytes, b = h->pipe.d2h_bytes, c = h->pipe.cache_hits;
+    for (const qck_handle* ch : h->children) { a += ch->pipe.h2d_bytes; b += ch->pipe.d2h_bytes; c += ch->pipe.cache_hits; }
+    if (h2d_bytes) *h2d_bytes = a;
+    if (d2h_bytes) *d2h_bytes = b;
+    if (cache_hits) *cache_hits = c;
+    return QCK_OK;
+}
+
+int qck_invalidate(qck_handle* h) {
+    if (!h) return QCK_EINVAL;
+    h->pipe.valid_mask = 0; h->pipe.z_staged = false; h->pipe.z_on_device = false; h->pipe.mu_on_device = false;
+    for (qck_handle* c : h->children) qck_invalidate(c);
     return QCK_OK;
 }
 

@@ -101,6 +101,16 @@ struct QckClassDev {
     double pade_r[8];
 };
 
+// Launch geometry of one class, filled by the launcher at the first launch on a device (attribute + occupancy calls
+// happen once per handle, not on every callback).
+struct QckPlanCache {
+    const void* kern = nullptr;
+    size_t smem = 0;
+    int per_sm = 0;
+};
+
+#define QCK_ST_EXP_RANGE 1  // exponential integrator with a Hessian: ||h A||_1 needs more squarings than the tape holds
+
 struct QckLaunch {
     QckClassDev c;
     const double* Z;
@@ -124,6 +134,8 @@ struct QckLaunch {
     long long* timing;       // optional per-stage cycle counters (debug)
     unsigned stagger_ns;     // start-up delay step between the CTAs of one SM
     int hoff;                // row-slice kernel: image offset where the Hessian part starts
+    int* status;             // device-side error word (QCK_ST_* bits)
+    QckPlanCache* plan;      // host-side: per-class launch plan cache (may be NULL)
 };
 
 struct QckReduce {  // fixed-order reduction of shared Hessian positions
@@ -143,6 +155,10 @@ int qck_fused_aux_limit(void);
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,
                       int npart, cudaStream_t stream, int* launches);
+// gathers the non-redundant positions of a value array into the compact D2H buffer: out[t*ostride + i] = arr[t*nnz + src[i]], i < C
+int qck_launch_pack(const double* arr, double* out, const int* src, int C, long long ostride, long long nnz, long long nk, cudaStream_t stream, int* launches);
+// out[t*C + i] = arr[t*nnz + src[i]] the other way round (scatter back): arr[t*nnz + src[i]] = in[t*C + i]
+int qck_launch_unpack(double* arr, const double* in, const int* src, int C, long long ostride, long long nnz, long long nk, cudaStream_t stream, int* launches);
 // scratch sizing shared by host map builder and kernels
 void qck_scratch_layout(QckClassDev& c);   // phase 1: matrices + scalars (needed to compute slots)
 void qck_smem_finalize(QckClassDev& c);    // phase 2: tables + staging, after W / tab_len / nseg are known

@@ -799,6 +799,12 @@ qck_quantum_kernel(const QckLaunch p) {
         nrm *= fabs(h);
         int sq = 0;
         while (nrm > 0.0625 && sq < 40) { nrm *= 0.5; ++sq; }
+        if (c.tape && sq > c.tape_levels) {
+            // ||h A||_1 > 2^(tape_levels - 4): the Hessian tape cannot hold that many squaring levels.  The same clamp applies
+            // to every call on the handle (with or without the Hessian in the mask) and the host reports QCK_ERANGE.
+            sq = c.tape_levels;
+            if (tid == 0 && p.status) atomicOr(p.status, QCK_ST_EXP_RANGE);
+        }
         const double y = ldexp(h, -sq);
         int cur = 0;
         {   // Horner start (m = TK): P = I + (Y/TK), L_j = Y_j/TK
@@ -821,7 +827,6 @@ qck_quantum_kernel(const QckLaunch p) {
         double2* tapeH = c.tape ? c.tape + (size_t)gid * c.tape_stride : nullptr;  // [(TK-1) steps][nd][N*N]
         double2* tapeS = tapeH ? tapeH + (size_t)(TK - 1) * nd * N * N : nullptr;        // [levels][1 + nd][N*N]
         const bool taping = needH && tapeH != nullptr;
-        if (taping && sq > c.tape_levels) sq = c.tape_levels;  // (never for ||h A||_1 <= 2^(tape_levels-4))
         auto tape_put = [&](double2* dst, const double2* src) {
             for (int e = tid; e < N * N; e += nthreads) dst[e] = src[(e % N) + NP * (e / N)];
         };
@@ -1534,10 +1539,15 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         gsmem = (gsmem + 15) & ~(size_t)15;
         L.group_smem = (int)gsmem;
         smem = gsmem * ngroups + (size_t)L.n_aux * sizeof(QckAux) + (L.moff_smem ? (size_t)nact * 12 + 16 : 0);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-        if (e != cudaSuccess) return (int)e;
+        if (L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem) {
+            per_sm = L.plan->per_sm;  // found at an earlier launch of this class on this device
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+            if (e != cudaSuccess) return (int)e;
+            if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = smem; L.plan->per_sm = per_sm; }
+        }
         if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
         grid = (long long)sm_count * per_sm;
         if (c.max_ctas > 0 && grid * ngroups > c.max_ctas) grid = c.max_ctas / ngroups;  // the Hessian tape was sized for this many groups
@@ -1552,9 +1562,9 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     }
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
     static const bool tim = getenv("QCK_DEBUG_TIMING") != nullptr;
-    static long long* d_tim = nullptr;
+    long long* d_tim = nullptr;
     if (tim) {
-        if (!d_tim) cudaMalloc(&d_tim, 8 * sizeof(long long));
+        cudaMalloc(&d_tim, 8 * sizeof(long long));  // (debug knob only; freed below)
         cudaMemsetAsync(d_tim, 0, 8 * sizeof(long long), stream);
         L.timing = d_tim;
     }
@@ -1566,6 +1576,7 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         cudaStreamSynchronize(stream);
         double per = 1.0 / (double)n_items;
         fprintf(stderr, "[qcknot timing] cycles/item (thread 0): loop-top %.0f | wait+bar %.0f | stage0 %.0f | prefetch-issue %.0f | stage1 %.0f | stage2 %.0f | write-out %.0f | mask=%u\n", h[0] * per, h[1] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per, L.mask);
+        cudaFree(d_tim);
     }
     if (launches) ++*launches;
     return (int)cudaGetLastError();

@@ -474,8 +474,11 @@ int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, 
     while (nwarps > 1 && shared + nwarps * per_warp > 227 * 1024) --nwarps;
     const size_t smem = shared + nwarps * per_warp;
     if (smem > 227 * 1024) return 0;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (!(L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = smem; L.plan->per_sm = 1; }
+    }
     long long grid = sm_count;
     if (grid * nwarps > L.n_knots) grid = (L.n_knots + nwarps - 1) / nwarps;
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;

@@ -35,7 +35,11 @@ class QuantumDynamics:
 
     knot_range=(t0, t1)       evaluate only the constraint blocks t0 <= t < t1 (0-based; one-knot halo is read);
                               F/dF/mu_d2F then return that shard's contiguous segment of the global arrays.
-    integrator_range=(q0,q1)  ensemble sharding: evaluate only integrators q0 <= q < q1 (structures stay global).
+    integrator_range=(q0,q1)  manual ensemble sharding: evaluate only integrators q0 <= q < q1 (structures stay global;
+                              q0 == q1 is an empty shard that launches nothing).
+    n_gpus, shard_mode        n_gpus > 1: this ONE object drives GPUs device .. device+n_gpus-1 (or `devices`), the knot blocks
+                              ("knot") or the quantum integrators ("ensemble") partitioned inside libqcknot; F/dF/mu_d2F fill
+                              the caller's single arrays exactly as with one GPU.
     """
 
     def __init__(
@@ -46,6 +50,10 @@ class QuantumDynamics:
         device: int = 0,
         knot_range: Optional[Tuple[int, int]] = None,
         integrator_range: Optional[Tuple[int, int]] = None,
+        n_gpus: int = 1,
+        shard_mode: str = "knot",
+        devices: Optional[Sequence[int]] = None,
+        host_threads: int = 0,
     ):
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -81,10 +89,22 @@ class QuantumDynamics:
                 d.ctrl_off = I.dx_components.start
             else:
                 raise TypeError(f"unsupported integrator {type(I).__name__}")
-        q0, q1 = integrator_range if integrator_range is not None else (0, 0)
+        q0, q1 = integrator_range if integrator_range is not None else (0, -1)  # integ_end < 0: every integrator
         self.integrator_range = (q0, q1) if integrator_range is not None else (0, len(self.integrators))
+        if shard_mode not in ("knot", "ensemble"):
+            raise ValueError("shard_mode must be 'knot' or 'ensemble'")
+        self.n_gpus = max(1, int(n_gpus))
+        self.shard_mode = shard_mode
+        devs = None
+        if devices is not None:
+            if len(devices) != self.n_gpus:
+                raise ValueError("devices must list n_gpus ordinals")
+            devs = (C.c_int32 * self.n_gpus)(*[int(x) for x in devices])
+            self._keep.append(devs)
         pd = _lib.ProblemDesc(self.T, self.zdim, dt_off, dt_fixed, len(self.integrators), int(self.eval_hessian),
-                              int(device), int(q0), int(q1), 0, descs)
+                              int(device), int(q0), int(q1), self.n_gpus, descs,
+                              _lib.QCK_SHARD_ENSEMBLE if shard_mode == "ensemble" else _lib.QCK_SHARD_KNOT,
+                              int(host_threads), devs)
         rc = self._lib.qck_create(C.byref(pd), C.byref(self._h))
         if rc != 0:
             msg = self._lib.qck_last_error(None).decode()
@@ -203,6 +223,65 @@ class QuantumDynamics:
         if n.value:
             self._check(self._lib.qck_shared_hessian_positions(self._h, C.byref(n), _ptr(pos)))
         return pos
+
+    # ---- multi-GPU handles -------------------------------------------------------------------------------------------
+    def shards(self):
+        """[(device, block_begin, block_end, integ_begin, integ_end)] of every GPU behind this object."""
+        n = C.c_int32()
+        self._check(self._lib.qck_shard_count(self._h, C.byref(n)))
+        out = []
+        for g in range(n.value):
+            dev, ib, ie = C.c_int32(), C.c_int32(), C.c_int32()
+            b0, b1 = C.c_int64(), C.c_int64()
+            self._check(self._lib.qck_shard_info(self._h, g, C.byref(dev), C.byref(b0), C.byref(b1), C.byref(ib), C.byref(ie)))
+            out.append((dev.value, b0.value, b1.value, ib.value, ie.value))
+        return out
+
+    def upload(self, Z, mu=None) -> None:
+        Z_ = self._Z(Z)
+        mu_ = self._mu(mu) if mu is not None else None
+        self._check(self._lib.qck_upload(self._h, _ptr(Z_), _ptr(mu_)))
+
+    def eval_resident(self, mask: int = 7) -> None:
+        self._check(self._lib.qck_eval_resident(self._h, mask))
+
+    def gather_device(self, mask: int = 7) -> None:
+        self._check(self._lib.qck_gather_device(self._h, mask))
+
+    def shard_device_buffers(self, g: int):
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self._check(self._lib.qck_shard_device_buffers(self._h, g, *[C.byref(p) for p in ptrs]))
+        return tuple(p.value for p in ptrs)
+
+    def gathered_buffers(self, g: int):
+        ptrs = [C.c_void_p() for _ in range(3)]
+        self._check(self._lib.qck_gathered_buffers(self._h, g, *[C.byref(p) for p in ptrs]))
+        return tuple(p.value for p in ptrs)
+
+    def nccl_version(self):
+        v, n = C.c_int32(), C.c_int32()
+        self._check(self._lib.qck_nccl_version(self._h, C.byref(v), C.byref(n)))
+        return v.value, n.value
+
+    def transfer_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.qck_transfer_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"h2d_bytes": a.value, "d2h_bytes": b.value, "cache_hits": c.value}
+
+    def compact_map(self, arr: int) -> np.ndarray:
+        """(n, 4) int32: (offset in the knot block, offset in the compact layout, length, repeats) of value array arr."""
+        n = C.c_int64()
+        self._check(self._lib.qck_compact_map(self._h, arr, C.byref(n), None))
+        segs = np.empty((n.value, 4), dtype=np.int32)
+        if n.value:
+            self._check(self._lib.qck_compact_map(self._h, arr, C.byref(n), _ptr(segs)))
+        return segs
+
+    def expand_host(self, arr: int, compact: np.ndarray, out: np.ndarray, nk: int) -> None:
+        self._check(self._lib.qck_expand_host(self._h, arr, _ptr(compact), _ptr(out), nk))
+
+    def invalidate(self) -> None:
+        self._check(self._lib.qck_invalidate(self._h))
 
     @property
     def launch_count(self) -> int:

@@ -28,6 +28,10 @@ def knot_shards(n_blocks: int, world: int) -> List[Tuple[int, int]]:
 def integrator_shard(n_quantum: int, n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """Ensemble sharding: quantum integrators [q0, q1) of rank `rank`; the trailing non-quantum (derivative)
     integrators go to the last rank so that every integrator is evaluated exactly once."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    if n_quantum < world:
+        raise ValueError(f"{n_quantum} quantum integrators cannot be sharded over {world} ranks")
     q0, q1 = n_quantum * rank // world, n_quantum * (rank + 1) // world
     if rank == world - 1:
         q1 = n_total
@@ -48,10 +52,12 @@ def all_gather_segments(local: torch.Tensor, counts: Sequence[int]) -> torch.Ten
 
 
 def all_reduce_shared(H_local: torch.Tensor, shared_pos: torch.Tensor, nnzH: int) -> torch.Tensor:
-    """Ensemble sharding: sum the per-rank partial sums of the Hessian positions that several integrators share
-    (a x a, a x dt, dt x dt); every other position is written by exactly one rank, so a sum over ranks of the
-    zero-initialised arrays assembles them as well.  Returns the assembled array (same on every rank)."""
-    del shared_pos, nnzH  # the disjoint part rides on the same reduction; kept in the signature for clarity
-    out = H_local.clone()
-    dist.all_reduce(out, op=dist.ReduceOp.SUM)
-    return out
+    """Ensemble sharding, one process per GPU: sum the per-rank partial sums of the Hessian positions that several
+    integrators share (a x a, a x dt, dt x dt) -- ONLY those, (T-1) * len(shared_pos) doubles -- in place.  Every other
+    position of H_local is written by exactly one rank and is left alone."""
+    nb = H_local.numel() // nnzH
+    idx = (torch.arange(nb, device=H_local.device)[:, None] * nnzH + shared_pos.to(H_local.device)[None, :]).reshape(-1)
+    buf = H_local[idx]
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    H_local[idx] = buf
+    return H_local

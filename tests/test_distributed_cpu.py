@@ -69,8 +69,27 @@ def _worker(rank, world, port, ret):
         for I, r0 in list(zip(full.integrators, full.row_off))[q0:q1]:
             Hm += I.hessian(zt, zt1, mu[t * full.dyn + r0: t * full.dyn + r0 + I.dim])
         Hloc[t * full.nnzH:(t + 1) * full.nnzH] = Hm[rr, cc]
-    Hsum = all_reduce_shared(torch.from_numpy(Hloc), torch.from_numpy(shared), full.nnzH).numpy()
-    ok = ok and np.allclose(Hsum, full.mu_d2F(Z, mu), rtol=0, atol=1e-14) and len(shared) == 6
+    Hsum = all_reduce_shared(torch.from_numpy(Hloc.copy()), torch.from_numpy(shared), full.nnzH)
+    Href = full.mu_d2F(Z, mu)
+    idx = (np.arange(traj.T - 1)[:, None] * full.nnzH + shared[None, :]).reshape(-1)
+    # the shared entries are complete on every rank, the others untouched (each is written by exactly one rank) ...
+    ok = ok and np.allclose(Hsum.numpy()[idx], Href[idx], rtol=0, atol=1e-14) and len(shared) == 6
+    rest = np.setdiff1d(np.arange(Href.size), idx)
+    ok = ok and np.array_equal(Hsum.numpy()[rest], Hloc[rest])
+    # ... and the disjoint parts of all ranks assemble to the full array (test plumbing: sum with the shared part counted once)
+    asm = Hsum.clone()
+    if rank != 0:
+        asm[torch.from_numpy(idx)] = 0.0
+    dist.all_reduce(asm)
+    ok = ok and np.allclose(asm.numpy(), Href, rtol=0, atol=1e-14)
+    # a shard with no integrator at all is legal (begin == end) and 'every integrator' is spelled integ_end < 0
+    E = qcknot.QuantumDynamics(integrators, traj, device=-1, integrator_range=(2, 2))
+    ok = ok and E.integrator_range == (2, 2) and E.shards()[0][3:] == (2, 2)
+    try:
+        integrator_shard(2, 4, 0, 4)
+        ok = False
+    except ValueError:
+        pass
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

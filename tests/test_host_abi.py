@@ -129,3 +129,83 @@ def test_trajectory_layout_matches_reference_fixture():
     z = traj.datavec
     assert np.array_equal(z[15:30], traj.data[:, 1])
     assert np.array_equal(qcknot.operator_to_iso_vec(np.eye(2)), [1, 0, 0, 0, 0, 1, 0, 0])
+
+
+# ---- round 2: host-buffer path (compact layout + threaded expansion) and multi-GPU handles, host side ------------------------
+def _expected_expand(D, arr, nnz, full, nk):
+    """What the host half must produce from the compact form of `full`: owned positions, kron copies = first copy."""
+    segs = D.compact_map(arr)
+    C_ = int(segs[:, 2].sum())
+    comp = np.empty(nk * C_)
+    want = np.full(nk * nnz, np.nan)
+    f2, c2, w2 = full.reshape(nk, nnz), comp.reshape(nk, C_), want.reshape(nk, nnz)
+    for fo, co, ln, rep in segs:
+        c2[:, co:co + ln] = f2[:, fo:fo + ln]
+        for r in range(rep):
+            w2[:, fo + r * ln:fo + (r + 1) * ln] = f2[:, fo:fo + ln]
+    return segs, comp, want
+
+
+@pytest.mark.parametrize("name,kw", [("cz", {"T": 9}), ("hadamard", {"T": 40}), ("ket", {"T": 12}),
+                                     ("sampling", {"T": 5, "n_systems": 7}), ("cz", {"T": 5, "integrator": "exponential"})])
+def test_compact_map_covers_every_position_once_and_expands(name, kw):
+    systems, traj, integrators = wl.config(name, **kw)
+    D = qcknot.QuantumDynamics(integrators, traj, device=-1)
+    nk = D.n_blocks
+    rng = np.random.default_rng(5)
+    for arr, nnz in ((0, D.dyn), (1, D.nnzJ), (2, D.nnzH)):
+        full = rng.standard_normal(nk * nnz)
+        segs, comp, want = _expected_expand(D, arr, nnz, full, nk)
+        cover = np.zeros(nnz, dtype=int)
+        for fo, co, ln, rep in segs:
+            cover[fo:fo + ln * rep] += 1
+        assert np.all(cover == 1), "an unsharded handle writes every position of the knot block exactly once"
+        assert np.array_equal(np.cumsum(np.r_[0, segs[:-1, 2]]), segs[:, 1])
+        out = np.full(nk * nnz, np.nan)
+        D.expand_host(arr, comp, out, nk)
+        assert np.array_equal(out, want)
+    if name == "cz" and "integrator" not in kw:
+        # SURVEY 8: 5,832 of the 6,674 Jacobian values per knot are 9-fold replicas of two 18x18 blocks
+        J = D.compact_map(1)
+        assert int(J[:, 2].sum()) == 6674 - 5832 + 2 * 324 and sorted(J[J[:, 3] > 1][:, 3].tolist()) == [9, 9]
+        assert int(D.compact_map(0)[:, 2].sum()) + int(J[:, 2].sum()) + int(D.compact_map(2)[:, 2].sum()) == 3303
+    D.close()
+
+
+def test_multi_gpu_handle_partitions_host_side():
+    """n_gpus > 1 on a structure-only handle: the partition the library would use, no device needed."""
+    systems, traj, integrators = wl.config("cz", T=1001)
+    D = qcknot.QuantumDynamics(integrators, traj, device=-1, n_gpus=8, shard_mode="knot")
+    sh = D.shards()
+    assert len(sh) == 8 and sh[0][1] == 0 and sh[-1][2] == 1000
+    assert all(a[2] == b[1] for a, b in zip(sh, sh[1:])) and all(110 <= s[2] - s[1] <= 140 for s in sh)
+    assert all(s[3:] == (0, len(integrators)) for s in sh)
+    assert (D.dyn, D.nnzJ, D.nnzH) == (170, 6674, 1643)
+    with pytest.raises(qcknot.QcknotError):
+        D.F(traj.datavec)  # no CPU evaluation path, multi-GPU or not
+    D.close()
+    systems, traj, integrators = wl.config("sampling", T=4, n_systems=10)
+    D = qcknot.QuantumDynamics(integrators, traj, device=-1, n_gpus=4, shard_mode="ensemble")
+    sh = D.shards()
+    assert [s[3] for s in sh] == [0, 2, 5, 7] and sh[-1][4] == len(integrators) and all(s[1:3] == (0, 3) for s in sh)
+    D.close()
+    with pytest.raises(qcknot.QcknotError):
+        qcknot.QuantumDynamics(integrators, traj, device=-1, n_gpus=16, shard_mode="ensemble")  # 10 systems over 16 GPUs
+    systems, traj, integrators = wl.config("hadamard", T=4)
+    with pytest.raises(qcknot.QcknotError):
+        qcknot.QuantumDynamics(integrators, traj, device=-1, n_gpus=8, shard_mode="knot")  # 3 blocks over 8 GPUs
+
+
+def test_ensemble_children_exclude_shared_entries_from_their_segments():
+    systems, traj, integrators = wl.config("sampling", T=3, n_systems=4)
+    full = qcknot.QuantumDynamics(integrators, traj, device=-1)
+    shared = set(full.shared_hessian_positions().tolist())
+    cover = np.zeros(full.nnzH, dtype=int)
+    for q0, q1 in ((0, 2), (2, len(integrators))):
+        S = qcknot.QuantumDynamics(integrators, traj, device=-1, integrator_range=(q0, q1))
+        for fo, co, ln, rep in S.compact_map(2):
+            cover[fo:fo + ln * rep] += 1
+        S.close()
+    # manual integrator ranges keep their local partial sums at the shared positions (both shards write them) ...
+    assert all(cover[p] == 2 for p in shared) and all(cover[p] == 1 for p in range(full.nnzH) if p not in shared)
+    full.close()
