@@ -4,11 +4,21 @@
 One "step" = one pass of the hot path over the whole (per-GPU) knot range: residual + every Jacobian value + every
 Hessian-of-Lagrangian value of every dynamics integrator, written into the solver's fixed-structure value arrays.
 
-  value   device-resident throughput: Z and mu already in HBM, values left in HBM (one fused kernel launch/step)
-  e2e     the same metric through the reference-facing host-buffer call (qck_eval_all through QuantumDynamics.eval_all):
-          H2D of Z and mu from page-locked host memory + kernel + D2H of F, J, H values, every step
-  roofline  algorithmic bytes 8*(2*zdim + 2*dyn + nnzJ + nnzH) per knot block / measured kernel time vs measured HBM peak
-  cpu_baseline  oracle/knot_oracle.c (C restatement of the reference algorithm, pthreads over knots) on the host cores
+  value     device-resident throughput: Z and mu already in HBM, values left in HBM (one fused kernel launch per step).
+            The timed region is stretched to >= 1 s by repeating the K steps R times (config.timed_passes = K * R); all
+            numbers are per step.
+  e2e       the same metric through the reference-facing host-buffer call (QuantumDynamics.eval_all -> qck_eval_all) with
+            ordinary (pageable) numpy arrays, every step on a DIFFERENT trajectory (two alternate) so that nothing is cached:
+            staging + H2D of Z and mu, kernels, compact D2H (kron blocks once), host-side expansion into the caller's arrays.
+            With N > 1 GPUs ONE caller (rank 0) drives all N GPUs through one multi-GPU handle (n_gpus = N, knot-sharded);
+            the other ranks idle behind a host-side barrier.
+  roofline  algorithmic bytes 8*(2*zdim + 2*dyn + nnzJ + nnzH) per knot block / measured kernel time vs measured HBM peak;
+            `pcie`: bytes the e2e step moved over PCIe / e2e time vs the measured link; `host`: bytes written into the
+            caller's arrays / e2e time next to what the host threads reach on their own (expansion only, no GPU involved).
+  cpu_baseline  oracle/knot_oracle.c (C restatement of the reference algorithm, pthreads over knots) on the host cores:
+            `value` = the tuned variant (constant anticommutators hoisted, G_j G + G G_j reused), `literal` = the naive one.
+  extra     sub-records (rank 0): exponential integrators, T = 100,000, the sampling problem (ensemble-sharded when N > 1),
+            the NCCL all-gather of the device-resident segments (N > 1).
 
 Workload (default): two-transmon (3 levels each, N=9, 4 drives) CZ UnitarySmoothPulseProblem shape, Pade-4 integrator,
 free timestep, T = 10,000 knot points per GPU (BASELINE.json north_star target config; configs[3] sweep point),
@@ -30,6 +40,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FP64_PEAK_TFLOPS = 35.4  # DFMA loop measured on this pool's B200 (profiles/r01_box_peaks_fp64_hbm_pcie.txt)
+PCIE_PEAK_GBS = 56.0     # pinned D2H measured on this pool's B200 boxes (same file)
+METRIC = "knot-pt constraint+Jac+Hess evals/s"
 
 
 def parse():
@@ -42,11 +54,10 @@ def parse():
     ap.add_argument("--integrator", default="pade", choices=["pade", "exponential"])
     ap.add_argument("--T", type=int, default=10000, help="knot points per GPU")
     ap.add_argument("--systems", type=int, default=None, help="sampled systems (sampling workload)")
-    ap.add_argument("--shard", default="knot", choices=["knot", "ensemble"],
-                    help="knot: every GPU evaluates T knots (weak scaling); ensemble (sampling workload): the sampled systems are "
-                         "split over the GPUs, shared-control Hessian entries are summed with one NCCL all-reduce (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget (bounded sample)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra sub-records")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU-baseline budget (bounded sample)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="minimum length of the timed regions")
     return ap.parse_args()
 
 
@@ -55,9 +66,13 @@ def workload_name(args, n):
          "hadamard": "single-qubit Hadamard UnitarySmoothPulseProblem, N=2, 2 drives",
          "sampling": f"UnitarySamplingProblem 4-level transmon, {args.systems or 256} systems",
          "ket": "QuantumStateSmoothPulseProblem, N=2, 2 drives"}[args.workload]
-    if getattr(args, "shard", "knot") == "ensemble":
-        return f"{d}, {args.integrator} integrator, free dt, T={args.T} knots, systems split over {n} GPU(s) (ensemble-sharded)"
     return f"{d}, {args.integrator} integrator, free dt, T={args.T} knots/GPU x {n} GPU(s), knot-sharded"
+
+
+def config_dict(args, n):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(args, n), "seed": 1234, "evals_per_step": n * (args.T - 1),
+            "l2": "outputs per step exceed L2 (inputs+outputs larger than L2, no flush needed)"}
 
 
 def algorithmic_bytes(zdim, dyn, nnzJ, nnzH):
@@ -114,69 +129,190 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def build_problem(args, n_gpus):
+def build_problem(args, n_gpus, **kw):
     from qcknot import workloads as wl
     T_total = n_gpus * (args.T - 1) + 1
-    return wl.config(args.workload, T=T_total, integrator=args.integrator, n_systems=args.systems)
+    return wl.config(kw.get("workload", args.workload), T=kw.get("T", T_total), integrator=kw.get("integrator", args.integrator),
+                     n_systems=kw.get("systems", args.systems))
 
 
-def run_reference(args):
-    """--impl reference: the reference algorithm's CPU restatement (oracle/knot_oracle.c) on all host cores.
-    The Julia reference itself cannot run here or on the box (no julia, its arithmetic lives in un-vendored packages)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU legs (the only places that execute oracle/) --------------------------------------------------------------------------
+def _cpu_port(args, T):
     from oracle.bridge import oracle_dynamics
     from oracle.c_port import CPort
     from qcknot import workloads as wl
     a2 = argparse.Namespace(**vars(args))
-    systems, traj, integrators = build_problem(a2, 1)  # one GPU's worth of knots is the bounded sample per step
+    a2.T = T
+    systems, traj, integrators = build_problem(a2, 1)
     O = oracle_dynamics(integrators, traj)
     cp = CPort(O)
-    Z = traj.datavec
     nb = traj.T - 1
-    mu = wl.random_multipliers(nb * O.dyn)
+    return cp, traj.datavec, wl.random_multipliers(nb * O.dyn), nb
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU restatement (oracle/knot_oracle.c, tuned variant) on all host cores.
+    The Julia reference itself cannot run here or on the box (no julia, its arithmetic lives in un-vendored packages)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cp, Z, mu, nb = _cpu_port(args, args.T)  # one GPU's worth of knots is the bounded sample per step
     cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cp.eval(Z, mu, nthreads=cores)
+    out = cp.eval(Z, mu, nthreads=cores, tuned=True)
+    for _ in range(min(args.warmup, 2)):
+        cp.eval(Z, mu, nthreads=cores, tuned=True, out=out)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cp.eval(Z, mu, nthreads=cores)
+        cp.eval(Z, mu, nthreads=cores, tuned=True, out=out)
     dt = time.perf_counter() - t0
     value = nb * args.steps / dt
-    sample = f"{nb} knot blocks/step x {args.steps} steps of the same workload, all {cores} host cores"
+    sample = (f"{nb} knot blocks/step x {args.steps} steps of the same workload, all {cores} host cores, tuned variant "
+              "(constant anticommutators hoisted, G_j G + G G_j reused)")
     print(json.dumps({
-        "impl": "reference", "metric": "knot-pt constraint+Jac+Hess evals/s", "value": value, "unit": "evals/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, args.gpus)},
+        "config": config_dict(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline(args, integrators_builder):
-    from oracle.bridge import oracle_dynamics
-    from oracle.c_port import CPort
-    from qcknot import workloads as wl
-    a2 = argparse.Namespace(**vars(args))
-    a2.T = min(args.T, 4001)
-    systems, traj, integrators = build_problem(a2, 1)
-    O = oracle_dynamics(integrators, traj)
-    cp = CPort(O)
-    Z, nb = traj.datavec, traj.T - 1
-    mu = wl.random_multipliers(nb * O.dyn)
+def cpu_baseline(args):
+    cp, Z, mu, nb = _cpu_port(args, min(args.T, 4001))
     cores = os.cpu_count() or 1
-    cp.eval(Z, mu, nthreads=cores)
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        cp.eval(Z, mu, nthreads=cores)
-        reps += 1
-        dt = time.perf_counter() - t0
-        if dt > args.cpu_seconds or reps >= 200:
-            break
-    return {"value": nb * reps / dt, "unit": "evals/s", "cores": cores, "kind": "port",
-            "sample": f"{nb} knot blocks of the same workload x {reps} passes ({dt:.1f} s), pthreads over knots"}
+    res = {}
+    for tuned, budget in ((True, 0.7 * args.cpu_seconds), (False, 0.3 * args.cpu_seconds)):
+        out = cp.eval(Z, mu, nthreads=cores, tuned=tuned)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            cp.eval(Z, mu, nthreads=cores, tuned=tuned, out=out)
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt > budget or reps >= 200:
+                break
+        res[tuned] = (nb * reps / dt, reps, dt)
+    return {"value": res[True][0], "unit": "evals/s", "cores": cores, "kind": "port", "literal": res[False][0],
+            "sample": f"{nb} knot blocks of the same workload x {res[True][1]} passes ({res[True][2]:.1f} s) tuned "
+                      f"(anticommutators hoisted, G_j G + G G_j reused) / x {res[False][1]} passes literal, pthreads over knots"}
+
+
+# ---- device-resident timing of one handle ------------------------------------------------------------------------------------
+def time_device(D, Z, mu, F, J, H, stream, steps, warmup, min_seconds, barrier=None, mask=7):
+    """Returns (ms per pass, passes timed, launches in the timed region)."""
+    import torch
+    st = stream.cuda_stream
+
+    def step():
+        D.eval_device(mask, Z.data_ptr(), mu.data_ptr(), F.data_ptr(), J.data_ptr(), H.data_ptr(), st)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(warmup, 3)):
+        step()
+    e0.record(stream)
+    for _ in range(3):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1) / 3, 1e-3)
+    reps = max(1, int(np.ceil(min_seconds * 1e3 / (steps * est))))
+    if barrier:
+        reps = barrier(reps)  # the same repeat count on every rank
+    l0 = D.launch_count
+    if barrier:
+        barrier(0)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps * reps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier(0)
+    return e0.elapsed_time(e1) / (steps * reps), steps * reps, D.launch_count - l0
+
+
+def time_e2e(D, Zs, mus, F, J, H, min_seconds, min_steps=5, max_steps=400):
+    """Host-buffer calls on alternating trajectories; returns (s per step, steps, transfer stats of the last step)."""
+    for i in range(3):
+        D.eval_all(Zs[i & 1], mus[i & 1], F, J, H)
+    t0 = time.perf_counter()
+    D.eval_all(Zs[1], mus[1], F, J, H)
+    est = time.perf_counter() - t0
+    steps = int(min(max_steps, max(min_steps, np.ceil(min_seconds / est))))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        D.eval_all(Zs[i & 1], mus[i & 1], F, J, H)
+    dt = (time.perf_counter() - t0) / steps
+    return dt, steps, D.transfer_stats()
+
+
+def expand_only_gbs(D, nb):
+    """The host half alone (compact layout -> caller arrays, no GPU): what the host threads and memory system can absorb."""
+    bufs, out_bytes = [], 0
+    for arr, nnz in ((0, D.dyn), (1, D.nnzJ), (2, D.nnzH)):
+        C_ = int(D.compact_map(arr)[:, 2].sum())
+        bufs.append((arr, np.zeros(nb * C_), np.empty(nb * nnz)))
+        out_bytes += nb * nnz * 8
+    best = 0.0
+    for rep in range(4):
+        t0 = time.perf_counter()
+        for arr, comp, out in bufs:
+            D.expand_host(arr, comp, out, nb)
+        if rep:
+            best = max(best, out_bytes / (time.perf_counter() - t0) * 1e-9)
+    return best
+
+
+def extra_records(args, dev, stream, n_gpus, rank0_devices):
+    """Sub-records beside the headline (rank 0 only): every one is a device-timed pass through the same C-ABI."""
+    import torch
+    import qcknot
+    from qcknot import workloads as wl
+    peak, _ = hbm_peak()
+    out = {}
+
+    def dev_arm(workload, T, integrator, systems=None, min_seconds=0.3):
+        a2 = argparse.Namespace(**vars(args))
+        a2.workload, a2.T, a2.integrator, a2.systems = workload, T, integrator, systems
+        systems_, traj, integrators = build_problem(a2, 1)
+        D = qcknot.QuantumDynamics(integrators, traj, device=dev.index)
+        nb = D.n_blocks
+        Z = torch.from_numpy(traj.datavec[: traj.T * D.zdim]).to(dev)
+        mu = torch.from_numpy(wl.random_multipliers(nb * D.dyn)).to(dev)
+        F = torch.empty(nb * D.dyn, dtype=torch.float64, device=dev)
+        J = torch.empty(nb * D.nnzJ, dtype=torch.float64, device=dev)
+        H = torch.empty(nb * max(D.nnzH, 1), dtype=torch.float64, device=dev)
+        ms, passes, launches = time_device(D, Z, mu, F, J, H, stream, 5, 3, min_seconds)
+        bpe = algorithmic_bytes(D.zdim, D.dyn, D.nnzJ, D.nnzH)
+        rec = {"evals_per_s": nb / (ms * 1e-3), "us_per_pass": ms * 1e3, "knot_blocks": nb, "passes": passes,
+               "launches_per_pass": launches / passes, "bytes_per_eval": bpe, "hbm_gbs": bpe * nb / (ms * 1e-3) * 1e-9,
+               "hbm_frac": bpe * nb / (ms * 1e-3) * 1e-9 / peak}
+        D.close()
+        del Z, mu, F, J, H
+        return rec, (systems_, traj, integrators)
+
+    # the residual the north_star names: U_{t+1} - exp(-i H dt) U_t (F + J + H, the Hessian is ours: the reference has none)
+    rec, _ = dev_arm("cz", args.T, "exponential")
+    # exact count of complex N x N x N products of the implemented algorithm (DESIGN.md): degree-8 Taylor with nd Frechet jets,
+    # s squarings with the jets, reverse sweep for the second derivatives
+    rec["note"] = "F+J+H; roofline = min(HBM, FP64), see DESIGN.md for the operation count"
+    out["exponential"] = rec
+    rec, _ = dev_arm("cz", 100000, "pade")
+    out["cz_T100000"] = rec
+    rec, _ = dev_arm("sampling", 200, "pade", systems=256)
+    out["sampling_256_T200"] = rec
+    rec, _ = dev_arm("hadamard", 100000, "pade")
+    out["hadamard_T100000"] = rec
+    return out
 
 
 def main():
@@ -192,34 +328,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        host_group = dist.new_group(backend="gloo")  # host-side barrier: does not occupy the GPUs while rank 0 drives them
     n_gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
-    ensemble = args.shard == "ensemble"
-    if ensemble and args.workload != "sampling":
-        raise SystemExit("--shard ensemble needs --workload sampling")
-    if ensemble:
-        # strong scaling: the same T knots on every GPU, each GPU owns a slice of the sampled systems
-        from qcknot.sharding import integrator_shard
-        systems, traj, integrators = build_problem(args, 1)
-        q0, q1 = integrator_shard(len(systems), len(integrators), rank, n_gpus)
-        D = qcknot.QuantumDynamics(integrators, traj, device=local_rank, integrator_range=(q0, q1))
-        nb = D.n_blocks
-        Zh = np.ascontiguousarray(traj.datavec[: (nb + 1) * D.zdim])
-        muh = wl.random_multipliers(nb * D.dyn, seed=1234)
-    else:
-        systems, traj, integrators = build_problem(args, n_gpus)
-        nbp = args.T - 1
-        t0k, t1k = rank * nbp, (rank + 1) * nbp
-        D = qcknot.QuantumDynamics(integrators, traj, device=local_rank, knot_range=(t0k, t1k))
-        nb = D.n_blocks
-        Zh = np.ascontiguousarray(traj.datavec[t0k * D.zdim:(t1k + 1) * D.zdim])
-        muh = wl.random_multipliers(nb * D.dyn, seed=1234 + rank)
-
-    # ---- device-resident arm ------------------------------------------------------------------------------------------
+    # ---- device-resident arm: one process per GPU, rank g evaluates its knot shard (weak scaling, no data-path collective) ----
+    systems, traj, integrators = build_problem(args, n_gpus)
+    nbp = args.T - 1
+    t0k, t1k = rank * nbp, (rank + 1) * nbp
+    D = qcknot.QuantumDynamics(integrators, traj, device=local_rank, knot_range=(t0k, t1k))
+    nb = D.n_blocks
+    Zh = np.ascontiguousarray(traj.datavec[t0k * D.zdim:(t1k + 1) * D.zdim])
+    muh = wl.random_multipliers(nb * D.dyn, seed=1234 + rank)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     Z = torch.from_numpy(Zh).to(dev)
@@ -227,74 +351,109 @@ def main():
     F = torch.empty(nb * D.dyn, dtype=torch.float64, device=dev)
     J = torch.empty(nb * D.nnzJ, dtype=torch.float64, device=dev)
     H = torch.empty(nb * max(D.nnzH, 1), dtype=torch.float64, device=dev)
-    st = stream.cuda_stream
 
-    shared_idx = None
-    if ensemble and world > 1:
-        pos = torch.from_numpy(D.shared_hessian_positions()).to(dev)
-        shared_idx = (torch.arange(nb, device=dev)[:, None] * D.nnzH + pos[None, :]).reshape(-1)
-
-    def step():
-        D.eval_device(7, Z.data_ptr(), mu.data_ptr(), F.data_ptr(), J.data_ptr(), H.data_ptr(), st)
-        if shared_idx is not None:  # the one data-path collective: partial sums of the entries on the shared controls
-            buf = H[shared_idx]
-            dist.all_reduce(buf)
-            H[shared_idx] = buf
-
-    def barrier():
+    def barrier(reps):
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            t = torch.tensor([reps], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            reps = int(t.item())
         torch.cuda.synchronize()
+        return reps
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = D.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = D.launch_count - l0
-
-    # ---- end-to-end arm: host buffers through the reference-facing call --------------------------------------------------
-    Fh, Jh, Hh = np.empty(nb * D.dyn), np.empty(nb * D.nnzJ), np.empty(nb * max(D.nnzH, 1))
-    for a in (Zh, muh, Fh, Jh, Hh):
-        qcknot.host_register(a)
-    e2e_steps = max(3, min(args.steps, 10))
-    D.eval_all(Zh, muh, Fh, Jh, Hh)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        D.eval_all(Zh, muh, Fh, Jh, Hh)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    ms, passes, launches = time_device(D, Z, mu, F, J, H, stream, args.steps, args.warmup, args.min_seconds, barrier)
     clocks = sampler.stop()
-    checksum = float(Fh.sum() + Jh[:: 997].sum() + Hh[:: 997].sum())
-
-    tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(tms[0]), float(tms[1])
-    total_evals_per_step = nb if ensemble else nb * n_gpus
-    value = total_evals_per_step * args.steps / (ms * 1e-3)
-    e2e_value = total_evals_per_step * e2e_steps / (e2e_ms * 1e-3)
+    ms = float(tms[0])
+    checksum = float(F.sum().item() + J[::997].sum().item() + H[::997].sum().item())
+    del Z, mu, F, J, H
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: ONE caller, host buffers, through the reference-facing call -----------------------------------------------
+    e2e = None
+    host = None
+    if rank == 0:
+        if n_gpus == 1:
+            De, nbe = D, nb
+            Ze = [Zh, Zh + 1e-7]
+            mue = [muh, wl.random_multipliers(nb * D.dyn, seed=99)]
+        else:
+            De = qcknot.QuantumDynamics(integrators, traj, device=0, n_gpus=n_gpus, shard_mode="knot")
+            nbe = De.n_blocks
+            Z0 = np.ascontiguousarray(traj.datavec[: traj.T * D.zdim])
+            Ze = [Z0, Z0 + 1e-7]
+            mue = [wl.random_multipliers(nbe * D.dyn, seed=1234), wl.random_multipliers(nbe * D.dyn, seed=99)]
+        Fh, Jh, Hh = np.empty(nbe * D.dyn), np.empty(nbe * D.nnzJ), np.empty(nbe * max(D.nnzH, 1))
+        e2e_s, e2e_steps, st = time_e2e(De, Ze, mue, Fh, Jh, Hh, args.min_seconds)
+        moved = st["h2d_bytes"] + st["d2h_bytes"]
+        written = Fh.nbytes + Jh.nbytes + Hh.nbytes
+        e2e = {"value": nbe / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(st["h2d_bytes"]),
+               "d2h_bytes_per_step": int(st["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_s * 1e3,
+               "caller": "one host thread calling qck_eval_all" + (f" on one handle with n_gpus={n_gpus} (knot-sharded)" if n_gpus > 1 else ""),
+               "inputs": "pageable numpy arrays, two alternating trajectories (no cache hits)",
+               "timing": "host wall clock around synchronous calls",
+               "pcie": {"bytes_per_step": int(moved), "achieved_gbs": moved / e2e_s * 1e-9, "links": n_gpus,
+                        "peak_gbs": PCIE_PEAK_GBS * n_gpus, "frac": moved / e2e_s * 1e-9 / (PCIE_PEAK_GBS * n_gpus),
+                        "full_layout_bytes": int(written + Ze[0].nbytes + mue[0].nbytes)}}
+        exp_gbs = expand_only_gbs(De, min(nbe, 9999))
+        host = {"written_bytes_per_step": int(written), "written_gbs": written / e2e_s * 1e-9, "expand_only_gbs": exp_gbs,
+                "frac_of_expand_only": written / e2e_s * 1e-9 / exp_gbs if exp_gbs else None, "threads": os.cpu_count(),
+                "note": "expand_only = the library's host threads writing the caller's arrays from the compact layout with no GPU "
+                        "involved: the ceiling of the e2e path on this host's memory system"}
+        checksum += float(Fh.sum() + Jh[::997].sum() + Hh[::997].sum())
+        if De is not D:
+            extra_multi = {}
+            try:
+                import ctypes
+                ver, nranks = De.nccl_version()
+                De.upload(Ze[0], mue[0])
+                for _ in range(2):
+                    De.eval_resident(7)
+                    De.gather_device(7)
+                De.synchronize()
+                t0 = time.perf_counter()
+                reps = 5
+                for _ in range(reps):
+                    De.eval_resident(7)
+                    De.gather_device(7)
+                De.synchronize()
+                dtg = (time.perf_counter() - t0) / reps
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    De.eval_resident(7)
+                De.synchronize()
+                dte = (time.perf_counter() - t0) / reps
+                per_gpu_bytes = written * (n_gpus - 1) / n_gpus
+                extra_multi = {"nccl_version": ver, "nccl_nranks": nranks, "eval_resident_ms": dte * 1e3,
+                               "eval_plus_allgather_ms": dtg * 1e3,
+                               "allgather_gbs_per_gpu_in": per_gpu_bytes / max(dtg - dte, 1e-9) * 1e-9,
+                               "note": "one caller: kernels on every GPU, then ncclBroadcast-grouped all-gather of the F/J/H segments "
+                                       "so that every GPU holds the assembled arrays"}
+            except Exception as ex:  # noqa: BLE001
+                extra_multi = {"error": str(ex)}
+            e2e["gather"] = extra_multi
+            De.close()
+    if host_group is not None:
+        dist.barrier(group=host_group)
+
+    extra = None
+    if rank == 0 and not args.no_extra:
+        try:
+            extra = extra_records(args, dev, stream, n_gpus, None)
+        except Exception as ex:  # noqa: BLE001
+            extra = {"error": str(ex)}
+    if host_group is not None:
+        dist.barrier(group=host_group)
 
     if rank == 0:
         bpe = algorithmic_bytes(D.zdim, D.dyn, D.nnzJ, D.nnzH)
-        kernel_s = ms * 1e-3 / args.steps
-        achieved = bpe * nb / kernel_s * 1e-9 / (n_gpus if ensemble else 1)  # per GPU
-        peak, peak_src = 6650.0, "fallback"
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
-        except Exception:
-            pass
+        kernel_s = ms * 1e-3
+        achieved = bpe * nb / kernel_s * 1e-9  # per GPU
+        peak, peak_src = hbm_peak()
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -304,36 +463,33 @@ def main():
         q = next(I for I in integrators if hasattr(I, "system"))
         nq = sum(1 for I in integrators if hasattr(I, "system"))
         fl = flops_per_eval(q.system.levels, q.system.n_drives, q.system.levels if q.unitary else 1) * nq
+        cfg = config_dict(args, n_gpus)
+        cfg_run = {"timed_passes": passes, "timed_seconds": ms * 1e-3 * passes}
         out = {
-            "metric": "knot-pt constraint+Jac+Hess evals/s", "value": value, "unit": "evals/s", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong" if ensemble else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, n_gpus), "seed": 1234, "evals_per_step": total_evals_per_step,
-                       "l2": "outputs per step exceed L2 (inputs+outputs larger than L2, no flush needed)"
-                       if bpe * nb > 2 * 126e6 else "working set fits L2; flush not applied"},
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(Zh.nbytes + muh.nbytes),
-                    "d2h_bytes_per_step": int(Fh.nbytes + Jh.nbytes + Hh.nbytes), "steps": e2e_steps,
-                    "timing": "host wall clock around synchronous qck_eval_all calls, max over ranks"},
+            "metric": METRIC, "value": nb * n_gpus / kernel_s, "unit": "evals/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg, "run": cfg_run,
+            "e2e": e2e, "host": host,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                         "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_eval": bpe, "kernel_us": kernel_s * 1e6,
                          "fp64": {"flops_per_eval": fl, "achieved_tflops": fl * nb / kernel_s * 1e-12,
                                   "peak_tflops": FP64_PEAK_TFLOPS,
                                   "frac": fl * nb / kernel_s * 1e-12 / FP64_PEAK_TFLOPS}},
             "checksum": checksum,
+            "extra": extra,
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args, None)
+            out["cpu_baseline"] = cpu_baseline(args)
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out))
-    for a in (Zh, muh, Fh, Jh, Hh):
-        qcknot.host_unregister(a)
     D.close()
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
 
 

@@ -184,6 +184,46 @@ int qck_expand_host(const qck_handle* h, int32_t arr, const double* compact, dou
 /* forget the staged inputs / device-resident results (e.g. after writing into the handle's device buffers directly) */
 int qck_invalidate(qck_handle* h);
 
+/* ---- objective and terminal-constraint terms on the device ----------------------------------
+ * The terms the problem templates add next to the dynamics, evaluated from the same device-resident Z as the dynamics (one
+ * upload serves every callback of an Ipopt iteration):
+ *   QCK_OBJ_QUADRATIC_REGULARIZER  QuadraticRegularizer(name, traj, R; timestep_name)   unitary_smooth_pulse_problem.jl:151-153
+ *                                  J = sum_t 1/2 weight * dt_t^2 * sum_i R_i v_ti^2
+ *   QCK_OBJ_UNITARY_INFIDELITY     UnitaryInfidelityObjective(state_name, traj, Q; subspace)   unitary_smooth_pulse_problem.jl:132-137
+ *                                  J = weight * (1 - |tr(U_goal' U_T)|^2 / n_sub^2) on the final knot
+ *   QCK_OBJ_MINIMUM_TIME           MinimumTimeObjective(traj; D)   unitary_minimum_time_problem.jl:67-69:  J = weight * sum_{t<T} dt_t
+ * and FinalUnitaryFidelityConstraint(state_name, val, traj)  (unitary_minimum_time_problem.jl:80-84): g = F(U_T) - val >= 0. */
+#define QCK_OBJ_QUADRATIC_REGULARIZER 0
+#define QCK_OBJ_UNITARY_INFIDELITY 1
+#define QCK_OBJ_MINIMUM_TIME 2
+typedef struct qck_objective_term {
+    int32_t kind;
+    int32_t comp_off;   /* component inside z_t: the regularised variable / the unitary's iso-vec (ignored for MINIMUM_TIME) */
+    int32_t comp_len;
+    int32_t levels;     /* infidelity: N (comp_len = 2 N^2) */
+    double weight;      /* Q / D / a factor on R */
+    const double* R;    /* regularizer: comp_len weights, NULL = ones */
+    const double* goal; /* infidelity: iso-vec of the goal operator (zeros outside the subspace of an EmbeddedOperator) */
+    int32_t n_sub;      /* infidelity: dimension of the subspace the fidelity is normalised with; 0 = levels */
+    int32_t reserved;
+} qck_objective_term;
+/* J = sum of the terms.  Works on single-GPU and knot-sharded multi-GPU handles (per-GPU partial sums, added in GPU order). */
+int qck_objective_attach(qck_handle* h, const qck_objective_term* terms, int32_t n_terms);
+/* n_vars = T * zdim (gradient length); nnz_hess values in the structure below */
+int qck_objective_sizes(const qck_handle* h, int64_t* n_vars, int64_t* nnz_hess);
+/* 1-based (row <= col), knot-major: for every knot the regularizers' [v_i x v_i | v_i x dt | dt x dt] entries in term order,
+ * then the infidelity terms' dense upper triangles (by column) on the final knot; duplicates are summed by the consumer */
+int qck_objective_hessian_structure(const qck_handle* h, int64_t* rows, int64_t* cols);
+int qck_eval_objective(qck_handle* h, const double* Z, double* value);
+int qck_eval_objective_gradient(qck_handle* h, const double* Z, double* grad);
+int qck_eval_objective_hessian(qck_handle* h, const double* Z, double sigma, double* vals);
+/* terminal fidelity constraint (term->kind = QCK_OBJ_UNITARY_INFIDELITY describes state component, goal, subspace).
+ * qck_eval_fidelity_constraint: g (may be NULL), its Jacobian row over the final knot's state component (comp_len values,
+ * 1-based columns (T-1)*zdim + comp_off + 1 ..., may be NULL) and mu * the upper triangle (by column) of its Hessian
+ * (comp_len (comp_len + 1) / 2 values, may be NULL). */
+int qck_fidelity_constraint_attach(qck_handle* h, const qck_objective_term* term, double min_fidelity);
+int qck_eval_fidelity_constraint(qck_handle* h, const double* Z, double mu, double* g, double* jac, double* hess);
+
 /* kernels launched on this handle since creation (bench.py's gpu_launches) */
 int qck_launch_count(const qck_handle* h, int64_t* launches);
 /* version string of the library */

@@ -35,3 +35,16 @@ def rel_err(a, b) -> float:
     """max |a-b| relative to max(1, max|b|): the 1e-10 criterion of BASELINE.json's north_star."""
     a, b = np.asarray(a), np.asarray(b)
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if a.size else 0.0
+
+
+def entry_err(a, b, floor: float = 1e-6) -> float:
+    """Per-entry relative error, max_i |a_i - b_i| / max(|b_i|, floor * max|b|): a bad small-magnitude term inside a large
+    array shows up here even when rel_err (relative to the largest entry) hides it.  The absolute floor keeps entries that
+    are rounding noise next to their neighbours (cancellation of O(max|b|) terms) from dominating."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if not a.size:
+        return 0.0
+    scale = float(np.max(np.abs(b)))
+    if scale == 0.0:
+        return float(np.max(np.abs(a)))
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor * scale)))

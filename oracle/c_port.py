@@ -56,21 +56,27 @@ class CPort:
         self.Hr = np.array([r for r, _ in dyn.hess_knot], dtype=np.int32)
         self.Hc = np.array([c for _, c in dyn.hess_knot], dtype=np.int32)
         self.dt_off = L.components[L.dt_name][0] if L.dt_name else -1
-        self.lib.ko_eval.restype = C.c_int
+        self.lib.ko_eval2.restype = C.c_int
 
-    def eval(self, Z, mu=None, want=("F", "J", "H"), nthreads: int = 0, T=None):
+    def eval(self, Z, mu=None, want=("F", "J", "H"), nthreads: int = 0, T=None, tuned: bool = False, out=None):
+        """tuned: constant anticommutators hoisted out of the knot loop and G_j G + G G_j reused (see knot_oracle.c);
+        out = (F, J, H) preallocated arrays (a timed loop must not pay for page faults of fresh arrays)."""
         d = self.dyn
         T = d.T if T is None else T
         nb = T - 1
         Z = np.ascontiguousarray(Z, dtype=np.float64)
-        F = np.empty(nb * d.dyn) if "F" in want else None
-        J = np.empty(nb * d.nnzJ) if "J" in want else None
-        H = np.empty(nb * d.nnzH) if ("H" in want and d.eval_hessian) else None
+        if out is not None:
+            F, J, H = out
+        else:
+            F = np.empty(nb * d.dyn) if "F" in want else None
+            J = np.empty(nb * d.nnzJ) if "J" in want else None
+            H = np.empty(nb * d.nnzH) if ("H" in want and d.eval_hessian) else None
         mu = np.ascontiguousarray(mu, dtype=np.float64) if mu is not None else None
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-        rc = self.lib.ko_eval(C.c_int(len(d.integrators)), self.arr, C.c_long(T), C.c_int(d.zdim), C.c_int(self.dt_off),
-                              C.c_double(d.layout.dt_fixed), p(Z), p(mu), C.c_int(d.dyn), C.c_long(d.nnzJ), p(self.Jr),
-                              p(self.Jc), C.c_long(d.nnzH), p(self.Hr), p(self.Hc), p(F), p(J), p(H), C.c_int(nthreads))
+        rc = self.lib.ko_eval2(C.c_int(len(d.integrators)), self.arr, C.c_long(T), C.c_int(d.zdim), C.c_int(self.dt_off),
+                               C.c_double(d.layout.dt_fixed), p(Z), p(mu), C.c_int(d.dyn), C.c_long(d.nnzJ), p(self.Jr),
+                               p(self.Jc), C.c_long(d.nnzH), p(self.Hr), p(self.Hc), p(F), p(J), p(H), C.c_int(nthreads),
+                               C.c_int(1 if tuned else 0))
         if rc != 0:
             raise MemoryError("ko_eval failed")
         return F, J, H

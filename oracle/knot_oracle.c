@@ -14,6 +14,11 @@
  *   - a threaded loop over knots t = 1..T-1 that fills a per-knot dense block and copies its structural entries
  *     one by one into the flat value vector in structure order              (SURVEY 8a6, 3.2 steps 3-5;
  *     surface at /root/reference/test/scripts/integrator_test_1qubit.jl:45-52)
+ *
+ * Two timings of the same arithmetic (bench.py reports both, the speed-up ratios use the faster one):
+ *   literal (tuned = 0)  every product is formed where the formula names it, per knot
+ *   tuned   (tuned = 1)  what SURVEY 8a2 says the reference does: the constant anticommutators {G_i, G_j} are computed ONCE
+ *                        per call, and G_j G + G G_j is formed once per knot and reused by the Jacobian and the Hessian terms
  */
 #include <math.h>
 #include <stdlib.h>
@@ -60,6 +65,7 @@ typedef struct {
     int n_integ; const ko_integ* integ; long T; int zdim, dt_off; double dt_fixed; const double* Z; const double* mu;
     int dyn; long nnzJ; const int *Jr, *Jc; long nnzH; const int *Hr, *Hc; double *F, *J, *H;
     int maxn2, maxnd; long t_begin, t_end; int failed;
+    int tuned; const double* const* AC; /* tuned: per integrator, the anticommutators {G_i, G_j}, pairs (j, i <= j) */
 } ko_job;
 
 /* one host thread: knot blocks [t_begin, t_end)  (the reference's Threads.@threads loop body) */
@@ -77,12 +83,14 @@ static void* ko_worker(void* arg) {
         /* per-thread scratch: dense per-knot blocks + small matrices */
         double* Jb = J ? (double*)calloc(jb, sizeof(double)) : NULL;
         double* Hb = H ? (double*)calloc(hb, sizeof(double)) : NULL;
-        double* w = (double*)malloc(sizeof(double) * (size_t)mm * (8 + 2 * maxnd + 4));
+        const int tuned = jb_->tuned;
+        double* w = (double*)malloc(sizeof(double) * (size_t)mm * (8 + 3 * maxnd + 4));
         if ((J && !Jb) || (H && !Hb) || !w) failed = 1;
         if (!failed) {
         double *G = w, *G2 = G + mm, *Fm = G2 + mm, *Bm = Fm + mm, *F1 = Bm + mm, *B1 = F1 + mm, *tmp = B1 + mm,
                *tmp2 = tmp + mm, *dFj = tmp2 + mm /* maxnd */, *dBj = dFj + (size_t)mm * maxnd /* maxnd */,
-               *v1 = dBj + (size_t)mm * maxnd, *v2 = v1 + mm, *v3 = v2 + mm, *v4 = v3 + mm;
+               *v1 = dBj + (size_t)mm * maxnd, *v2 = v1 + mm, *v3 = v2 + mm, *v4 = v3 + mm,
+               *CG = v4 + mm /* maxnd: G_j G + G G_j of this knot (tuned) */;
         for (long t = jb_->t_begin; t < jb_->t_end; ++t) {
             const double* zt = Z + t * zdim;
             const double* zt1 = zt + zdim;
@@ -145,11 +153,12 @@ static void* ko_worker(void* arg) {
                 /* dF_j = dt/2 G_j + dt^2/12 (G_j G + G G_j) */
                 for (int j = 0; j < nd; ++j) {
                     const double* Gj = I->G_drives + (size_t)nn * j;
-                    gemm(0, n2, n2, n2, 1.0, Gj, n2, G, n2, 0.0, tmp, n2);
-                    gemm(0, n2, n2, n2, 1.0, G, n2, Gj, n2, 1.0, tmp, n2);
+                    double* cg = tuned ? CG + (size_t)nn * j : tmp;
+                    gemm(0, n2, n2, n2, 1.0, Gj, n2, G, n2, 0.0, cg, n2);
+                    gemm(0, n2, n2, n2, 1.0, G, n2, Gj, n2, 1.0, cg, n2);
                     for (int e = 0; e < nn; ++e) {
-                        dFj[(size_t)nn * j + e] = 0.5 * dt * Gj[e] + dt * dt / 12.0 * tmp[e];
-                        dBj[(size_t)nn * j + e] = -0.5 * dt * Gj[e] + dt * dt / 12.0 * tmp[e];
+                        dFj[(size_t)nn * j + e] = 0.5 * dt * Gj[e] + dt * dt / 12.0 * cg[e];
+                        dBj[(size_t)nn * j + e] = -0.5 * dt * Gj[e] + dt * dt / 12.0 * cg[e];
                     }
                 }
                 if (J) {
@@ -184,15 +193,22 @@ static void* ko_worker(void* arg) {
                         for (int i2 = 0; i2 <= j; ++i2) { /* {G_i, G_j} (W1 - W0), weight dt^2/12 */
                             const double* Gi = I->G_drives + (size_t)nn * i2;
                             const double* Gj = I->G_drives + (size_t)nn * j;
-                            gemm(0, n2, n2, n2, 1.0, Gi, n2, Gj, n2, 0.0, tmp, n2);
-                            gemm(0, n2, n2, n2, 1.0, Gj, n2, Gi, n2, 1.0, tmp, n2);
-                            gemm(0, n2, nc, n2, dt * dt / 12.0, tmp, n2, v4, n2, 0.0, v2, n2);
+                            const double* ac = tmp;
+                            if (tuned) ac = jb_->AC[q] + (size_t)nn * (j * (j + 1) / 2 + i2);
+                            else {
+                                gemm(0, n2, n2, n2, 1.0, Gi, n2, Gj, n2, 0.0, tmp, n2);
+                                gemm(0, n2, n2, n2, 1.0, Gj, n2, Gi, n2, 1.0, tmp, n2);
+                            }
+                            gemm(0, n2, nc, n2, dt * dt / 12.0, ac, n2, v4, n2, 0.0, v2, n2);
                             Hb[co + i2 + (size_t)ld * (co + j)] += dot(Mu, v2, dim);
                         }
                         if (free_time) { /* d/ddt of dB_j W1 - dF_j W0 */
                             const double* Gj = I->G_drives + (size_t)nn * j;
-                            gemm(0, n2, n2, n2, 1.0, Gj, n2, G, n2, 0.0, tmp, n2);
-                            gemm(0, n2, n2, n2, 1.0, G, n2, Gj, n2, 1.0, tmp, n2);
+                            if (tuned) memcpy(tmp, CG + (size_t)nn * j, sizeof(double) * nn);
+                            else {
+                                gemm(0, n2, n2, n2, 1.0, Gj, n2, G, n2, 0.0, tmp, n2);
+                                gemm(0, n2, n2, n2, 1.0, G, n2, Gj, n2, 1.0, tmp, n2);
+                            }
                             for (int e = 0; e < nn; ++e) { tmp2[e] = 0.5 * Gj[e] + dt / 6.0 * tmp[e]; tmp[e] = -0.5 * Gj[e] + dt / 6.0 * tmp[e]; }
                             gemm(0, n2, nc, n2, 1.0, tmp, n2, W1, n2, 0.0, v2, n2);
                             gemm(0, n2, nc, n2, -1.0, tmp2, n2, W0, n2, 1.0, v2, n2);
@@ -226,10 +242,10 @@ static void* ko_worker(void* arg) {
 
 /* evaluates every integrator on knot blocks [0, T-1); F/J/H may be NULL.  Jr/Jc/Hr/Hc: per-knot structure
  * (0-based row, col inside the dyn x 2zdim / 2zdim x 2zdim block).  nthreads <= 0: all online cores.
- * Returns 0, or -1 on allocation failure. */
-int ko_eval(int n_integ, const ko_integ* integ, long T, int zdim, int dt_off, double dt_fixed, const double* Z,
-            const double* mu, int dyn, long nnzJ, const int* Jr, const int* Jc, long nnzH, const int* Hr,
-            const int* Hc, double* F, double* J, double* H, int nthreads) {
+ * tuned: see the header.  Returns 0, or -1 on allocation failure. */
+int ko_eval2(int n_integ, const ko_integ* integ, long T, int zdim, int dt_off, double dt_fixed, const double* Z,
+             const double* mu, int dyn, long nnzJ, const int* Jr, const int* Jc, long nnzH, const int* Hr,
+             const int* Hc, double* F, double* J, double* H, int nthreads, int tuned) {
     int maxn2 = 2, maxnd = 1;
     for (int q = 0; q < n_integ; ++q)
         if (integ[q].kind != KO_DERIVATIVE) {
@@ -241,18 +257,48 @@ int ko_eval(int n_integ, const ko_integ* integ, long T, int zdim, int dt_off, do
     if (nthreads > 256) nthreads = 256;
     long nb = T - 1;
     if (nthreads > nb) nthreads = nb > 0 ? (int)nb : 1;
+    /* tuned: the constant anticommutators, once per call */
+    double** AC = NULL;
+    if (tuned && H) {
+        AC = (double**)calloc((size_t)n_integ, sizeof(double*));
+        if (!AC) return -1;
+        for (int q = 0; q < n_integ; ++q) {
+            if (integ[q].kind == KO_DERIVATIVE) continue;
+            const int n2 = 2 * integ[q].N, nn = n2 * n2, nd = integ[q].n_drives;
+            AC[q] = (double*)malloc(sizeof(double) * (size_t)nn * (nd * (nd + 1) / 2));
+            if (!AC[q]) return -1;
+            for (int j = 0; j < nd; ++j)
+                for (int i2 = 0; i2 <= j; ++i2) {
+                    double* ac = AC[q] + (size_t)nn * (j * (j + 1) / 2 + i2);
+                    const double* Gi = integ[q].G_drives + (size_t)nn * i2;
+                    const double* Gj = integ[q].G_drives + (size_t)nn * j;
+                    gemm(0, n2, n2, n2, 1.0, Gi, n2, Gj, n2, 0.0, ac, n2);
+                    gemm(0, n2, n2, n2, 1.0, Gj, n2, Gi, n2, 1.0, ac, n2);
+                }
+        }
+    }
     ko_job jobs[256];
     pthread_t tid[256];
     for (int i = 0; i < nthreads; ++i) {
         ko_job j = {n_integ, integ, T, zdim, dt_off, dt_fixed, Z, mu, dyn, nnzJ, Jr, Jc, nnzH, Hr, Hc, F, J, H,
-                    maxn2, maxnd, nb * i / nthreads, nb * (i + 1) / nthreads, 0};
+                    maxn2, maxnd, nb * i / nthreads, nb * (i + 1) / nthreads, 0, tuned && AC, (const double* const*)AC};
         jobs[i] = j;
     }
     for (int i = 1; i < nthreads; ++i) pthread_create(&tid[i], NULL, ko_worker, &jobs[i]);
     ko_worker(&jobs[0]);
     int failed = jobs[0].failed;
     for (int i = 1; i < nthreads; ++i) { pthread_join(tid[i], NULL); failed |= jobs[i].failed; }
+    if (AC) {
+        for (int q = 0; q < n_integ; ++q) free(AC[q]);
+        free(AC);
+    }
     return failed ? -1 : 0;
+}
+
+int ko_eval(int n_integ, const ko_integ* integ, long T, int zdim, int dt_off, double dt_fixed, const double* Z,
+            const double* mu, int dyn, long nnzJ, const int* Jr, const int* Jc, long nnzH, const int* Hr,
+            const int* Hc, double* F, double* J, double* H, int nthreads) {
+    return ko_eval2(n_integ, integ, T, zdim, dt_off, dt_fixed, Z, mu, dyn, nnzJ, Jr, Jc, nnzH, Hr, Hc, F, J, H, nthreads, 0);
 }
 
 int ko_num_cores(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }

@@ -13,6 +13,13 @@ from .integrators import (  # noqa: F401
     UnitaryExponentialIntegrator,
     UnitaryPadeIntegrator,
 )
+from .objectives import (  # noqa: F401
+    FinalUnitaryFidelityConstraint,
+    MinimumTimeObjective,
+    Objective,
+    QuadraticRegularizer,
+    UnitaryInfidelityObjective,
+)
 from .isomorphisms import iso_to_ket, iso_vec_to_operator, ket_to_iso, operator_to_iso_vec  # noqa: F401
 from .quantum_system import QuantumSystem  # noqa: F401
 from .trajectory import NamedTrajectory  # noqa: F401

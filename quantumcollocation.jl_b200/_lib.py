@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("QCK_LIB") or os.path.join(HERE, "libqcknot.so")  # QC
 QCK_UNITARY_PADE, QCK_UNITARY_EXP, QCK_KET_PADE, QCK_KET_EXP, QCK_DERIVATIVE = range(5)
 QCK_EVAL_F, QCK_EVAL_J, QCK_EVAL_H = 1, 2, 4
 QCK_SHARD_KNOT, QCK_SHARD_ENSEMBLE = 0, 1
+QCK_OBJ_QUADRATIC_REGULARIZER, QCK_OBJ_UNITARY_INFIDELITY, QCK_OBJ_MINIMUM_TIME = 0, 1, 2
 
 EXPORTS = [
     "qck_create", "qck_destroy", "qck_last_error", "qck_sizes", "qck_jacobian_structure", "qck_hessian_structure",
@@ -19,6 +20,9 @@ EXPORTS = [
     "qck_shard_count", "qck_shard_info", "qck_shard_device_buffers", "qck_upload", "qck_eval_resident",
     "qck_gather_device", "qck_gathered_buffers", "qck_nccl_version", "qck_transfer_stats", "qck_invalidate",
     "qck_compact_map", "qck_expand_host",
+    "qck_objective_attach", "qck_objective_sizes", "qck_objective_hessian_structure", "qck_eval_objective",
+    "qck_eval_objective_gradient", "qck_eval_objective_hessian", "qck_fidelity_constraint_attach",
+    "qck_eval_fidelity_constraint",
 ]
 
 
@@ -37,6 +41,14 @@ class ProblemDesc(C.Structure):
         ("integ_begin", C.c_int32), ("integ_end", C.c_int32), ("n_gpus", C.c_int32),
         ("integrators", C.POINTER(IntegratorDesc)),
         ("shard_mode", C.c_int32), ("host_threads", C.c_int32), ("devices", C.POINTER(C.c_int32)),
+    ]
+
+
+class ObjectiveTerm(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("comp_off", C.c_int32), ("comp_len", C.c_int32), ("levels", C.c_int32),
+        ("weight", C.c_double), ("R", C.POINTER(C.c_double)), ("goal", C.POINTER(C.c_double)),
+        ("n_sub", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -86,6 +98,14 @@ def load() -> C.CDLL:
     lib.qck_nccl_version.argtypes = [vp, i32p, i32p]
     lib.qck_transfer_stats.argtypes = [vp, i64p, i64p, i64p]
     lib.qck_invalidate.argtypes = [vp]
+    lib.qck_objective_attach.argtypes = [vp, C.POINTER(ObjectiveTerm), C.c_int32]
+    lib.qck_objective_sizes.argtypes = [vp, i64p, i64p]
+    lib.qck_objective_hessian_structure.argtypes = [vp, vp, vp]
+    lib.qck_eval_objective.argtypes = [vp, vp, dp]
+    lib.qck_eval_objective_gradient.argtypes = [vp, vp, vp]
+    lib.qck_eval_objective_hessian.argtypes = [vp, vp, C.c_double, vp]
+    lib.qck_fidelity_constraint_attach.argtypes = [vp, C.POINTER(ObjectiveTerm), C.c_double]
+    lib.qck_eval_fidelity_constraint.argtypes = [vp, vp, C.c_double, dp, vp, vp]
     lib.qck_compact_map.argtypes = [vp, C.c_int32, i64p, vp]
     lib.qck_expand_host.argtypes = [vp, C.c_int32, vp, vp, C.c_int64]
     _lib = lib

@@ -9,8 +9,13 @@ import subprocess
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/qck_kernels.cu", "csrc/qck_rowslice.cu", "csrc/qck_rs3.cu", "csrc/qck_column.cu", "csrc/qck_pack.cu",
-           "csrc/qck_host.cpp", "csrc/qck_pipe.cpp", "csrc/qck_multi.cpp"]
+# (source, extra flags, object tag): the rs3 kernel file is compiled once per drive count, in parallel
+UNITS = [("csrc/qck_kernels.cu", [], ""), ("csrc/qck_rowslice.cu", [], ""), ("csrc/qck_column.cu", [], ""), ("csrc/qck_pack.cu", [], ""),
+         ("csrc/qck_objective.cu", [], ""),
+         ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=1"], ".nd1"), ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=2"], ".nd2"),
+         ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=3"], ".nd3"), ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=4"], ".nd4"),
+         ("csrc/qck_host.cpp", [], ""), ("csrc/qck_pipe.cpp", [], ""), ("csrc/qck_multi.cpp", [], "")]
+SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["csrc/qck_internal.h", "csrc/qck_handle.h", "csrc/qck_device.cuh", "../include/qcknot.h"]
 LIB = os.path.join(HERE, "libqcknot.so")
 OBJDIR = os.path.join(HERE, "build")
@@ -22,11 +27,11 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    return SOURCES
 
 
-def _obj(src: str) -> str:
-    return os.path.join(OBJDIR, os.path.basename(src) + ".o")
+def _obj(unit) -> str:
+    return os.path.join(OBJDIR, os.path.basename(unit[0]) + unit[2] + ".o")
 
 
 def _stale(target: str, deps) -> bool:
@@ -45,14 +50,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJDIR, exist_ok=True)
-    srcs = _sources()
-    todo = [s for s in srcs if force or _stale(_obj(s), [s] + HEADERS)]
+    todo = [u for u in UNITS if force or _stale(_obj(u), [u[0]] + HEADERS)]
 
-    def compile_one(src):
-        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", _obj(src), src]
+    def compile_one(unit):
+        cmd = [nvcc, *NVCC_FLAGS, *unit[1], "-c", "-o", _obj(unit), unit[0]]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
-        return src, subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+        return unit[0] + unit[2], subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as ex:
         for src, res in ex.map(compile_one, todo):
@@ -61,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 print(f"== {src}\n" + res.stdout + res.stderr)
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB,
-            *[_obj(s) for s in srcs], "-ldl", "-lpthread"]
+            *[_obj(u) for u in UNITS], "-ldl", "-lpthread"]
     res = subprocess.run(link, cwd=HERE, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

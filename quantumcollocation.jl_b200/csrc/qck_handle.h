@@ -142,13 +142,20 @@ struct qck_handle {
     // positions of F / J / H this handle writes (everything for an unsharded handle), kron blocks marked
     std::vector<QckOwnSeg> own[3];
     bool exclude_shared = false;  // child of an ensemble-sharded handle: shared Hessian entries travel separately
+    bool skip_local_reduce = false;  // (set around a launch) the parent sums the partial columns of all GPUs itself
     int host_threads = 0;
     QckPipe pipe;
+    void* objective = nullptr;    // QckObjective* (qck_objective.cu): objective / terminal-constraint terms attached to this handle
+    int con_off = 0, con_len = 0;
     // multi-GPU parent (n_gpus > 1): structure-only itself, the children do the work
     std::vector<qck_handle*> children;
     std::vector<long long> child_t0;   // KNOT: first block of every child (+ end sentinel)
     int shard_mode = QCK_SHARD_KNOT;
     void* nccl = nullptr;              // QckNccl*, created on first use
+    // ENSEMBLE, device-resident: all-reduce by all-read over peer memory
+    bool peer_ready = false, peer_ok = false;
+    std::vector<QckPeerReduce> peer;   // per child (tables on that child's device)
+    std::vector<cudaEvent_t> ev_kernel, ev_reduce;  // per child: partial columns written / read by everybody
     std::vector<double*> gF, gJ, gH;   // per child: gathered (full) value arrays, allocated by qck_gather_device
 };
 
@@ -162,6 +169,8 @@ int qck_check_status(qck_handle* h);  // after a synchronisation: turns device-s
 int qck_create_single(const qck_problem_desc* d, qck_handle** out, bool exclude_shared);
 // qck_pipe.cpp
 int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, double* J, double* H);
+int qck_pipe_ensure_z(qck_handle* h, const double* Z);  // Z staged + on the device (uploaded on h->stream unless it is already there)
+void qck_objective_free(qck_handle* h);                 // qck_objective.cu
 void qck_pipe_destroy(qck_handle* h);
 void qck_stream_copy(double* dst, const double* src, size_t n);  // non-temporal stores
 // qck_multi.cpp

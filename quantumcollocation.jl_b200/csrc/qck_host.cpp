@@ -77,8 +77,10 @@ struct MapEnt {
 // their own contiguous image range, allocated in destination order so that destination-adjacent groups are also
 // image-adjacent (they merge into one segment); groups with a common stride > 1 that interleave share one range.
 struct Run { int dst, len, img, period; };
+// parity: every run gets an image offset of the same parity as its destination (rs3 kernel: the write-out of a run is then
+// [scalar head] + 16-byte aligned bulk copy + [scalar tail] whatever the parity of the knot block's base address).
 bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* base, short* stride, std::vector<Run>& segs,
-                 std::string& why, int* dst0 = nullptr) {
+                 std::string& why, int* dst0 = nullptr, bool parity = false) {
     if (e.empty()) return true;
     struct Group { int qid; long long d0; int s, n, period; };
     std::map<int, std::vector<MapEnt>> by_q;
@@ -103,7 +105,7 @@ bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* bas
         if (g.s == 1) {
             const bool periodic = g.period > 0 && g.period < g.n;
             const bool glue = !periodic && run_end == g.d0 && ((g.d0 < split) == (g.d0 - 1 < split));
-            b = glue ? cursor : ((cursor + 1) & ~1);
+            b = glue ? cursor : (parity ? cursor + (int)((cursor ^ g.d0) & 1) : ((cursor + 1) & ~1));
             cursor = b + (periodic ? g.period : g.n);
             run_end = periodic ? -2 : g.d0 + g.n;
         } else {
@@ -111,7 +113,7 @@ bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* bas
             for (auto& f : fams)
                 if (f.s == g.s && g.d0 >= f.d0 && g.d0 < f.d0 + f.s) b = f.base + (int)(g.d0 - f.d0);
             if (b < 0) {
-                b = (cursor + 1) & ~1;
+                b = parity ? cursor + (int)((cursor ^ g.d0) & 1) : ((cursor + 1) & ~1);
                 fams.push_back({g.d0, g.s, b});
                 cursor = b + g.n * g.s;
             }
@@ -138,7 +140,8 @@ bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* bas
                 ++k2;
             segs.push_back(Run{(int)e[k].dst, (int)(k2 - k), img_of(e[k]), (int)(k2 - k)});
         }
-        if (segs.back().img & 1) { why = "internal: odd segment image offset"; return false; }
+        if (!parity && (segs.back().img & 1)) { why = "internal: odd segment image offset"; return false; }
+        if (parity && ((segs.back().img ^ segs.back().dst) & 1)) { why = "internal: image / destination parity mismatch"; return false; }
         k = k2;
     }
     return true;
@@ -186,6 +189,50 @@ std::vector<QckSeg> balance_units(const std::vector<Run> (&runs)[3], int nwarps,
     }
     for (int w = nwarps; w < QCK_SEG_HDR; ++w) hdr[w] = (int)out.size();
     for (auto& sgm : out) sgm.arr |= (32 % std::max(sgm.n / 2, 1)) << 8;
+    return out;
+}
+
+// rs3 kernel: units of the F + J part (phase 1) and of the Hessian part (phase 2), each balanced over the knot's three warps;
+// hdr = [phase 1: first unit of warp 0, 1, 2, end | phase 2: likewise].  One lane issues one unit, so units are kept small
+// enough that all lanes of the three warps take part: kron blocks go two repetitions per unit, plain runs <= 512 doubles.
+std::vector<QckSeg> rs3_units(const std::vector<Run> (&runs)[3], long long nnzH, int* hdr /* QCK_SEG_HDR */, std::string& why) {
+    std::vector<QckSeg> out;
+    for (int phase = 0; phase < 2; ++phase) {
+        struct Unit { QckSeg s; long long cost; };
+        std::vector<Unit> units;
+        for (int arr = phase == 0 ? 0 : 2; arr < (phase == 0 ? 2 : 3); ++arr)
+            for (auto& r : runs[arr]) {
+                if (arr == 2 && r.dst >= nnzH) { why = "shared Hessian entries (partial columns) are not supported by the rs3 kernel"; return {}; }
+                if (r.period < r.len) {
+                    const int nrep = r.len / r.period;
+                    for (int r0 = 0; r0 < nrep; r0 += 2) {
+                        const int k = std::min(2, nrep - r0);
+                        units.push_back({{r.dst + r0 * r.period, r.period, r.img | (k << 16), arr}, (long long)k * r.period});
+                    }
+                } else {
+                    for (int o = 0; o < r.len; o += 512) {
+                        const int k = std::min(512, r.len - o);
+                        units.push_back({{r.dst + o, k, (r.img + o) | (1 << 16), arr}, (long long)k});
+                    }
+                }
+            }
+        std::vector<size_t> order(units.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return units[a].cost > units[b].cost; });
+        long long load[3] = {0, 0, 0};
+        std::vector<size_t> mine[3];
+        for (size_t i : order) {
+            const int w = (int)(std::min_element(load, load + 3) - load);
+            load[w] += units[i].cost + 64;
+            mine[w].push_back(i);
+        }
+        for (int w = 0; w < 3; ++w) {
+            hdr[4 * phase + w] = (int)out.size();
+            for (size_t i : mine[w]) out.push_back(units[i].s);
+        }
+        hdr[4 * phase + 3] = (int)out.size();
+    }
+    for (int w = 8; w < QCK_SEG_HDR; ++w) hdr[w] = (int)out.size();
     return out;
 }
 
@@ -348,6 +395,10 @@ int build(qck_handle* h) {
         c.n_tbuf = C.member_end - C.member_begin > 1 ? 2 : 1;
         c.threads = qck_pick_threads(c);
         const int nwarps = c.threads / 32;
+        // three-warps-per-knot kernel: 9-level Pade-4 unitaries, one active member, nothing shared with other integrators
+        static const int rs3_knob = getenv("QCK_RS3") ? atoi(getenv("QCK_RS3")) : 7;  // knots per CTA (5..8), 0 = off
+        c.rs3 = (rs3_knob >= 5 && rs3_knob <= 8 && c.kind == QCK_UNITARY_PADE && c.order == 4 && c.N == 9 && c.nd >= 1 && c.nd <= 4 &&
+                 C.member_end - C.member_begin == 1 && h->npart == 0) ? rs3_knob : 0;
         for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
         std::vector<int> qdst((size_t)nm * QO_COUNT, -1);  // per member: first destination of every output quantity
         {
@@ -364,17 +415,25 @@ int build(qck_handle* h) {
                 for (int i = 0; i < I.dim; ++i) mf.push_back({(long long)I.row_off + i, QO_R, i, 0});
                 int cursor = 0;
                 std::string why;
-                if (!place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why, d0) ||
-                    !place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why, d0) ||
-                    !place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why, d0))
-                    return fail(h, QCK_EINVAL, "unsupported trajectory layout: %s", why.c_str());
+                const bool par = c.rs3 != 0;
+                bool ok = place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why, d0, par);
+                if (par) cursor += 2;  // (the image of every array may be shifted by one double on its own)
+                ok = ok && place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why, d0, par);
+                if (par) cursor = (cursor + 3) & ~1;
+                ok = ok && place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why, d0, par);
+                if (!ok) return fail(h, QCK_EINVAL, "unsupported trajectory layout: %s", why.c_str());
                 for (int arr = 0; arr < 3; ++arr)
                     for (auto& r : runs[arr]) {
                         if (arr == 2 && r.dst >= h->nnzH) continue;  // partial column: the reduce kernel writes the shared position
                         if (r.period < r.len) h->own[arr].push_back({r.dst, 0, r.period, r.len / r.period});
                         else h->own[arr].push_back({r.dst, 0, r.len, 1});
                     }
-                per_member[m2] = balance_units(runs, nwarps, hdrs[m2].data());
+                if (c.rs3) {
+                    per_member[m2] = rs3_units(runs, h->nnzH, hdrs[m2].data(), why);
+                    if (per_member[m2].empty()) return fail(h, QCK_EINVAL, "rs3 unit table: %s", why.c_str());
+                } else {
+                    per_member[m2] = balance_units(runs, nwarps, hdrs[m2].data());
+                }
                 if (first) {
                     memcpy(c.pl_base, base, sizeof base); memcpy(c.pl_stride, stride, sizeof stride);
                     c.img_doubles = cursor; c.nseg = (int)per_member[m2].size();
@@ -455,7 +514,12 @@ int build(qck_handle* h) {
         }
         c.ac_cap = ac_cap;
         qck_smem_finalize(c);
-        if ((size_t)c.sm_bytes > 227 * 1024 - 4096)
+        if (c.rs3) {  // as many knots per CTA as the shared memory holds
+            const int hoff = qck_rs3_hoff(c);
+            while (c.rs3 >= 5 && qck_rs3_smem(c, hoff, c.rs3) > 227 * 1024) --c.rs3;
+            if (c.rs3 < 5) return fail(h, QCK_EINVAL, "rs3 kernel: the tables of this problem leave no room for five knots per CTA");
+        }
+        if (!c.rs3 && (size_t)c.sm_bytes > 227 * 1024 - 4096)
             return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024 - 4096);
         c.cmat_stride = N * N + c.ell_stride + kk_cap + ac_cap;
         std::vector<double2> cmat((size_t)nm * c.cmat_stride, make_double2(0.0, 0.0));
@@ -643,7 +707,7 @@ int qck_run(qck_handle* h, uint32_t mask, long long k0, long long nk, const doub
         int rc = qck_launch_aux(L, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "aux kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }
-    if ((mask & QCK_EVAL_H) && h->red.n_shared && h->npart > 0) {
+    if ((mask & QCK_EVAL_H) && h->red.n_shared && h->npart > 0 && !h->skip_local_reduce) {
         int rc = qck_launch_reduce(h->red, L.H, L.partial, nk, h->nnzH, h->npart, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "reduce kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }
@@ -801,6 +865,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
 void qck_destroy(qck_handle* h) {
     if (!h) return;
     if (!h->children.empty() || h->nccl) qck_multi_destroy(h);
+    qck_objective_free(h);
     if (h->device < 0) { delete h; return; }
     cudaSetDevice(h->device);
     qck_pipe_destroy(h);

@@ -8,6 +8,7 @@
 
 #define QCK_TILE 3          // register tile edge of the small complex products (3x3 complex per thread)
 #define QCK_MAX_DRIVES 6
+#define QCK_MAX_OBJ_TERMS 12
 #define QCK_MAX_PADE_M 5    // Pade order <= 10
 enum { QK_PADE4 = 0, QK_EXP = 1, QK_PADEN = 2 };  // kernel families
 
@@ -64,6 +65,8 @@ struct QckClassDev {
     int kind, N, NP, nc, ncp, nd, order, W;
     int free_time, dt_off, zdim, dyn;
     int antiherm;  // every member's Hamiltonians are Hermitian: A(a) = -i H(a) is anti-Hermitian
+    int rs3;       // > 0: built for the three-warps-per-knot kernel (qck_rs3.cu) with this many knots per CTA: parity-matched
+                   // image placement, unit table [phase][warp] (see qck_host.cpp)
     double dt_fixed;
     int n_members;
     // scratch (offsets in doubles)
@@ -145,12 +148,26 @@ struct QckReduce {  // fixed-order reduction of shared Hessian positions
     int n_shared;
 };
 
+#define QCK_MAX_GPUS 16
+struct QckPeerReduce {  // shared Hessian positions summed over the partial columns of several GPUs (peer memory)
+    const int* pos;   // [n_shared] position inside the knot block
+    const int* ptr;   // [n_shared+1] CSR into cols
+    const int* cols;  // (gpu << 24) | partial column, ascending integrator order
+    int n_shared;
+    const double* partial[QCK_MAX_GPUS];  // every GPU's partial-column buffer (peer pointers)
+    int npart[QCK_MAX_GPUS];
+};
+int qck_launch_peer_reduce(const QckPeerReduce& R, double* H, long long n_knots, long long nnzH, cudaStream_t stream, int* launches);
+
 // kernel launchers (qck_kernels.cu).  Return cudaError_t as int.
 int qck_launch_quantum(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches);
 int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches);
 // specialised kernels (own translation units); *done tells whether the class was taken
 int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+int qck_launch_rs3(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+size_t qck_rs3_smem(const QckClassDev& c, int hoff, int kpc);
+int qck_rs3_hoff(const QckClassDev& c);
 int qck_fused_aux_limit(void);
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,

@@ -7,7 +7,9 @@
 //   shard_mode ENSEMBLE  GPU g owns a contiguous range of the quantum integrators (the sampled systems of
 //                        unitary_sampling_problem.jl:134-155) for every knot.  Rows / Jacobian entries of different systems are
 //                        disjoint; Hessian entries on the shared controls are summed over the GPUs (host path: fixed order on
-//                        the host, bitwise reproducible; device-resident path: ncclAllReduce of the packed entries).
+//                        the host, bitwise reproducible; device-resident path: every GPU sums the partial columns of all GPUs
+//                        over NVLink peer memory in one launch -- same order, same bits as a one-GPU run; ncclAllReduce of
+//                        the packed entries where peer access is not available or with QCK_ENSEMBLE_NCCL=1).
 //
 // Host-buffer calls run the single-GPU pipeline (qck_pipe.cpp) of every child concurrently, one host thread per GPU, each
 // GPU copying over its own PCIe link into its own page-locked ring and the shared pool expanding into the caller's arrays.
@@ -73,6 +75,64 @@ int nccl_init(qck_handle* h) {
         return qck_fail(h, QCK_ENCCL, "ncclCommInitAll over %d devices: %s", (int)devs.size(), msg);
     }
     h->nccl = N;
+    return QCK_OK;
+}
+
+// ENSEMBLE, device-resident: peer access between all GPUs of the handle + the global contributor tables on every GPU
+int peer_init(qck_handle* h) {
+    if (h->peer_ready) return QCK_OK;
+    h->peer_ready = true;
+    h->peer_ok = false;
+    const int n = (int)h->children.size();
+    if (n > QCK_MAX_GPUS || getenv("QCK_ENSEMBLE_NCCL")) return QCK_OK;
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, h->children[a]->device, h->children[b]->device) != cudaSuccess || !can) return QCK_OK;
+        }
+    for (int a = 0; a < n; ++a) {
+        QCK_CUDA_TRY(h, cudaSetDevice(h->children[a]->device));
+        for (int b = 0; b < n; ++b) {
+            if (a == b) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(h->children[b]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { cudaGetLastError(); return QCK_OK; }
+        }
+    }
+    // global contributor list of every shared position: the children's lists one after the other (ascending integrators)
+    const int ns = (int)h->sh_pos.size();
+    std::vector<int> ptr(ns + 1, 0), cols;
+    for (int s = 0; s < ns; ++s) {
+        for (int g = 0; g < n; ++g) {
+            const qck_handle* c = h->children[g];
+            for (int k = c->sh_ptr[s]; k < c->sh_ptr[s + 1]; ++k) cols.push_back((g << 24) | c->sh_cols[k]);
+        }
+        ptr[s + 1] = (int)cols.size();
+    }
+    h->peer.assign(n, QckPeerReduce{});
+    h->ev_kernel.assign(n, nullptr);
+    h->ev_reduce.assign(n, nullptr);
+    for (int g = 0; g < n; ++g) {
+        qck_handle* c = h->children[g];
+        QCK_CUDA_TRY(h, cudaSetDevice(c->device));
+        QckPeerReduce& R = h->peer[g];
+        R.n_shared = ns;
+        R.pos = c->red.pos;
+        int *dptr = nullptr, *dcols = nullptr;
+        QCK_CUDA_TRY(h, cudaMalloc((void**)&dptr, sizeof(int) * ptr.size()));
+        QCK_CUDA_TRY(h, cudaMalloc((void**)&dcols, sizeof(int) * std::max<size_t>(cols.size(), 1)));
+        c->allocs.push_back(dptr);
+        c->allocs.push_back(dcols);
+        QCK_CUDA_TRY(h, cudaMemcpy(dptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+        if (!cols.empty()) QCK_CUDA_TRY(h, cudaMemcpy(dcols, cols.data(), sizeof(int) * cols.size(), cudaMemcpyHostToDevice));
+        R.ptr = dptr;
+        R.cols = dcols;
+        for (int b = 0; b < n; ++b) { R.partial[b] = h->children[b]->dpartial; R.npart[b] = h->children[b]->npart; }
+        QCK_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_kernel[g], cudaEventDisableTiming));
+        QCK_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_reduce[g], cudaEventDisableTiming));
+    }
+    h->peer_ok = true;
     return QCK_OK;
 }
 
@@ -157,6 +217,8 @@ void qck_multi_destroy(qck_handle* h) {
     for (size_t g = 0; g < h->children.size(); ++g) {
         if (h->children[g]->device >= 0) {
             cudaSetDevice(h->children[g]->device);
+            if (g < h->ev_kernel.size() && h->ev_kernel[g]) cudaEventDestroy(h->ev_kernel[g]);
+            if (g < h->ev_reduce.size() && h->ev_reduce[g]) cudaEventDestroy(h->ev_reduce[g]);
             for (double* p : {g < h->gF.size() ? h->gF[g] : nullptr, g < h->gJ.size() ? h->gJ[g] : nullptr, g < h->gH.size() ? h->gH[g] : nullptr})
                 if (p) cudaFree(p);
         }
@@ -263,14 +325,41 @@ int qck_eval_resident(qck_handle* h, uint32_t mask) {
         return qck_run(h, mask, 0, h->T - 1, h->dZ, h->dmu, (mask & QCK_EVAL_F) ? h->dF : nullptr, (mask & QCK_EVAL_J) ? h->dJ : nullptr,
                        (mask & QCK_EVAL_H) ? h->dH : nullptr, h->stream, 0);
     }
-    for (qck_handle* c : h->children) {
+    const bool shared = h->shard_mode == QCK_SHARD_ENSEMBLE && (mask & QCK_EVAL_H) && h->eval_hessian && !h->sh_pos.empty();
+    if (shared) {
+        int rc = peer_init(h);
+        if (rc) return rc;
+    }
+    const bool peer = shared && h->peer_ok;
+    const int n = (int)h->children.size();
+    for (int g = 0; g < n; ++g) {
+        qck_handle* c = h->children[g];
         QCK_CUDA_TRY(h, cudaSetDevice(c->device));
+        if (peer)  // the partial columns of the previous pass have been read by every GPU
+            for (int b = 0; b < n; ++b)
+                if (b != g) QCK_CUDA_TRY(h, cudaStreamWaitEvent(c->stream, h->ev_reduce[b], 0));
+        c->skip_local_reduce = peer;
         int rc = qck_run(c, mask, 0, c->T - 1, c->dZ, c->dmu, (mask & QCK_EVAL_F) ? c->dF : nullptr, (mask & QCK_EVAL_J) ? c->dJ : nullptr,
                          (mask & QCK_EVAL_H) ? c->dH : nullptr, c->stream, 0);
+        c->skip_local_reduce = false;
         if (rc) { h->err = c->err; return rc; }
         c->pipe.valid_mask = 0;
+        if (peer) QCK_CUDA_TRY(h, cudaEventRecord(h->ev_kernel[g], c->stream));
     }
-    if (h->shard_mode == QCK_SHARD_ENSEMBLE && (mask & QCK_EVAL_H) && h->eval_hessian && !h->sh_pos.empty()) {
+    if (peer) {
+        // all-reduce by all-read: every GPU sums the partial columns of all GPUs over NVLink (one launch per GPU, fixed order)
+        for (int g = 0; g < n; ++g) {
+            qck_handle* c = h->children[g];
+            QCK_CUDA_TRY(h, cudaSetDevice(c->device));
+            for (int b = 0; b < n; ++b)
+                if (b != g) QCK_CUDA_TRY(h, cudaStreamWaitEvent(c->stream, h->ev_kernel[b], 0));
+            int launches = 0;
+            int e = qck_launch_peer_reduce(h->peer[g], c->dH, c->T - 1, c->nnzH, c->stream, &launches);
+            if (e) return qck_fail(h, QCK_ECUDA, "peer reduce launch: %s", cudaGetErrorString((cudaError_t)e));
+            c->launches += launches;
+            QCK_CUDA_TRY(h, cudaEventRecord(h->ev_reduce[g], c->stream));
+        }
+    } else if (shared) {
         int rc = nccl_init(h);
         if (rc) return rc;
         QckNccl* N = static_cast<QckNccl*>(h->nccl);

@@ -44,7 +44,41 @@ __global__ void __launch_bounds__(256) qck_unpack_small_kernel(double* __restric
     }
 }
 
+// Ensemble sharding, device-resident: the Hessian entries on the shared controls are sums over integrators that live on
+// different GPUs.  Every GPU reads the partial columns of ALL GPUs over NVLink (peer pointers) and sums them itself -- an
+// all-reduce by all-read, no collective call, one launch.  The contributor list of a position is the concatenation of the
+// GPUs' lists in ascending integrator order and lane l adds entries l, l+32, ... before the butterfly: the same order as the
+// single-GPU reduce kernel, so the sums are bitwise identical to a one-GPU run.
+__global__ void __launch_bounds__(256) qck_peer_reduce_kernel(const QckPeerReduce r, double* __restrict__ H, long long n_knots, long long nnzH) {
+    const int lane = threadIdx.x & 31;
+    const long long total = n_knots * r.n_shared;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += nwarps) {
+        const long long t = i / r.n_shared;
+        const int s = (int)(i - t * r.n_shared);
+        const int k0 = r.ptr[s], k1 = r.ptr[s + 1];
+        double acc = 0.0;
+        for (int k = k0 + lane; k < k1; k += 32) {
+            const int e = r.cols[k], g = e >> 24, col = e & 0xffffff;
+            acc += r.partial[g][t * r.npart[g] + col];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) H[t * nnzH + r.pos[s]] = acc;
+    }
+}
+
 }  // namespace
+
+int qck_launch_peer_reduce(const QckPeerReduce& R, double* H, long long n_knots, long long nnzH, cudaStream_t stream, int* launches) {
+    if (R.n_shared == 0 || n_knots <= 0) return 0;
+    const long long total = n_knots * R.n_shared;
+    long long grid = (total + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    qck_peer_reduce_kernel<<<(unsigned)grid, 256, 0, stream>>>(R, H, n_knots, nnzH);
+    if (launches) ++*launches;
+    return (int)cudaGetLastError();
+}
 
 int qck_launch_pack(const double* arr, double* out, const int* src, int C, long long ostride, long long nnz, long long nk, cudaStream_t stream, int* launches) {
     if (C <= 0 || nk <= 0) return 0;

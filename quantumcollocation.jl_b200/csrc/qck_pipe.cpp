@@ -540,6 +540,32 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     return h->uses_status ? qck_check_status(h) : QCK_OK;
 }
 
+// The objective / constraint terms (qck_objective.cu) read the same device-resident Z as the dynamics: if the caller's Z is the
+// staged one nothing moves, otherwise it is staged and uploaded whole (on the handle's own stream) and the cached results of
+// the previous Z are dropped.
+int qck_pipe_ensure_z(qck_handle* h, const double* Z) {
+    QCK_CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = pipe_init(h);
+    if (rc) return rc;
+    QckPipe& P = h->pipe;
+    QckPool& pool = QckPool::get(h->host_threads);
+    static const bool no_cache = getenv("QCK_NO_CACHE") != nullptr;
+    const long long n = h->T * (long long)h->zdim;
+    if (!no_cache && P.z_staged && P.z_on_device && same_as_staged(pool, P.pinZ, Z, n)) { ++P.cache_hits; P.h2d_bytes = 0; return QCK_OK; }
+    P.valid_mask = 0;
+    P.z_staged = P.z_on_device = false;
+    const long long piece = 1ll << 15;
+    pool.parallel_for((int)((n + piece - 1) / piece), [&](int i) {
+        const long long o = (long long)i * piece;
+        memcpy(P.pinZ + o, Z + o, sizeof(double) * std::min(piece, n - o));
+    });
+    QCK_CUDA_TRY(h, cudaMemcpyAsync(h->dZ, P.pinZ, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    QCK_CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // (the pipeline's own streams may read dZ next)
+    P.h2d_bytes = sizeof(double) * n;
+    P.z_staged = P.z_on_device = true;
+    return QCK_OK;
+}
+
 extern "C" {
 
 // what crosses PCIe for value array `arr` (0 F, 1 J, 2 H): runs (full offset, compact offset, length, repeats) per knot block

@@ -280,6 +280,54 @@ class QuantumDynamics:
     def expand_host(self, arr: int, compact: np.ndarray, out: np.ndarray, nk: int) -> None:
         self._check(self._lib.qck_expand_host(self._h, arr, _ptr(compact), _ptr(out), nk))
 
+    # ---- objective / terminal-constraint terms --------------------------------------------------------------
+    def attach_objective(self, J) -> None:
+        """J: an objectives.Objective (sum of terms); evaluated on the device from the same Z as the dynamics."""
+        from .objectives import term_array
+        arr, keep = term_array(J)
+        self._check(self._lib.qck_objective_attach(self._h, arr, len(J.terms)))
+        n, nh = C.c_int64(), C.c_int64()
+        self._check(self._lib.qck_objective_sizes(self._h, C.byref(n), C.byref(nh)))
+        self.n_vars, self.nnz_obj_hess = n.value, nh.value
+        self._obj_struct = None
+
+    def objective(self, Z) -> float:
+        v = C.c_double()
+        self._check(self._lib.qck_eval_objective(self._h, _ptr(self._Z(Z)), C.byref(v)))
+        return v.value
+
+    def objective_gradient(self, Z, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty(self.n_vars) if out is None else out
+        self._check(self._lib.qck_eval_objective_gradient(self._h, _ptr(self._Z(Z)), _ptr(out)))
+        return out
+
+    def objective_hessian(self, Z, sigma: float = 1.0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty(self.nnz_obj_hess) if out is None else out
+        self._check(self._lib.qck_eval_objective_hessian(self._h, _ptr(self._Z(Z)), float(sigma), _ptr(out)))
+        return out
+
+    @property
+    def objective_hessian_structure(self) -> np.ndarray:
+        if self._obj_struct is None:
+            rows, cols = np.empty(self.nnz_obj_hess, dtype=np.int64), np.empty(self.nnz_obj_hess, dtype=np.int64)
+            self._check(self._lib.qck_objective_hessian_structure(self._h, _ptr(rows), _ptr(cols)))
+            self._obj_struct = np.stack([rows, cols], axis=1)
+        return self._obj_struct
+
+    def attach_fidelity_constraint(self, con) -> None:
+        from .objectives import term_array
+        arr, keep = term_array(con)
+        self._check(self._lib.qck_fidelity_constraint_attach(self._h, arr, con.val))
+        self._con_len = len(con.comp)
+
+    def fidelity_constraint(self, Z, mu: Optional[float] = None):
+        """(g, jacobian row[, mu * Hessian upper triangle by column])."""
+        g = C.c_double()
+        jac = np.empty(self._con_len)
+        hess = np.empty(self._con_len * (self._con_len + 1) // 2) if mu is not None else None
+        self._check(self._lib.qck_eval_fidelity_constraint(self._h, _ptr(self._Z(Z)), float(mu or 0.0), C.byref(g), _ptr(jac), _ptr(hess)))
+        return (g.value, jac) if mu is None else (g.value, jac, hess)
+
     def invalidate(self) -> None:
         self._check(self._lib.qck_invalidate(self._h))
 

@@ -1,2 +1,2 @@
 """Test helpers (thin re-export of the oracle bridge)."""
-from oracle.bridge import oracle_dynamics, rel_err  # noqa: F401
+from oracle.bridge import entry_err, oracle_dynamics, rel_err  # noqa: F401
