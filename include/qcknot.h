@@ -224,6 +224,18 @@ int qck_eval_objective_hessian(qck_handle* h, const double* Z, double sigma, dou
 int qck_fidelity_constraint_attach(qck_handle* h, const qck_objective_term* term, double min_fidelity);
 int qck_eval_fidelity_constraint(qck_handle* h, const double* Z, double mu, double* g, double* jac, double* hess);
 
+/* ---- rollouts on the device ---------------------------------------------------------------
+ * unitary_rollout (ket = 0) / rollout (ket = 1) of the reference (src/trajectory_initialization.jl:426,493; the fidelity
+ * assertions of every template test, e.g. unitary_smooth_pulse_problem.jl:218-220; robustness sweeps over sampled systems,
+ * unitary_sampling_problem.jl:233-243):  X_1 = X_init, X_{t+1} = exp(dt_t G_s(a_t)) X_t for n_systems systems sharing the
+ * controls.  H_drift [n_systems][N*N] (may be NULL), H_drives [n_systems][n_drives][N*N]: ComplexF64 column-major, interleaved;
+ * a [T][n_drives] = vec of the n_drives x T control matrix; dt [T]; X_init [n_systems][dim] iso-vec(s), NULL = identity / first
+ * basis ket; X_out [n_systems][T][dim], dim = 2 N^2 (unitary) or 2 N (ket): per system the dim x T component, column-major.
+ * levels <= 16.  Independent of any handle; errors through qck_rollout_last_error(). */
+int qck_rollout(int32_t device, int32_t ket, int32_t levels, int32_t n_drives, int32_t n_systems, const double* H_drift,
+                const double* H_drives, int64_t T, const double* a, const double* dt, const double* X_init, double* X_out);
+const char* qck_rollout_last_error(void);
+
 /* kernels launched on this handle since creation (bench.py's gpu_launches) */
 int qck_launch_count(const qck_handle* h, int64_t* launches);
 /* version string of the library */

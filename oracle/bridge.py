@@ -12,6 +12,7 @@ _CLS = {
     "UnitaryExponentialIntegrator": ko.UnitaryExponentialIntegrator,
     "QuantumStatePadeIntegrator": ko.QuantumStatePadeIntegrator,
     "QuantumStateExponentialIntegrator": ko.QuantumStateExponentialIntegrator,
+    "DensityOperatorExponentialIntegrator": ko.QuantumStateExponentialIntegrator,  # ket integrator on N^2 levels, Lindbladian as the system
 }
 
 

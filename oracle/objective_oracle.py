@@ -15,8 +15,8 @@ restates them from their call sites and docstrings in /root/reference and from t
       g(Z) = F(U_T) - val >= 0
 
 Each term gives value, dense gradient (length zdim*T) and upper-triangular Hessian entries; the objective's Hessian structure
-is knot-major: for every knot t, for every term in order, the term's entries at that knot (duplicates are summed by the
-consumer like every (values, structure) pair of the reference, test/test_utils.jl:14-27).
+is knot-major: for every knot t the per-knot terms' entries in term order, then the terminal terms' dense blocks on the final
+knot (duplicates are summed by the consumer like every (values, structure) pair of the reference, test/test_utils.jl:14-27).
 """
 from __future__ import annotations
 
@@ -158,9 +158,13 @@ class Objective:
 
     def _entries(self, Z):
         out = []
-        for t in range(self.T):
+        for t in range(self.T):  # per-knot terms, knot-major
             for term in self.terms:
-                out += term.hessian_entries(Z, self.T, self.zdim, t)
+                if not isinstance(term, UnitaryInfidelityObjective):
+                    out += term.hessian_entries(Z, self.T, self.zdim, t)
+        for term in self.terms:  # terminal terms after the final knot
+            if isinstance(term, UnitaryInfidelityObjective):
+                out += term.hessian_entries(Z, self.T, self.zdim, self.T - 1)
         return out
 
     def hessian_structure(self):

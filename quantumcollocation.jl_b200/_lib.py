@@ -22,7 +22,7 @@ EXPORTS = [
     "qck_compact_map", "qck_expand_host",
     "qck_objective_attach", "qck_objective_sizes", "qck_objective_hessian_structure", "qck_eval_objective",
     "qck_eval_objective_gradient", "qck_eval_objective_hessian", "qck_fidelity_constraint_attach",
-    "qck_eval_fidelity_constraint",
+    "qck_eval_fidelity_constraint", "qck_rollout", "qck_rollout_last_error",
 ]
 
 
@@ -106,6 +106,8 @@ def load() -> C.CDLL:
     lib.qck_eval_objective_hessian.argtypes = [vp, vp, C.c_double, vp]
     lib.qck_fidelity_constraint_attach.argtypes = [vp, C.POINTER(ObjectiveTerm), C.c_double]
     lib.qck_eval_fidelity_constraint.argtypes = [vp, vp, C.c_double, dp, vp, vp]
+    lib.qck_rollout.argtypes = [C.c_int32] * 5 + [vp, vp, C.c_int64, vp, vp, vp, vp]
+    lib.qck_rollout_last_error.restype = C.c_char_p
     lib.qck_compact_map.argtypes = [vp, C.c_int32, i64p, vp]
     lib.qck_expand_host.argtypes = [vp, C.c_int32, vp, vp, C.c_int64]
     _lib = lib

@@ -148,9 +148,56 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uns
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (the bulk copy engine)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// same entries from a shared-memory copy of the table (row-slice kernel): the knot's inputs are L1 / L2 hits by now
+__device__ __forceinline__ void do_aux_smem(const QckLaunch& p, const QckAux* auxs, long long t, int tid, int nthreads) {
+    const QckClassDev& c = p.c;
+    const double* zt = p.Z + t * c.zdim;
+    const double dt = c.free_time ? __ldg(zt + c.dt_off) : c.dt_fixed;
+    for (int k = tid; k < p.n_aux; k += nthreads) {
+        const QckAux a = auxs[k];
+        if (!((p.mask >> a.out) & 1u)) continue;
+        double v;
+        switch (a.op) {
+            case QAUX_CONST: v = a.c; break;
+            case QAUX_NEG_DT: v = -dt; break;
+            case QAUX_NEG_Z: v = -__ldg(zt + a.i0); break;
+            case QAUX_NEG_MU: v = -__ldg(p.mu + t * c.dyn + a.i0); break;
+            default: v = __ldg(zt + c.zdim + a.i0) - __ldg(zt + a.i0) - dt * __ldg(zt + a.i1); break;
+        }
+        if (a.out == 0) p.F[t * c.dyn + a.pos] = v;
+        else if (a.out == 1) p.J[t * p.nnzJ + a.pos] = v;
+        else if (a.pos < p.nnzH) p.H[t * p.nnzH + a.pos] = v;
+        else p.partial[t * p.npart + (a.pos - p.nnzH)] = v;
+    }
+}
+
+// Lane-parallel write-out for images placed with destination parity (qck_host.cpp: place_array(parity), rs3_units): one lane
+// = one unit = nrep back-to-back copies of [scalar head] + 16-byte aligned TMA bulk copy + [scalar tail].  `stage` holds the
+// F + J part of the image at offset 0 (shifted by shF / shJ doubles) or the Hessian part (image offsets >= hoff, shifted by
+// shH); a shift is the parity of the array's knot-block base address, so source and destination of a unit always agree mod 16.
+__device__ __forceinline__ void flush_units_lanes(const double* __restrict__ stage, const QckSeg* __restrict__ units, int u0, int u1, int lane,
+                                                  double* baseF, double* baseJ, double* baseH, int shF, int shJ, int shH, int hoff, unsigned mask) {
+    for (int u = u0 + lane; u < u1; u += 32) {
+        const QckSeg sg = units[u];
+        const int arr = sg.arr & 255;
+        if (!((mask >> arr) & 1u)) continue;
+        double* dst = (arr == 0 ? baseF : (arr == 1 ? baseJ : baseH)) + sg.dst;
+        const int off = sg.img_nrep & 0xffff, nrep = sg.img_nrep >> 16, n = sg.n;
+        const double* src = stage + (arr == 2 ? off - hoff + shH : off + (arr == 0 ? shF : shJ));
+        const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);  // == parity of src by construction
+        const int body = (n - head) & ~1;
+        for (int r = 0; r < nrep; ++r, dst += n) {
+            if (head) dst[0] = src[0];
+            if (body) bulk_store(dst + head, src + head, (unsigned)body * 8u);
+            if (head + body < n) dst[n - 1] = src[n - 1];
+        }
+    }
+}
 
 // Write-out: every unit is nrep back-to-back contiguous copies image -> value array, owned by ONE warp (the host
 // balanced the units over the warps).  Consecutive lanes store consecutive positions with 16-byte stores; a destination

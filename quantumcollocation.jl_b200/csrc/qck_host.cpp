@@ -80,7 +80,7 @@ struct Run { int dst, len, img, period; };
 // parity: every run gets an image offset of the same parity as its destination (rs3 kernel: the write-out of a run is then
 // [scalar head] + 16-byte aligned bulk copy + [scalar tail] whatever the parity of the knot block's base address).
 bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* base, short* stride, std::vector<Run>& segs,
-                 std::string& why, int* dst0 = nullptr, bool parity = false) {
+                 std::string& why, int* dst0 = nullptr, bool parity = false, bool no_image = false) {
     if (e.empty()) return true;
     struct Group { int qid; long long d0; int s, n, period; };
     std::map<int, std::vector<MapEnt>> by_q;
@@ -119,7 +119,8 @@ bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* bas
             }
             run_end = -2;
         }
-        if (cursor > 32000) { why = "output image too large"; return false; }
+        if (cursor > 32000 && !no_image) { why = "output image too large"; return false; }
+        if (cursor > 32000) { b = 0; cursor = 32000; }  // (large-level classes never stage an image: only destinations and strides matter)
         base[g.qid] = (short)b;
         stride[g.qid] = (short)g.s;
         if (dst0) dst0[g.qid] = (int)g.d0;  // destination of element 0 (column kernel: values go straight to the arrays)
@@ -140,7 +141,7 @@ bool place_array(std::vector<MapEnt> e, long long split, int& cursor, short* bas
                 ++k2;
             segs.push_back(Run{(int)e[k].dst, (int)(k2 - k), img_of(e[k]), (int)(k2 - k)});
         }
-        if (!parity && (segs.back().img & 1)) { why = "internal: odd segment image offset"; return false; }
+        if (!parity && !no_image && (segs.back().img & 1)) { why = "internal: odd segment image offset"; return false; }
         if (parity && ((segs.back().img ^ segs.back().dst) & 1)) { why = "internal: image / destination parity mismatch"; return false; }
         k = k2;
     }
@@ -232,7 +233,21 @@ std::vector<QckSeg> rs3_units(const std::vector<Run> (&runs)[3], long long nnzH,
         }
         hdr[4 * phase + 3] = (int)out.size();
     }
-    for (int w = 8; w < QCK_SEG_HDR; ++w) hdr[w] = (int)out.size();
+    hdr[8] = hdr[9] = hdr[10] = (int)out.size();
+    // third list: phase 1 split by the moment the values are complete -- the kron blocks (one repetition per unit: one lane, one
+    // bulk copy) right after A^2, the rest at the end of the phase: hdr[11] .. hdr[12] blocks, hdr[12] .. hdr[13] rest
+    hdr[11] = (int)out.size();
+    for (int arr = 0; arr < 2; ++arr)
+        for (auto& r : runs[arr])
+            if (r.period < r.len)
+                for (int r0 = 0; r0 < r.len / r.period; ++r0) out.push_back({r.dst + r0 * r.period, r.period, r.img | (1 << 16), arr});
+    hdr[12] = (int)out.size();
+    for (int arr = 0; arr < 2; ++arr)
+        for (auto& r : runs[arr])
+            if (!(r.period < r.len))
+                for (int o = 0; o < r.len; o += 512) out.push_back({r.dst + o, std::min(512, r.len - o), (r.img + o) | (1 << 16), arr});
+    hdr[13] = (int)out.size();
+    for (int w = 14; w < QCK_SEG_HDR; ++w) hdr[w] = (int)out.size();
     return out;
 }
 
@@ -395,9 +410,17 @@ int build(qck_handle* h) {
         c.n_tbuf = C.member_end - C.member_begin > 1 ? 2 : 1;
         c.threads = qck_pick_threads(c);
         const int nwarps = c.threads / 32;
-        // three-warps-per-knot kernel: 9-level Pade-4 unitaries, one active member, nothing shared with other integrators
-        static const int rs3_knob = getenv("QCK_RS3") ? atoi(getenv("QCK_RS3")) : 7;  // knots per CTA (5..8), 0 = off
-        c.rs3 = (rs3_knob >= 5 && rs3_knob <= 8 && c.kind == QCK_UNITARY_PADE && c.order == 4 && c.N == 9 && c.nd >= 1 && c.nd <= 4 &&
+        // Pade-4 classes whose image / matrices do not fit the tiled kernel's shared memory (up to 32 levels) run on the large-level
+        // kernel (qck_big.cu): operands in shared memory, every output straight to its destination (QCK_BIG=1 forces it from
+        // 5 levels on, for A/B runs)
+        static const int big_knob = getenv("QCK_BIG") ? atoi(getenv("QCK_BIG")) : 0;
+        const bool big_ok = (c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && c.N >= 5 && c.N <= 32 &&
+                            qck_big_smem(c) <= 227 * 1024;
+        // 9-level Pade-4 unitaries, one active member, nothing shared with other integrators: parity-matched image placement and
+        // per-phase unit tables for the row-slice kernel (QCK_RS3=1, default: one warp per knot) or its three-warps-per-knot
+        // variant (QCK_RS3=5..7 knots per CTA; parity-green, measured slower: profiles/); QCK_RS3=0: the tiled kernel
+        static const int rs3_knob = getenv("QCK_RS3") ? atoi(getenv("QCK_RS3")) : 1;
+        c.rs3 = ((rs3_knob == 1 || (rs3_knob >= 5 && rs3_knob <= 7)) && c.kind == QCK_UNITARY_PADE && c.order == 4 && c.N == 9 && c.nd >= 1 && c.nd <= 4 &&
                  C.member_end - C.member_begin == 1 && h->npart == 0) ? rs3_knob : 0;
         for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
         std::vector<int> qdst((size_t)nm * QO_COUNT, -1);  // per member: first destination of every output quantity
@@ -416,11 +439,11 @@ int build(qck_handle* h) {
                 int cursor = 0;
                 std::string why;
                 const bool par = c.rs3 != 0;
-                bool ok = place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why, d0, par);
+                bool ok = place_array(mf, (long long)1 << 60, cursor, base, stride, runs[0], why, d0, par, big_ok);
                 if (par) cursor += 2;  // (the image of every array may be shifted by one double on its own)
-                ok = ok && place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why, d0, par);
+                ok = ok && place_array(mj[m2], (long long)1 << 60, cursor, base, stride, runs[1], why, d0, par, big_ok);
                 if (par) cursor = (cursor + 3) & ~1;
-                ok = ok && place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why, d0, par);
+                ok = ok && place_array(mh[m2], h->nnzH, cursor, base, stride, runs[2], why, d0, par, big_ok);
                 if (!ok) return fail(h, QCK_EINVAL, "unsupported trajectory layout: %s", why.c_str());
                 for (int arr = 0; arr < 3; ++arr)
                     for (auto& r : runs[arr]) {
@@ -514,12 +537,13 @@ int build(qck_handle* h) {
         }
         c.ac_cap = ac_cap;
         qck_smem_finalize(c);
-        if (c.rs3) {  // as many knots per CTA as the shared memory holds
+        if (c.rs3 >= 5) {  // three-warp variant: as many knots per CTA as the shared memory holds
             const int hoff = qck_rs3_hoff(c);
             while (c.rs3 >= 5 && qck_rs3_smem(c, hoff, c.rs3) > 227 * 1024) --c.rs3;
-            if (c.rs3 < 5) return fail(h, QCK_EINVAL, "rs3 kernel: the tables of this problem leave no room for five knots per CTA");
+            if (c.rs3 < 5) c.rs3 = 1;
         }
-        if (!c.rs3 && (size_t)c.sm_bytes > 227 * 1024 - 4096)
+        c.big = big_ok && !c.rs3 && (big_knob || (size_t)c.sm_bytes > 227 * 1024 - 4096 || c.img_doubles >= 32000) ? 1 : 0;
+        if (!c.rs3 && !c.big && (size_t)c.sm_bytes > 227 * 1024 - 4096)
             return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024 - 4096);
         c.cmat_stride = N * N + c.ell_stride + kk_cap + ac_cap;
         std::vector<double2> cmat((size_t)nm * c.cmat_stride, make_double2(0.0, 0.0));
@@ -574,7 +598,7 @@ int build(qck_handle* h) {
         }
         // column kernel (levels <= 4): dense drive matrices A_j = -i H_j, row-major, and the per-member destinations
         c.dense_aj = nullptr; c.qdst = nullptr;
-        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && N <= 4) {
+        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && (N <= 4 || c.big)) {
             std::vector<double2> daj((size_t)nm * nd * N * N);
             for (int m2 = 0; m2 < nm; ++m2) {
                 const Integ& I = h->integ[C.members[m2]];

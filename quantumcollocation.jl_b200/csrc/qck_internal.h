@@ -65,6 +65,7 @@ struct QckClassDev {
     int kind, N, NP, nc, ncp, nd, order, W;
     int free_time, dt_off, zdim, dyn;
     int antiherm;  // every member's Hamiltonians are Hermitian: A(a) = -i H(a) is anti-Hermitian
+    int big;       // the class runs on the large-level kernel (qck_big.cu): operands in shared memory, outputs straight to the arrays
     int rs3;       // > 0: built for the three-warps-per-knot kernel (qck_rs3.cu) with this many knots per CTA: parity-matched
                    // image placement, unit table [phase][warp] (see qck_host.cpp)
     double dt_fixed;
@@ -137,6 +138,8 @@ struct QckLaunch {
     long long* timing;       // optional per-stage cycle counters (debug)
     unsigned stagger_ns;     // start-up delay step between the CTAs of one SM
     int hoff;                // row-slice kernel: image offset where the Hessian part starts
+    int db;                  // row-slice kernel: separate staging buffers for the F + J image and the Hessian image
+    int spread;              // row-slice kernel: the kron block copies are issued right after A^2, ahead of the rest of phase 1
     int* status;             // device-side error word (QCK_ST_* bits)
     QckPlanCache* plan;      // host-side: per-class launch plan cache (may be NULL)
 };
@@ -166,6 +169,8 @@ int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches);
 int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 int qck_launch_rs3(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+int qck_launch_big(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+size_t qck_big_smem(const QckClassDev& c);
 size_t qck_rs3_smem(const QckClassDev& c, int hoff, int kpc);
 int qck_rs3_hoff(const QckClassDev& c);
 int qck_fused_aux_limit(void);

@@ -1496,10 +1496,13 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     if (n_items <= 0) return 0;
     {
         bool done = false;
-        int rc = qck_launch_rs3(L, sm_count, stream, launches, &done);
+        int rc = qck_launch_big(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
-        if (c.rs3) return (int)cudaErrorInvalidConfiguration;  // the class tables were built for the rs3 kernel only
+        if (c.big) return (int)cudaErrorInvalidConfiguration;  // (no other kernel can hold this class)
+        rc = qck_launch_rs3(L, sm_count, stream, launches, &done);
+        if (rc || done) return rc;
         rc = qck_launch_rowslice9(L, sm_count, stream, launches, &done);
+        if (!rc && !done && c.rs3) return (int)cudaErrorInvalidConfiguration;  // the class tables were built for the row-slice kernels only
         if (rc || done) return rc;
         rc = qck_launch_column(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;

@@ -243,8 +243,8 @@ namespace {
 // values then leave in TRANSFER PIECES, each one D2H copy + one event + one batch of expansion work, small enough that the
 // host threads read a piece while it is still in the last-level cache the DMA engine wrote it into.
 constexpr long long kChunkBytes = 24ll << 20;  // compact bytes per compute chunk
-constexpr long long kPieceBytes = 6ll << 20;   // compact bytes per transfer piece
-constexpr int kRing = 12;                      // page-locked ring depth in pieces
+constexpr long long kPieceBytes = 2ll << 20;   // compact bytes per transfer piece
+constexpr int kRing = 24;                      // page-locked ring depth in pieces
 
 long long env_ll(const char* name, long long dflt) {
     const char* e = getenv(name);

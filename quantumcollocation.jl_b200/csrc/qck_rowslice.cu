@@ -1,4 +1,6 @@
 // Row-slice kernel (9-level Pade-4 unitaries, one warp per knot) of libqcknot.so.  Compiled as its own translation unit so that the kernel families build in parallel.
+#include <algorithm>
+
 #include "qck_device.cuh"
 
 namespace {
@@ -18,8 +20,12 @@ namespace {
 //     dt x dt = 1/6 sum Re<m, A A d>      a_j x dt = sum -1/2 Re<z1_j, s> + h/6 (Re<z1_j, A d> + Re<w1, A_j d>)
 //     a_i x a_j = h^2/12 Re tr({A_i, A_j} G),  G = D M^H     (sums over rows and columns = one warp reduction each)
 // 8 + 2 n_d dense row-slice products and 4 n_d products with the (sparse) drives per knot.  Values go into the warp's
-// staging buffer in the solver's structure order (same host placement and write-out units as the tiled kernel): first the
-// residual + Jacobian part, flushed, then the Hessian part in the same space.
+// staging buffer in the solver's structure order: first the residual + Jacobian part, flushed, then the Hessian part in the
+// same space.  Write-out (round 2): the host places every run at an image offset of the SAME PARITY as its destination
+// (place_array(parity)) and the kernel shifts an array's image by one double when that array's knot block starts at 8 mod 16
+// (odd nnzH flips the Hessian base every knot), so every unit is [scalar head] + one 16-byte aligned TMA bulk copy + [scalar
+// tail], decoded and issued by one lane per unit with all lanes in parallel (flush_units_lanes): ~10x fewer instructions than
+// the unit-by-unit loop of round 1 and no misaligned slow path.
 // ------------------------------------------------------------------------------------------------------------
 // WC: compile-time width of the sparse rows of the drives (loops fully unrolled); 0 = dense drive matrices
 // AH: A is anti-Hermitian (Hermitian Hamiltonians): A^H x = -(A x) runs on the register-resident rows of A
@@ -44,20 +50,25 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;
     QckSeg* const segtab = reinterpret_cast<QckSeg*>(smem_all + (((size_t)nconv * 16 + (size_t)c.icon_stride * 4 + 15) & ~(size_t)15));
     // output staging: the F + J part of the image first, flushed, then the Hessian part in the same space
-    const int hoff = p.hoff, stage_doubles = hoff > c.img_doubles - hoff ? hoff : c.img_doubles - hoff;
-    const int img_bytes = ((stage_doubles + 1) & ~1) * 8;
-    double2* const cAj = reinterpret_cast<double2*>(segtab + nrec);  // WC == 0: dense A_j, row-major
-    unsigned char* const wbase = reinterpret_cast<unsigned char*>(cAj + (WC > 0 ? 0 : ND * NN)) + (size_t)warp * (img_bytes + 8 * NN * 16);
-    double* const imgJ = reinterpret_cast<double*>(wbase);
-    double* const imgH = imgJ - hoff;
+    // staging: the F + J part of the image (image offsets < hoff) and the Hessian part (>= hoff), each + 4 doubles of slack for
+    // the parity shifts.  p.db: two separate buffers -- the copy engine drains one phase's image while the warp computes the
+    // next phase (the wait before re-using a buffer then concerns copies issued a whole phase earlier); else both share one.
+    const int hoff = p.hoff;
+    const int jbytes = ((hoff + 4 + 1) & ~1) * 8, hbytes = ((c.img_doubles - hoff + 4 + 1) & ~1) * 8;
+    const int img_bytes = p.db ? jbytes + hbytes : (jbytes > hbytes ? jbytes : hbytes);
+    QckAux* const auxs = reinterpret_cast<QckAux*>(segtab + nrec);   // derivative-integrator entries (CTA-wide copy)
+    double2* const cAj = reinterpret_cast<double2*>(auxs + p.n_aux);  // WC == 0: dense A_j, row-major
+    unsigned char* const wbase = reinterpret_cast<unsigned char*>(cAj + (WC > 0 ? 0 : ND * NN)) + (size_t)warp * (img_bytes + 7 * NN * 16);
+    double* const stage = reinterpret_cast<double*>(wbase);
+    double* const stageH = p.db ? stage + jbytes / 8 : stage;
     double2* const vD = reinterpret_cast<double2*>(wbase + img_bytes);  // columns of D = U1 - U0: element [c * 9 + r]
     double2* const vS = vD + NN;       // S = U1 + U0
     double2* const vM = vS + NN;       // multipliers
     double2* const vX2 = vM + NN;      // A D
     double2* const vW1 = vX2 + NN;     // A^H M
     double2* const vU = vW1 + NN;      // A_j D (current drive)
-    double2* const vZ1 = vU + NN;      // A_j^H M (current drive)
-    double2* const mA = vZ1 + NN;      // A, row-major (for A^H products and column access)
+    double2* const vZ1 = vU;           // A_j^H M (current drive; phase 2 only, when A_j D is dead)
+    double2* const mA = vU + NN;       // A, row-major (for A^H products and column access)
     {
         const double2* gv = c.cmat + (size_t)m * c.cmat_stride;
         const int* gc = c.ell_col + (size_t)m * c.icon_stride;
@@ -65,7 +76,8 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
         for (int e = threadIdx.x; e < c.icon_stride; e += blockDim.x) coni[e] = gc[e];
         const QckSeg* gs = c.segs + (size_t)m * nrec;
         for (int i = threadIdx.x; i < nrec; i += blockDim.x) segtab[i] = gs[i];
-        for (int i = lane; i < img_bytes / 8; i += 32) imgJ[i] = 0.0;
+        for (int i = lane; i < img_bytes / 8; i += 32) stage[i] = 0.0;
+        for (int i = threadIdx.x; i < p.n_aux; i += blockDim.x) auxs[i] = p.aux[i];
         if (WC == 0) {
             for (int e = threadIdx.x; e < ND * NN; e += blockDim.x) cAj[e] = make_double2(0.0, 0.0);
             __syncthreads();
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
     const int* const kkrc = kkptr + ND * (ND + 1) / 2 + 1;
     const int* const acptr = kkrc + kkc;
     const int* const acj = acptr + NN + 1;
-    const int* seghdr = reinterpret_cast<const int*>(segtab);
+    const int* seghdr = reinterpret_cast<const int*>(segtab);   // [phase][warp of three] first unit; hdr[3] / hdr[7] = ends
     const QckSeg* segs = segtab + QCK_SEG_HDR / 4;
     const int soff = p.moff_global[0], coff = p.moff_global[1], roff = p.moff_global[2];
     const int xo = cc * N;  // this lane's column inside the vector buffers
@@ -110,6 +122,17 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
             }
         }
         const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
+        double ctl[ND];  // the controls a_j of this knot: issued with the other global loads, used by the assembly of A
+#pragma unroll
+        for (int j = 0; j < ND; ++j) ctl[j] = zt[coff + j];
+        double* const baseF = p.F + t * c.dyn;
+        double* const baseJ = p.J + t * p.nnzJ;
+        double* const baseH = p.H + t * p.nnzH;
+        const int shF = (int)((reinterpret_cast<uintptr_t>(baseF) >> 3) & 1), shJ = (int)((reinterpret_cast<uintptr_t>(baseJ) >> 3) & 1),
+                  shH = (int)((reinterpret_cast<uintptr_t>(baseH) >> 3) & 1);
+        double* const imgF = stage + shF;
+        double* const imgJ = stage + shJ;
+        double* const imgH = stageH - hoff + shH;
         if (t + (long long)gridDim.x * nwarps < p.n_knots) {  // pull the next knot of this warp into L2 meanwhile
             const double* zn = zt + (long long)gridDim.x * nwarps * c.zdim;
             const double* mn = p.mu + (t + (long long)gridDim.x * nwarps) * c.dyn + roff;
@@ -133,7 +156,10 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
         for (int e = lane; e < NN; e += 32) {
             double2 v = A0[e];
             for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
-                const double aj = __ldg(zt + coff + acj[u]);  // (L1 hit: the controls were just loaded)
+                const int jd = acj[u];
+                double aj = ctl[0];
+#pragma unroll
+                for (int j = 1; j < ND; ++j) aj = jd == j ? ctl[j] : aj;
                 const double2 d = acv[u];
                 v.x = fma(aj, d.x, v.x);
                 v.y = fma(aj, d.y, v.y);
@@ -211,15 +237,15 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
 #pragma unroll
                 for (int i = 0; i < 3; ++i) s_hh += rdot(vM[xo + k3 + i], x3[i]);
             }
-            if (QCK_BULK_STORE) {
-                bulk_wait_read();  // the copy engine has finished reading the previous knot's staging buffer
-                __syncwarp();
-            }
+            // the copy engine has finished reading this buffer's previous image (two buffers: the group before the last one)
+            if (p.db && needH) bulk_wait_read_1();
+            else bulk_wait_read();
+            __syncwarp();
             // ---- phase 1: residual and Jacobian values ---------------------------------------------------------------------------
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double2 d = vD[xo + k3 + i];
-                put(imgJ, QO_R, i, make_double2(d.x - c1h * x1[i].x + c2h2 * x3[i].x, d.y - c1h * x1[i].y + c2h2 * x3[i].y));
+                put(imgF, QO_R, i, make_double2(d.x - c1h * x1[i].x + c2h2 * x3[i].x, d.y - c1h * x1[i].y + c2h2 * x3[i].y));
                 put(imgJ, QO_TH, i, make_double2(-0.5 * x1[i].x + c2h * x3[i].x, -0.5 * x1[i].y + c2h * x3[i].y));
             }
         }
@@ -241,6 +267,11 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                     imgJ[bF + k00 * sF] = -fr; imgJ[bF + (k00 + N) * sF] = -fi; imgJ[bF + k01 * sF] = fi; imgJ[bF + (k01 + N) * sF] = -fr;
                     imgJ[bB + k00 * sB] = br;  imgJ[bB + (k00 + N) * sB] = bi;  imgJ[bB + k01 * sB] = -bi; imgJ[bB + (k01 + N) * sB] = br;
                 }
+            }
+            if (p.spread) {  // the 2 x N block copies leave now and drain behind the drive loop (shorter bursts at the copy engine)
+                fence_async_smem();
+                __syncwarp();
+                flush_units_lanes(stage, segs, seghdr[11], seghdr[12], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & QCK_EVAL_J);
             }
         }
         if (needJ) {  // (a Hessian-only call gets its A_j d inside the Hessian loop and skips this one)
@@ -291,23 +322,20 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 }
             }
         }
-        if (p.n_aux) do_aux(p, t, lane, 32);  // derivative-integrator entries of this knot
-        if (QCK_BULK_STORE) fence_async_smem();
+        if (p.n_aux) do_aux_smem(p, auxs, t, lane, 32);  // derivative-integrator entries of this knot
+        fence_async_smem();
         __syncwarp();
-        // (when the Hessian phase follows at once, its first image write would wait for these copies anyway: one lane issues
-        //  them in order; as the knot's last flush they are issued from all lanes and drain behind the next knot's first products)
-        if (needH) write_units<2 * NN>(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
-        else write_units_lanes(imgJ, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
-        if (QCK_BULK_STORE) bulk_commit();
+        if (p.spread && needJ) flush_units_lanes(stage, segs, seghdr[12], seghdr[13], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
+        else flush_units_lanes(stage, segs, seghdr[0], seghdr[3], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
+        bulk_commit();
         __syncwarp();
         // ---- phase 2: Hessian-of-Lagrangian values, staged in the same buffer ------------------------------------------------------
         if (needH) {
             double2 w2[3];
             mvAH(w2, vW1 + xo);
-            if (QCK_BULK_STORE) {
-                bulk_wait_read();  // phase-1 copies have left the buffer
-                __syncwarp();
-            }
+            if (p.db) bulk_wait_read_1();  // the previous knot's Hessian image has left its buffer
+            else bulk_wait_read();         // phase-1 copies have left the shared buffer
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 put(imgH, QO_KH0, i, make_double2(-0.5 * w1[i].x - c2h * w2[i].x, -0.5 * w1[i].y - c2h * w2[i].y));
@@ -399,7 +427,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
             }
             if (act) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) vU[(k3 + i) * N + cc] = gr[i];  // G[row][column]  (vU: its last reader ran before phase 1's flush)
+                for (int i = 0; i < 3; ++i) vX2[(k3 + i) * N + cc] = gr[i];  // G[row][column]  (vX2 = A D: its last readers were the drive loops)
             }
             __syncwarp();
             constexpr int NPAIR = ND * (ND + 1) / 2;
@@ -409,7 +437,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 for (int u = kkptr[pr] + sub, u1 = kkptr[pr + 1]; u < u1; u += 3) {
                     const int rc = kkrc[u];
                     const double2 kv = kkv[u];
-                    const double2 gv = vU[(rc & 255) * N + (rc >> 8)];  // K[r, k] G[k, r]
+                    const double2 gv = vX2[(rc & 255) * N + (rc >> 8)];  // K[r, k] G[k, r]
                     val = fma(kv.x, gv.x, val);
                     val = fma(-kv.y, gv.y, val);
                 }
@@ -429,10 +457,10 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 for (int j = 0; j < ND; ++j)
                     if (c.pl_base[QO_HAH + j] >= 0) imgH[c.pl_base[QO_HAH + j]] = s_ah[j];
             }
-            if (QCK_BULK_STORE) fence_async_smem();
+            fence_async_smem();
             __syncwarp();
-            write_units_lanes(imgH, segs, seghdr[0], seghdr[QCK_SEG_HDR - 1], p, t, lane, p.mask & QCK_EVAL_H);
-            if (QCK_BULK_STORE) bulk_commit();
+            flush_units_lanes(stageH, segs, seghdr[4], seghdr[7], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & QCK_EVAL_H);
+            bulk_commit();
             __syncwarp();
         }
     }
@@ -447,7 +475,7 @@ int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, 
     const QckClassDev& c = L.c;
     *done = false;
     static const int enabled = getenv("QCK_ROWSLICE") ? atoi(getenv("QCK_ROWSLICE")) : 1;
-    if (!enabled || c.kind != QCK_UNITARY_PADE || c.order != 4 || c.N != 9 || L.member_end - L.member_begin != 1 || c.nd < 1 || c.nd > 4) return 0;
+    if (!enabled || !c.rs3 || c.kind != QCK_UNITARY_PADE || c.order != 4 || c.N != 9 || L.member_end - L.member_begin != 1 || c.nd < 1 || c.nd > 4) return 0;
     typedef void (*kern_t)(const QckLaunch);
     static const int sparse_ok = getenv("QCK_ROWSLICE_DENSE") ? 0 : 1;
     const int wc = sparse_ok && c.W <= 2 ? c.W : 0;  // sparse drive rows of width 1 or 2 are unrolled; wider ones run dense
@@ -458,33 +486,38 @@ int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, 
 #undef QCK_RS
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;
     // staging: F + J part and Hessian part of the output image share one buffer (the Hessian part starts at hoff)
-    int hoff = c.img_doubles;
-    for (int q = 0; q < QO_COUNT; ++q) {
-        const bool hq = q == QO_KH0 || q == QO_KH1 || (q >= QO_KA0 && q < QO_ONE);
-        if (hq && c.pl_base[q] >= 0 && c.pl_base[q] < hoff) hoff = c.pl_base[q];
-    }
-    hoff &= ~1;
-    const int stage_doubles = hoff > c.img_doubles - hoff ? hoff : c.img_doubles - hoff;
-    const size_t per_warp = (size_t)((stage_doubles + 1) & ~1) * 8 + 8 * 81 * 16;
+    const int hoff = qck_rs3_hoff(c);
+    const size_t jbytes = (size_t)((hoff + 4 + 1) & ~1) * 8, hbytes = (size_t)((c.img_doubles - hoff + 4 + 1) & ~1) * 8;
     const size_t shared = ((((size_t)(81 + c.ell_stride + c.kk_cap + c.ac_cap) * 16 + (size_t)c.icon_stride * 4) + 15) & ~(size_t)15) + (size_t)nrec * 16 +
-                          (wc > 0 ? 0 : (size_t)c.nd * 81 * 16);
-    int nwarps = 8;
+                          (size_t)L.n_aux * sizeof(QckAux) + (wc > 0 ? 0 : (size_t)c.nd * 81 * 16);
+    // two staging buffers per warp (6 warps fit) when the Hessian phase runs, one shared buffer (8 warps) otherwise
+    // knobs (A/B measurements in profiles/): issue the kron block copies early; separate staging buffers for the two phases
+    // (6 warps instead of 8: measured slower, off by default).  A write-out with plain 16-byte stores from registers instead of
+    // TMA bulk copies was measured 10 % slower (profiles/r02_rowslice_variants.txt) and is not kept.
+    static const int spread_knob = getenv("QCK_ROWSLICE_SPREAD") ? atoi(getenv("QCK_ROWSLICE_SPREAD")) : 1;
+    static const int db_knob = getenv("QCK_ROWSLICE_DB") ? atoi(getenv("QCK_ROWSLICE_DB")) : 0;
     static const int knob = getenv("QCK_ROWSLICE_WARPS") ? atoi(getenv("QCK_ROWSLICE_WARPS")) : 0;
+    int db = db_knob && (L.mask & QCK_EVAL_H) && (L.mask & (QCK_EVAL_F | QCK_EVAL_J)) ? 1 : 0;
+    size_t per_warp = (db ? jbytes + hbytes : std::max(jbytes, hbytes)) + 7 * 81 * 16;
+    if (db && shared + 4 * per_warp > 227 * 1024) { db = 0; per_warp = std::max(jbytes, hbytes) + 7 * 81 * 16; }
+    int nwarps = 8;
     if (knob >= 1 && knob <= 8) nwarps = knob;
     while (nwarps > 1 && shared + nwarps * per_warp > 227 * 1024) --nwarps;
     const size_t smem = shared + nwarps * per_warp;
     if (smem > 227 * 1024) return 0;
-    if (!(L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!(L.plan && L.plan->kern == (const void*)kern)) {  // once per handle: the largest opt-in size covers every mask
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = smem; L.plan->per_sm = 1; }
+        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = 227 * 1024; L.plan->per_sm = 1; }
     }
     long long grid = sm_count;
     if (grid * nwarps > L.n_knots) grid = (L.n_knots + nwarps - 1) / nwarps;
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
-    if (dbg) fprintf(stderr, "[qcknot] row-slice kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d\n", c.nd, nwarps, smem, grid, c.nseg);
+    if (dbg) fprintf(stderr, "[qcknot] row-slice kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d two-buffers=%d early-blocks=%d\n", c.nd, nwarps, smem, grid, c.nseg, db, spread_knob);
     QckLaunch L2 = L;
     L2.hoff = hoff;
+    L2.db = db;
+    L2.spread = spread_knob;
     kern<<<(unsigned)grid, nwarps * 32, smem, stream>>>(L2);
     if (launches) ++*launches;
     *done = true;

@@ -391,10 +391,10 @@ int qck_rs3_hoff(const QckClassDev& c) {
 int qck_launch_rs3(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done) {
     const QckClassDev& c = L.c;
     *done = false;
-    if (!c.rs3) return 0;
+    if (c.rs3 < 5) return 0;  // (1: the one-warp-per-knot kernel of qck_rowslice.cu takes the class)
     const int wc = c.W <= 2 ? c.W : 0;
     const int kpc = c.rs3;
-    if (kpc < 5 || kpc > 7) return (int)cudaErrorInvalidConfiguration;
+    if (kpc > 7) return (int)cudaErrorInvalidConfiguration;
     qck_rs3_kern_t kern = c.nd == 1 ? qck_rs3_get_1(wc, c.antiherm, kpc) : (c.nd == 2 ? qck_rs3_get_2(wc, c.antiherm, kpc) :
                           (c.nd == 3 ? qck_rs3_get_3(wc, c.antiherm, kpc) : qck_rs3_get_4(wc, c.antiherm, kpc)));
     const int hoff = qck_rs3_hoff(c);

@@ -65,6 +65,11 @@ class QuantumStateExponentialIntegrator(_QuantumIntegrator):
     unitary = False
 
 
+class DensityOperatorExponentialIntegrator(QuantumStateExponentialIntegrator):
+    """density_operator_smooth_pulse_problem.jl:104-106: vec(rho)~_{t+1} = exp(dt G(a_t)) vec(rho)~_t with the Lindbladian of an
+    `OpenQuantumSystem` -- the ket exponential integrator on N^2 levels (state = iso-vec [Re vec(rho); Im vec(rho)])."""
+
+
 class DerivativeIntegrator(AbstractIntegrator):
     kind = _lib.QCK_DERIVATIVE
 
