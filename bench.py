@@ -255,6 +255,25 @@ def time_e2e(D, Zs, mus, F, J, H, min_seconds, min_steps=5, max_steps=400):
     return dt, steps, D.transfer_stats()
 
 
+def pcie_peak_gbs(dev, mb=256):
+    """Pinned D2H / H2D copy rate of this box's link, measured live (GB/s each way): the denominator of the pcie sub-roofline."""
+    import torch
+    n = mb * (1 << 20) // 8
+    hbuf = torch.empty(n, dtype=torch.float64).pin_memory()
+    dbuf = torch.empty(n, dtype=torch.float64, device=dev)
+    out = {}
+    for name, (dst, src) in (("d2h", (hbuf, dbuf)), ("h2d", (dbuf, hbuf))):
+        best = 0.0
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, n * 8 / (time.perf_counter() - t0) * 1e-9)
+        out[name] = best
+    return out
+
+
 def expand_only_gbs(D, nb):
     """The host half alone (compact layout -> caller arrays, no GPU): what the host threads and memory system can absorb."""
     bufs, out_bytes = [], 0
@@ -312,6 +331,44 @@ def extra_records(args, dev, stream, n_gpus, rank0_devices):
     out["sampling_256_T200"] = rec
     rec, _ = dev_arm("hadamard", 100000, "pade")
     out["hadamard_T100000"] = rec
+    return out
+
+
+def extra_ensemble(args, n_gpus):
+    """BASELINE configs[4]: UnitarySamplingProblem, 256 sampled systems on a 4-level transmon, the ensemble split over the GPUs of
+    ONE handle (strong scaling: same problem, more GPUs).  Device-resident: kernels + the sum of the shared-control Hessian
+    entries over peer memory; e2e: host buffers through qck_eval_all."""
+    import qcknot
+    from qcknot import workloads as wl
+    out = {}
+    for T in (200, 2000):
+        a2 = argparse.Namespace(**vars(args))
+        a2.workload, a2.T, a2.integrator, a2.systems = "sampling", T, "pade", 256
+        systems, traj, integrators = build_problem(a2, 1)
+        D = qcknot.QuantumDynamics(integrators, traj, device=0, n_gpus=n_gpus, shard_mode="ensemble") if n_gpus > 1 else \
+            qcknot.QuantumDynamics(integrators, traj, device=0)
+        nb = D.n_blocks
+        Z = np.ascontiguousarray(traj.datavec[: traj.T * D.zdim])
+        mu = wl.random_multipliers(nb * D.dyn)
+        D.upload(Z, mu)
+        for _ in range(3):
+            D.eval_resident(7)
+        D.synchronize()
+        reps = 20 if T == 200 else 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            D.eval_resident(7)
+        D.synchronize()
+        dev_s = (time.perf_counter() - t0) / reps
+        Fh, Jh, Hh = np.empty(nb * D.dyn), np.empty(nb * D.nnzJ), np.empty(nb * D.nnzH)
+        Zs, mus = [Z, Z + 1e-7], [mu, wl.random_multipliers(nb * D.dyn, seed=7)]
+        e2e_s, steps, st = time_e2e(D, Zs, mus, Fh, Jh, Hh, 0.3, min_steps=3, max_steps=40)
+        out[f"T{T}"] = {"knot_blocks": nb, "systems": 256, "n_gpus": n_gpus,
+                        "device_us_per_pass": dev_s * 1e6, "device_knot_evals_per_s": nb / dev_s,
+                        "device_timing": "host wall clock around eval_resident x reps + synchronize (one caller, all GPUs)",
+                        "e2e_ms_per_step": e2e_s * 1e3, "e2e_knot_evals_per_s": nb / e2e_s, "e2e_steps": steps,
+                        "d2h_bytes_per_step": int(st["d2h_bytes"])}
+        D.close()
     return out
 
 
@@ -388,6 +445,7 @@ def main():
             Ze = [Z0, Z0 + 1e-7]
             mue = [wl.random_multipliers(nbe * D.dyn, seed=1234), wl.random_multipliers(nbe * D.dyn, seed=99)]
         Fh, Jh, Hh = np.empty(nbe * D.dyn), np.empty(nbe * D.nnzJ), np.empty(nbe * max(D.nnzH, 1))
+        link = pcie_peak_gbs(dev)
         e2e_s, e2e_steps, st = time_e2e(De, Ze, mue, Fh, Jh, Hh, args.min_seconds)
         moved = st["h2d_bytes"] + st["d2h_bytes"]
         written = Fh.nbytes + Jh.nbytes + Hh.nbytes
@@ -397,7 +455,10 @@ def main():
                "inputs": "pageable numpy arrays, two alternating trajectories (no cache hits)",
                "timing": "host wall clock around synchronous calls",
                "pcie": {"bytes_per_step": int(moved), "achieved_gbs": moved / e2e_s * 1e-9, "links": n_gpus,
-                        "peak_gbs": PCIE_PEAK_GBS * n_gpus, "frac": moved / e2e_s * 1e-9 / (PCIE_PEAK_GBS * n_gpus),
+                        "d2h_achieved_gbs": st["d2h_bytes"] / e2e_s * 1e-9,
+                        "peak_gbs": link["d2h"] * n_gpus, "frac": st["d2h_bytes"] / e2e_s * 1e-9 / (link["d2h"] * n_gpus),
+                        "peak_source": f"pinned 256 MB copies measured in this run on GPU 0: D2H {link['d2h']:.1f} GB/s, H2D {link['h2d']:.1f} GB/s "
+                                       f"(round-1 box: {PCIE_PEAK_GBS} GB/s); frac = D2H bytes / e2e time / D2H peak (H2D runs the other way, concurrently)",
                         "full_layout_bytes": int(written + Ze[0].nbytes + mue[0].nbytes)}}
         exp_gbs = expand_only_gbs(De, min(nbe, 9999))
         host = {"written_bytes_per_step": int(written), "written_gbs": written / e2e_s * 1e-9, "expand_only_gbs": exp_gbs,
@@ -437,6 +498,13 @@ def main():
                 extra_multi = {"error": str(ex)}
             e2e["gather"] = extra_multi
             De.close()
+        if not args.no_extra:
+            try:
+                e2e_ens = extra_ensemble(args, n_gpus)
+            except Exception as ex:  # noqa: BLE001
+                e2e_ens = {"error": str(ex)}
+        else:
+            e2e_ens = None
     if host_group is not None:
         dist.barrier(group=host_group)
 
@@ -446,6 +514,7 @@ def main():
             extra = extra_records(args, dev, stream, n_gpus, None)
         except Exception as ex:  # noqa: BLE001
             extra = {"error": str(ex)}
+        extra["ensemble_sampling_256"] = e2e_ens
     if host_group is not None:
         dist.barrier(group=host_group)
 

@@ -14,7 +14,8 @@
 //   state x dt: -(1/2 W1 +- h/6 A^H W1), W1 = A^H M       state x a_j: -(h/2 Z1 +- h^2/12 (A_j^H W1 + A^H Z1)), Z1 = A_j^H M
 //   dt x dt = 1/6 Re<W1, A D>    a_j x dt = -1/2 Re<Z1_j, S> + h/6 (Re<Z1_j, A D> + Re<W1, A_j D>)
 //   a_i x a_j = h^2/12 Re tr({A_i, A_j} G),  G = D M^H
-// 6 + 2 n_d dense N x N x nc products (+ 2 for the blocks, + G), register tiles of 2 x 2 complex, drives as sparse rows.
+// 6 + 2 n_d dense N x N x nc products (+ A^2 for the blocks: iso(B) follows from -iso(F) in place; + G), register tiles of
+// 2 x 2 complex, drives as sparse rows; two vertically adjacent results leave as one 16-byte store per part.
 #include <algorithm>
 
 #include "qck_device.cuh"
@@ -33,6 +34,7 @@ __device__ __forceinline__ double big_block_sum(double v, double* sh) {  // resu
 }
 
 // C[r][c] = sum_k op(A)[r][k] B[k][c],  op = conjugate transpose when adj.  A: N x N, B: N x nc, column-major (ld = N).
+// The epilogue gets two vertically adjacent results at a time: epi(r, c, C[r][c], C[r+1][c], second row valid).
 template <class Epi>
 __device__ __forceinline__ void big_mm(const double2* __restrict__ A, bool adj, const double2* __restrict__ B, int N, int nc, Epi epi) {
     const int ntr = (N + 1) >> 1, ntc = (nc + 1) >> 1;
@@ -48,10 +50,8 @@ __device__ __forceinline__ void big_mm(const double2* __restrict__ A, bool adj, 
             const double2 y0 = B[k + N * c0], y1 = B[k + N * c1];
             cfma(a00, x0, y0); cfma(a01, x0, y1); cfma(a10, x1, y0); cfma(a11, x1, y1);
         }
-        epi(r0, c0, a00);
-        if (c1ok) epi(r0, c1, a01);
-        if (r1ok) epi(r1, c0, a10);
-        if (r1ok && c1ok) epi(r1, c1, a11);
+        epi(r0, c0, a00, a10, r1ok);  // rows r0, r0 + 1 of one column: neighbours in every iso-vector quantity
+        if (c1ok) epi(r0, c1, a01, a11, r1ok);
     }
 }
 
@@ -101,17 +101,25 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
         const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
         const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
         // iso-vector quantity q, element (r, col): real part at (col * 2N + r), imaginary part N further
-        auto put = [&](double* arr0, int d0, int q, int r, int col, double2 v) {
+        // rows r, r + 1 of one column: two consecutive reals and two consecutive imaginaries -> 16-byte stores where aligned
+        auto put = [&](double* arr0, int d0, int q, int r, int col, double2 v0, double2 v1, bool two) {
             const int st = c.pl_stride[q], i = col * n2 + r;
-            arr0[d0 + i * st] = v.x;
-            arr0[d0 + (i + N) * st] = v.y;
+            double* pr = arr0 + d0 + i * st;
+            double* pi = arr0 + d0 + (i + N) * st;
+            if (two && st == 1 && !(reinterpret_cast<uintptr_t>(pr) & 15) && !(reinterpret_cast<uintptr_t>(pi) & 15)) {
+                *reinterpret_cast<double2*>(pr) = make_double2(v0.x, v1.x);
+                *reinterpret_cast<double2*>(pi) = make_double2(v0.y, v1.y);
+            } else {
+                pr[0] = v0.x; pi[0] = v0.y;
+                if (two) { pr[st] = v1.x; pi[st] = v1.y; }
+            }
         };
-        auto putJ = [&](int q, int r, int col, double2 v) { const int d0 = qd[q]; if (d0 >= 0) put(oJ, d0, q, r, col, v); };
-        auto putH = [&](int q, int r, int col, double2 v) {
+        auto putJ = [&](int q, int r, int col, double2 v0, double2 v1, bool two) { const int d0 = qd[q]; if (d0 >= 0) put(oJ, d0, q, r, col, v0, v1, two); };
+        auto putH = [&](int q, int r, int col, double2 v0, double2 v1, bool two) {
             const int d0 = qd[q];
             if (d0 < 0) return;
-            if (d0 < p.nnzH) put(oH, d0, q, r, col, v);
-            else put(oP, d0 - (int)p.nnzH, q, r, col, v);
+            if (d0 < p.nnzH) put(oH, d0, q, r, col, v0, v1, two);
+            else put(oP, d0 - (int)p.nnzH, q, r, col, v0, v1, two);
         };
         auto put_scalar = [&](int q, double v) {
             const int d0 = qd[q];
@@ -153,24 +161,29 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
         if (mi == 0 && p.n_aux) do_aux(p, t, tid, blockDim.x);  // derivative-integrator entries of this knot
         __syncthreads();
         // ---- S1: A D (-> V, V'), A^H M ------------------------------------------------------------------------------------------
-        big_mm(mA, false, mD, N, nc, [&](int r, int col, double2 acc) {
-            const int e = r + N * col;
-            const double2 s = mS[e];
-            mX2[e] = acc;
-            mV[e] = make_double2(-c1h * s.x + c2h2 * acc.x, -c1h * s.y + c2h2 * acc.y);
-            T1[e] = make_double2(-0.5 * s.x + c2h * acc.x, -0.5 * s.y + c2h * acc.y);
+        big_mm(mA, false, mD, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+            for (int i = 0; i < (two ? 2 : 1); ++i) {
+                const int e = r + i + N * col;
+                const double2 acc = i ? a1 : a0, s = mS[e];
+                mX2[e] = acc;
+                mV[e] = make_double2(-c1h * s.x + c2h2 * acc.x, -c1h * s.y + c2h2 * acc.y);
+                T1[e] = make_double2(-0.5 * s.x + c2h * acc.x, -0.5 * s.y + c2h * acc.y);
+            }
         });
-        if (needH) big_mm(mA, true, mM, N, nc, [&](int r, int col, double2 acc) { mW1[r + N * col] = acc; });
+        if (needH) big_mm(mA, true, mM, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+            mW1[r + N * col] = a0;
+            if (two) mW1[r + 1 + N * col] = a1;
+        });
         __syncthreads();
         // ---- S2: residual and d/dh --------------------------------------------------------------------------------------------------
         if (needF) {
             const int d0 = qd[QO_R];
-            big_mm(mA, false, mV, N, nc, [&](int r, int col, double2 acc) {
-                const double2 d = mD[r + N * col];
-                if (d0 >= 0) put(oF, d0, QO_R, r, col, make_double2(d.x + acc.x, d.y + acc.y));
+            big_mm(mA, false, mV, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+                const double2 d0v = mD[r + N * col], d1v = two ? mD[r + 1 + N * col] : make_double2(0.0, 0.0);
+                if (d0 >= 0) put(oF, d0, QO_R, r, col, make_double2(d0v.x + a0.x, d0v.y + a0.y), make_double2(d1v.x + a1.x, d1v.y + a1.y), two);
             });
         }
-        if (needJ && free_time) big_mm(mA, false, T1, N, nc, [&](int r, int col, double2 acc) { putJ(QO_TH, r, col, acc); });
+        if (needJ && free_time) big_mm(mA, false, T1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) { putJ(QO_TH, r, col, a0, a1, two); });
         if (needH && free_time) {
             double sloc = 0.0;
             for (int e = tid; e < NS; e += blockDim.x) sloc += rdot(mW1[e], mX2[e]);
@@ -181,25 +194,10 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
         // ---- S3: the kron blocks -iso(F), +iso(B) (A^2 once per block: no spare N x N matrix to keep it) ----------------------------------
         if (needJ) {
             double* const blk = reinterpret_cast<double*>(T1);  // 2N x 2N reals, column-major: [variable column][row]
-            for (int which = 0; which < 2; ++which) {
-                const int q = which ? QO_ISOB : QO_ISOF;
+            const int bl = n2 * n2, ncopy = KET ? 1 : N;
+            auto copy_out = [&](int q) {  // the block N times, 16-byte stores by the whole CTA
                 const int d0 = qd[q];
-                if (d0 < 0) continue;
-                const double sg = which ? -1.0 : 1.0;  // B = I - h/2 A + ..., stored +iso(B); F stored -iso(F)
-                big_mm(mA, false, mA, N, N, [&](int r, int col, double2 acc) {
-                    const double2 a = mA[r + N * col];
-                    const double id = r == col ? 1.0 : 0.0;
-                    const double xr = id + sg * c1h * a.x + c2h2 * acc.x, xi = sg * c1h * a.y + c2h2 * acc.y;
-                    const double o = which ? 1.0 : -1.0;
-                    // iso(X) = [Re X, -Im X; Im X, Re X]: column `col` holds (Re; Im), column `col + N` holds (-Im; Re)
-                    blk[r + n2 * col] = o * xr;
-                    blk[r + N + n2 * col] = o * xi;
-                    blk[r + n2 * (col + N)] = -o * xi;
-                    blk[r + N + n2 * (col + N)] = o * xr;
-                });
-                __syncthreads();
-                const int bl = n2 * n2;
-                const int ncopy = KET ? 1 : N;
+                if (d0 < 0) return;
                 double* dst0 = oJ + d0;
                 if ((reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
                     const double2* s2 = reinterpret_cast<const double2*>(blk);
@@ -211,38 +209,72 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
                     for (int cb = 0; cb < ncopy; ++cb)
                         for (int i = tid; i < bl; i += blockDim.x) dst0[(size_t)cb * bl + i] = blk[i];
                 }
-                __syncthreads();
+            };
+            // -iso(F), F = I + h/2 A + h^2/12 A^2;  iso(X) = [Re X, -Im X; Im X, Re X]: column c holds (Re; Im), column c + N (-Im; Re)
+            big_mm(mA, false, mA, N, N, [&](int r, int col, double2 a0, double2 a1, bool two) {
+                for (int i = 0; i < (two ? 2 : 1); ++i) {
+                    const int rr = r + i;
+                    const double2 acc = i ? a1 : a0, a = mA[rr + N * col];
+                    const double xr = (rr == col ? 1.0 : 0.0) + c1h * a.x + c2h2 * acc.x, xi = c1h * a.y + c2h2 * acc.y;
+                    blk[rr + n2 * col] = -xr;
+                    blk[rr + N + n2 * col] = -xi;
+                    blk[rr + n2 * (col + N)] = xi;
+                    blk[rr + N + n2 * (col + N)] = -xr;
+                }
+            });
+            __syncthreads();
+            copy_out(QO_ISOF);
+            __syncthreads();
+            // +iso(B), B = F - h A:  iso(B) = -(-iso(F)) - h iso(A), in place
+            for (int e = tid; e < NN; e += blockDim.x) {
+                const int rr = e % N, col = e / N;
+                const double2 a = mA[e];
+                const double hr = h * a.x, hi = h * a.y;
+                blk[rr + n2 * col] = -blk[rr + n2 * col] - hr;
+                blk[rr + N + n2 * col] = -blk[rr + N + n2 * col] - hi;
+                blk[rr + n2 * (col + N)] = -blk[rr + n2 * (col + N)] + hi;
+                blk[rr + N + n2 * (col + N)] = -blk[rr + N + n2 * (col + N)] - hr;
             }
+            __syncthreads();
+            copy_out(QO_ISOB);
+            __syncthreads();
         }
         // ---- S4: d/da_j ---------------------------------------------------------------------------------------------------------------
         for (int j = 0; j < nd && (needJ || needH); ++j) {
             double s_ah = 0.0;
-            for (int e = tid; e < NS; e += blockDim.x) {  // U_j = A_j D
+            for (int e = tid; e < NS; e += blockDim.x) {  // U_j = A_j D -> T1,  A_j V -> T2
                 const int r = e % N, col = e / N;
                 const double2 u = drive_elem(j, 0, mD, r, col);
                 T1[e] = u;
+                if (needJ) T2[e] = drive_elem(j, 0, mV, r, col);
                 if (needH) s_ah += c2h * rdot(mW1[e], u);
             }
             __syncthreads();
-            if (needJ) big_mm(mA, false, T1, N, nc, [&](int r, int col, double2 acc) {
-                const double2 y = drive_elem(j, 0, mV, r, col);
-                putJ(QO_TA + j, r, col, make_double2(y.x + c2h2 * acc.x, y.y + c2h2 * acc.y));
+            if (needJ) big_mm(mA, false, T1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+                const double2 y0 = T2[r + N * col], y1 = two ? T2[r + 1 + N * col] : make_double2(0.0, 0.0);
+                putJ(QO_TA + j, r, col, make_double2(y0.x + c2h2 * a0.x, y0.y + c2h2 * a0.y), make_double2(y1.x + c2h2 * a1.x, y1.y + c2h2 * a1.y), two);
             });
             __syncthreads();
-            if (needH) {  // Z1_j = A_j^H M; state x a_j blocks; a_j x dt
+            if (needH) {  // Z1_j = A_j^H M -> T1,  A_j^H W1 -> T2; state x a_j blocks; a_j x dt
                 for (int e = tid; e < NS; e += blockDim.x) {
                     const int r = e % N, col = e / N;
                     const double2 z1 = drive_elem(j, 1, mM, r, col);
                     T1[e] = z1;
+                    T2[e] = drive_elem(j, 1, mW1, r, col);
                     s_ah += -0.5 * rdot(z1, mS[e]) + c2h * rdot(z1, mX2[e]);
                 }
                 __syncthreads();
-                big_mm(mA, true, T1, N, nc, [&](int r, int col, double2 acc) {
-                    const double2 z1 = T1[r + N * col];
-                    const double2 z2 = drive_elem(j, 1, mW1, r, col);
-                    const double cr = c2h2 * (z2.x + acc.x), ci = c2h2 * (z2.y + acc.y);
-                    putH(QO_KA0 + j, r, col, make_double2(-c1h * z1.x - cr, -c1h * z1.y - ci));
-                    putH(QO_KA1 + j, r, col, make_double2(-c1h * z1.x + cr, -c1h * z1.y + ci));
+                big_mm(mA, true, T1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+                    double2 k0[2], k1[2];
+                    for (int i = 0; i < (two ? 2 : 1); ++i) {
+                        const int e = r + i + N * col;
+                        const double2 acc = i ? a1 : a0, z1 = T1[e], z2 = T2[e];
+                        const double cr = c2h2 * (z2.x + acc.x), ci = c2h2 * (z2.y + acc.y);
+                        k0[i] = make_double2(-c1h * z1.x - cr, -c1h * z1.y - ci);
+                        k1[i] = make_double2(-c1h * z1.x + cr, -c1h * z1.y + ci);
+                    }
+                    putH(QO_KA0 + j, r, col, k0[0], k0[1], two);
+                    putH(QO_KA1 + j, r, col, k1[0], k1[1], two);
                 });
                 if (free_time) {
                     const double tot = big_block_sum(s_ah, red);
@@ -253,10 +285,15 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
         }
         // ---- S5: state x dt, a_i x a_j ------------------------------------------------------------------------------------------------------
         if (needH) {
-            if (free_time) big_mm(mA, true, mW1, N, nc, [&](int r, int col, double2 acc) {
-                const double2 w1 = mW1[r + N * col];
-                putH(QO_KH0, r, col, make_double2(-0.5 * w1.x - c2h * acc.x, -0.5 * w1.y - c2h * acc.y));
-                putH(QO_KH1, r, col, make_double2(-0.5 * w1.x + c2h * acc.x, -0.5 * w1.y + c2h * acc.y));
+            if (free_time) big_mm(mA, true, mW1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+                double2 k0[2], k1[2];
+                for (int i = 0; i < (two ? 2 : 1); ++i) {
+                    const double2 acc = i ? a1 : a0, w1 = mW1[r + i + N * col];
+                    k0[i] = make_double2(-0.5 * w1.x - c2h * acc.x, -0.5 * w1.y - c2h * acc.y);
+                    k1[i] = make_double2(-0.5 * w1.x + c2h * acc.x, -0.5 * w1.y + c2h * acc.y);
+                }
+                putH(QO_KH0, r, col, k0[0], k0[1], two);
+                putH(QO_KH1, r, col, k1[0], k1[1], two);
             });
             for (int e = tid; e < NN; e += blockDim.x) {  // G[r][q] = sum_c D[r][c] conj(M[q][c])
                 const int r = e % N, q = e / N;

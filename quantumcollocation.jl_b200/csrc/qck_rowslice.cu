@@ -1,5 +1,8 @@
 // Row-slice kernel (9-level Pade-4 unitaries, one warp per knot) of libqcknot.so.  Compiled as its own translation unit so that the kernel families build in parallel.
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "qck_device.cuh"
 
@@ -29,12 +32,16 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 // WC: compile-time width of the sparse rows of the drives (loops fully unrolled); 0 = dense drive matrices
 // AH: A is anti-Hermitian (Hermitian Hamiltonians): A^H x = -(A x) runs on the register-resident rows of A
-template <int ND, int WC, bool AH>
-__global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p) {
+// BW: "block warps".  The two kron(I_N, .) blocks -iso(F), iso(B) are 69 % of a knot's bytes but need only A and A^2: four extra
+//     warps per CTA (a third warpgroup that hands its registers to the eight computing warps with setmaxnreg) assemble A, form the
+//     blocks in their own small buffers and issue the 2 x N bulk copies, on their own schedule -- no handshake with the computing
+//     warps, which drop the A^2 product, the block stores and 18 of their 24 blocking bulk-copy issues per knot.
+template <int ND, int WC, bool AH, bool BW>
+__global__ void __launch_bounds__(BW ? 384 : 256, 1) qck_rowslice9_kernel(const QckLaunch p) {
     constexpr int N = 9, NN = 81, n2 = 18, dim = 162;
     extern __shared__ __align__(16) unsigned char smem_all[];
     const QckClassDev& c = p.c;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = BW ? 8 : (int)(blockDim.x >> 5);
     const bool act = lane < 3 * N;
     const int cc = act ? lane / 3 : 0, k3 = act ? 3 * (lane - 3 * (lane / 3)) : 0;  // column, first row of this lane
     const bool needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
@@ -58,7 +65,9 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
     const int img_bytes = p.db ? jbytes + hbytes : (jbytes > hbytes ? jbytes : hbytes);
     QckAux* const auxs = reinterpret_cast<QckAux*>(segtab + nrec);   // derivative-integrator entries (CTA-wide copy)
     double2* const cAj = reinterpret_cast<double2*>(auxs + p.n_aux);  // WC == 0: dense A_j, row-major
-    unsigned char* const wbase = reinterpret_cast<unsigned char*>(cAj + (WC > 0 ? 0 : ND * NN)) + (size_t)warp * (img_bytes + 7 * NN * 16);
+    unsigned char* const wbase0 = reinterpret_cast<unsigned char*>(cAj + (WC > 0 ? 0 : ND * NN));
+    constexpr int kWarpExtra = ND * 32 * 8;  // per-lane partial sums of the a_j x dt entries, carried from phase 1 to phase 2
+    unsigned char* const wbase = wbase0 + (size_t)(warp < nwarps ? warp : 0) * (img_bytes + 7 * NN * 16 + kWarpExtra);
     double* const stage = reinterpret_cast<double*>(wbase);
     double* const stageH = p.db ? stage + jbytes / 8 : stage;
     double2* const vD = reinterpret_cast<double2*>(wbase + img_bytes);  // columns of D = U1 - U0: element [c * 9 + r]
@@ -69,6 +78,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
     double2* const vU = vW1 + NN;      // A_j D (current drive)
     double2* const vZ1 = vU;           // A_j^H M (current drive; phase 2 only, when A_j D is dead)
     double2* const mA = vU + NN;       // A, row-major (for A^H products and column access)
+    double* const sah = reinterpret_cast<double*>(mA + NN) + lane;  // [drive][lane]
     {
         const double2* gv = c.cmat + (size_t)m * c.cmat_stride;
         const int* gc = c.ell_col + (size_t)m * c.icon_stride;
@@ -76,7 +86,8 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
         for (int e = threadIdx.x; e < c.icon_stride; e += blockDim.x) coni[e] = gc[e];
         const QckSeg* gs = c.segs + (size_t)m * nrec;
         for (int i = threadIdx.x; i < nrec; i += blockDim.x) segtab[i] = gs[i];
-        for (int i = lane; i < img_bytes / 8; i += 32) stage[i] = 0.0;
+        if (warp < nwarps)
+            for (int i = lane; i < img_bytes / 8; i += 32) stage[i] = 0.0;
         for (int i = threadIdx.x; i < p.n_aux; i += blockDim.x) auxs[i] = p.aux[i];
         if (WC == 0) {
             for (int e = threadIdx.x; e < ND * NN; e += blockDim.x) cAj[e] = make_double2(0.0, 0.0);
@@ -103,6 +114,79 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
     const QckSeg* segs = segtab + QCK_SEG_HDR / 4;
     const int soff = p.moff_global[0], coff = p.moff_global[1], roff = p.moff_global[2];
     const int xo = cc * N;  // this lane's column inside the vector buffers
+
+    if constexpr (BW) {
+        if (warp >= 8) {
+            // ---- block warps: -iso(F), +iso(B) of the knots of this CTA, N copies each, straight from their own buffers ------------
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+            if (!needJ) return;
+            const int lw = warp - 8;
+            double* const bufF = reinterpret_cast<double*>(wbase0 + (size_t)8 * (img_bytes + 7 * NN * 16 + kWarpExtra)) + (size_t)lw * (2 * 328 + 2 * NN);
+            double* const bufB = bufF + 328;
+            double2* const sA = reinterpret_cast<double2*>(bufB + 328);  // A, row-major
+            const int imgF = c.pl_base[QO_ISOF];
+            const int u0 = seghdr[11], u1 = seghdr[12];
+            int dF0 = 0, dB0 = 0;  // first destination of either block inside the knot block (parity of the copies)
+            for (int u = u0; u < u1; ++u) {
+                const QckSeg sg = segs[u];
+                if ((sg.img_nrep & 0xffff) == imgF) { dF0 = sg.dst; break; }
+            }
+            for (int u = u0; u < u1; ++u) {
+                const QckSeg sg = segs[u];
+                if ((sg.img_nrep & 0xffff) != imgF) { dB0 = sg.dst; break; }
+            }
+            for (long long t = (long long)lw * gridDim.x + blockIdx.x; t < p.n_knots; t += (long long)gridDim.x * 4) {
+                const double* zt = p.Z + t * c.zdim;
+                const double h = free_time ? __ldg(zt + c.dt_off) : c.dt_fixed;
+                const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0);
+                for (int e = lane; e < NN; e += 32) {
+                    double2 v = A0[e];
+                    for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
+                        const double aj = __ldg(zt + coff + acj[u]);
+                        const double2 d = acv[u];
+                        v.x = fma(aj, d.x, v.x);
+                        v.y = fma(aj, d.y, v.y);
+                    }
+                    sA[(e % N) * N + e / N] = v;  // A0 is column-major
+                }
+                double* const baseJ = p.J + t * p.nnzJ;
+                const int pF = (int)((reinterpret_cast<uintptr_t>(baseJ + dF0) >> 3) & 1), pB = (int)((reinterpret_cast<uintptr_t>(baseJ + dB0) >> 3) & 1);
+                bulk_wait_read();  // the previous knot's copies have left the buffers
+                __syncwarp();
+                for (int e = lane; e < NN; e += 32) {
+                    const int r = e % N, col = e / N;
+                    double2 a2 = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) cfma(a2, sA[r * N + k], sA[k * N + col]);
+                    const double2 av = sA[r * N + col];
+                    const double id = r == col ? 1.0 : 0.0;
+                    const double fr = id + c1h * av.x + c2h2 * a2.x, fi = c1h * av.y + c2h2 * a2.y;
+                    const double br = id - c1h * av.x + c2h2 * a2.x, bi = -c1h * av.y + c2h2 * a2.y;
+                    const int k00 = r + n2 * col, k01 = r + n2 * (col + N);
+                    double* const iF = bufF + pF;
+                    double* const iB = bufB + pB;
+                    iF[k00] = -fr; iF[k00 + N] = -fi; iF[k01] = fi; iF[k01 + N] = -fr;
+                    iB[k00] = br;  iB[k00 + N] = bi;  iB[k01] = -bi; iB[k01 + N] = br;
+                }
+                fence_async_smem();
+                __syncwarp();
+                for (int u = u0 + lane; u < u1; u += 32) {  // one lane, one copy of one block
+                    const QckSeg sg = segs[u];
+                    double* dst = baseJ + sg.dst;
+                    const bool isF = (sg.img_nrep & 0xffff) == imgF;
+                    const double* src = isF ? bufF + pF : bufB + pB;
+                    const int n = sg.n, head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1), body = (n - head) & ~1;
+                    if (head) dst[0] = src[0];
+                    if (body) bulk_store(dst + head, src + head, (unsigned)body * 8u);
+                    if (head + body < n) dst[n - 1] = src[n - 1];
+                }
+                bulk_commit();
+            }
+            bulk_wait_all();
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    }
 
     // warp-major slots: the last, partially filled round spreads over all SMs (fewer active warps per SM run faster each)
     for (long long t = (long long)warp * gridDim.x + blockIdx.x; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
@@ -212,9 +296,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
             }
         };
 
-        double s_hh = 0.0, s_ah[ND];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) s_ah[j] = 0.0;
+        double s_hh = 0.0;
         double2 w1[3];
         {
             double2 x1[3], x2[3], x3[3];
@@ -249,7 +331,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 put(imgJ, QO_TH, i, make_double2(-0.5 * x1[i].x + c2h * x3[i].x, -0.5 * x1[i].y + c2h * x3[i].y));
             }
         }
-        if (needJ) {  // column cc of A^2 -> -iso(F), +iso(B)
+        if (needJ && !BW) {  // column cc of A^2 -> -iso(F), +iso(B)  (BW: the block warps do this)
             double2 a2[3], acol[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) acol[j] = mA[j * N + cc];
@@ -275,7 +357,9 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
             }
         }
         if (needJ) {  // (a Hessian-only call gets its A_j d inside the Hessian loop and skips this one)
-#pragma unroll
+            // (the drive loops are NOT unrolled: the straight-line kernel of round 1 was 110 KB of SASS and its warps stalled on
+            //  instruction fetch -- no_instruction 1.0-1.4 per issue, profiles/r02_*)
+#pragma unroll 1
             for (int j = 0; j < ND; ++j) {
                 double2 y[3], u[3], y3[3];
 #pragma unroll
@@ -316,16 +400,19 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 __syncwarp();
                 mv_reg(y3, vU + xo);
 #pragma unroll
+                double sp = 0.0;
+#pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     put(imgJ, QO_TA + j, i, make_double2(y[i].x + c2h2 * y3[i].x, y[i].y + c2h2 * y3[i].y));
-                    if (needH && act) s_ah[j] += c2h * rdot(w1[i], u[i]);
+                    if (needH && act) sp += c2h * rdot(w1[i], u[i]);
                 }
+                if (needH) sah[j * 32] = sp;
             }
         }
         if (p.n_aux) do_aux_smem(p, auxs, t, lane, 32);  // derivative-integrator entries of this knot
         fence_async_smem();
         __syncwarp();
-        if (p.spread && needJ) flush_units_lanes(stage, segs, seghdr[12], seghdr[13], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
+        if (BW || (p.spread && needJ)) flush_units_lanes(stage, segs, seghdr[12], seghdr[13], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
         else flush_units_lanes(stage, segs, seghdr[0], seghdr[3], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & (QCK_EVAL_F | QCK_EVAL_J));
         bulk_commit();
         __syncwarp();
@@ -341,8 +428,9 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 put(imgH, QO_KH0, i, make_double2(-0.5 * w1[i].x - c2h * w2[i].x, -0.5 * w1[i].y - c2h * w2[i].y));
                 put(imgH, QO_KH1, i, make_double2(-0.5 * w1[i].x + c2h * w2[i].x, -0.5 * w1[i].y + c2h * w2[i].y));
             }
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < ND; ++j) {
+                double sp = needJ ? sah[j * 32] : 0.0;
                 double2 z1[3], z2[3], z3[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) z1[i] = z2[i] = make_double2(0.0, 0.0);
@@ -395,7 +483,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                     }
                     if (act) {
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) s_ah[j] += c2h * rdot(w1[i], u[i]);
+                        for (int i = 0; i < 3; ++i) sp += c2h * rdot(w1[i], u[i]);
                     }
                 }
                 __syncwarp();  // the previous drive's readers of vZ1 are done
@@ -410,8 +498,10 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                     const double cr = c2h2 * (z2[i].x + z3[i].x), ci = c2h2 * (z2[i].y + z3[i].y);
                     put(imgH, QO_KA0 + j, i, make_double2(-c1h * z1[i].x - cr, -c1h * z1[i].y - ci));
                     put(imgH, QO_KA1 + j, i, make_double2(-c1h * z1[i].x + cr, -c1h * z1[i].y + ci));
-                    if (act) s_ah[j] += -0.5 * rdot(z1[i], vS[xo + k3 + i]) + c2h * rdot(z1[i], vX2[xo + k3 + i]);
+                    if (act) sp += -0.5 * rdot(z1[i], vS[xo + k3 + i]) + c2h * rdot(z1[i], vX2[xo + k3 + i]);
                 }
+                sp = warp_sum(sp);
+                if (lane == 0 && c.pl_base[QO_HAH + j] >= 0) imgH[c.pl_base[QO_HAH + j]] = sp;
             }
             // a_i x a_j = h^2/12 Re tr({A_i, A_j} G),  G = D M^H (one more row-slice product, into the idle A_j D buffer);
             // the constant sparse anticommutators come as (row, column, value) lists, three lanes per pair
@@ -449,14 +539,7 @@ __global__ void __launch_bounds__(256, 1) qck_rowslice9_kernel(const QckLaunch p
                 if (c.pl_base[q] >= 0) imgH[c.pl_base[q]] = c2h2 * (val + v1 + v2);
             }
             s_hh = warp_sum(s_hh);
-#pragma unroll
-            for (int j = 0; j < ND; ++j) s_ah[j] = warp_sum(s_ah[j]);
-            if (lane == 0) {
-                if (c.pl_base[QO_HHH] >= 0) imgH[c.pl_base[QO_HHH]] = s_hh * (1.0 / 6.0);
-#pragma unroll
-                for (int j = 0; j < ND; ++j)
-                    if (c.pl_base[QO_HAH + j] >= 0) imgH[c.pl_base[QO_HAH + j]] = s_ah[j];
-            }
+            if (lane == 0 && c.pl_base[QO_HHH] >= 0) imgH[c.pl_base[QO_HHH]] = s_hh * (1.0 / 6.0);
             fence_async_smem();
             __syncwarp();
             flush_units_lanes(stageH, segs, seghdr[4], seghdr[7], lane, baseF, baseJ, baseH, shF, shJ, shH, hoff, p.mask & QCK_EVAL_H);
@@ -480,10 +563,6 @@ int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, 
     static const int sparse_ok = getenv("QCK_ROWSLICE_DENSE") ? 0 : 1;
     const int wc = sparse_ok && c.W <= 2 ? c.W : 0;  // sparse drive rows of width 1 or 2 are unrolled; wider ones run dense
     kern_t kern;
-#define QCK_RS(ND_) (c.antiherm ? (wc == 1 ? qck_rowslice9_kernel<ND_, 1, true> : (wc == 2 ? qck_rowslice9_kernel<ND_, 2, true> : qck_rowslice9_kernel<ND_, 0, true>)) \
-                                 : (wc == 1 ? qck_rowslice9_kernel<ND_, 1, false> : (wc == 2 ? qck_rowslice9_kernel<ND_, 2, false> : qck_rowslice9_kernel<ND_, 0, false>)))
-    kern = c.nd == 1 ? QCK_RS(1) : (c.nd == 2 ? QCK_RS(2) : (c.nd == 3 ? QCK_RS(3) : QCK_RS(4)));
-#undef QCK_RS
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;
     // staging: F + J part and Hessian part of the output image share one buffer (the Hessian part starts at hoff)
     const int hoff = qck_rs3_hoff(c);
@@ -498,27 +577,49 @@ int qck_launch_rowslice9(const QckLaunch& L, int sm_count, cudaStream_t stream, 
     static const int db_knob = getenv("QCK_ROWSLICE_DB") ? atoi(getenv("QCK_ROWSLICE_DB")) : 0;
     static const int knob = getenv("QCK_ROWSLICE_WARPS") ? atoi(getenv("QCK_ROWSLICE_WARPS")) : 0;
     int db = db_knob && (L.mask & QCK_EVAL_H) && (L.mask & (QCK_EVAL_F | QCK_EVAL_J)) ? 1 : 0;
-    size_t per_warp = (db ? jbytes + hbytes : std::max(jbytes, hbytes)) + 7 * 81 * 16;
-    if (db && shared + 4 * per_warp > 227 * 1024) { db = 0; per_warp = std::max(jbytes, hbytes) + 7 * 81 * 16; }
+    const size_t wextra = (size_t)c.nd * 32 * 8;
+    size_t per_warp = (db ? jbytes + hbytes : std::max(jbytes, hbytes)) + 7 * 81 * 16 + wextra;
+    if (db && shared + 4 * per_warp > 227 * 1024) { db = 0; per_warp = std::max(jbytes, hbytes) + 7 * 81 * 16 + wextra; }
+    // block warps: only when the Jacobian is asked for, the blocks are contiguous in the structure, and the drives are sparse
+    // (the dense-drive variants keep the plain kernel: fewer template instances)
+    static const int bw_knob = getenv("QCK_ROWSLICE_BW") ? atoi(getenv("QCK_ROWSLICE_BW")) : 1;
+    const size_t light_bytes = (size_t)4 * (2 * 328 * 8 + 2 * 81 * 8);  // block warps: two block buffers + A each
+    const bool bw = bw_knob && wc > 0 && (L.mask & QCK_EVAL_J) && !db && c.pl_stride[QO_ISOF] == 1 && c.pl_stride[QO_ISOB] == 1 && c.pl_base[QO_ISOF] >= 0 &&
+                    shared + 8 * per_warp + light_bytes <= 227 * 1024;
+#define QCK_RS3(ND_, WC_, AH_) (bw ? qck_rowslice9_kernel<ND_, WC_, AH_, true> : qck_rowslice9_kernel<ND_, WC_, AH_, false>)
+#define QCK_RS(ND_) (c.antiherm ? (wc == 1 ? QCK_RS3(ND_, 1, true) : (wc == 2 ? QCK_RS3(ND_, 2, true) : qck_rowslice9_kernel<ND_, 0, true, false>)) \
+                                 : (wc == 1 ? QCK_RS3(ND_, 1, false) : (wc == 2 ? QCK_RS3(ND_, 2, false) : qck_rowslice9_kernel<ND_, 0, false, false>)))
+    kern = c.nd == 1 ? QCK_RS(1) : (c.nd == 2 ? QCK_RS(2) : (c.nd == 3 ? QCK_RS(3) : QCK_RS(4)));
+#undef QCK_RS
+#undef QCK_RS3
     int nwarps = 8;
-    if (knob >= 1 && knob <= 8) nwarps = knob;
-    while (nwarps > 1 && shared + nwarps * per_warp > 227 * 1024) --nwarps;
-    const size_t smem = shared + nwarps * per_warp;
+    if (knob >= 1 && knob <= 8 && !bw) nwarps = knob;
+    const size_t light = bw ? light_bytes : 0;
+    while (nwarps > 1 && shared + nwarps * per_warp + light > 227 * 1024) --nwarps;
+    const size_t smem = shared + nwarps * per_warp + light;
     if (smem > 227 * 1024) return 0;
-    if (!(L.plan && L.plan->kern == (const void*)kern)) {  // once per handle: the largest opt-in size covers every mask
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = 227 * 1024; L.plan->per_sm = 1; }
+    {   // once per (device, kernel): the largest opt-in size covers every mask; masks with and without the Jacobian alternate
+        // between two kernels (with / without block warps), so the per-class plan cache (one kernel) is not enough here
+        static std::mutex mu;
+        static std::set<std::pair<int, const void*>> ready;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ready.count({dev, (const void*)kern})) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            ready.insert({dev, (const void*)kern});
+        }
     }
     long long grid = sm_count;
     if (grid * nwarps > L.n_knots) grid = (L.n_knots + nwarps - 1) / nwarps;
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
-    if (dbg) fprintf(stderr, "[qcknot] row-slice kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d two-buffers=%d early-blocks=%d\n", c.nd, nwarps, smem, grid, c.nseg, db, spread_knob);
+    if (dbg) fprintf(stderr, "[qcknot] row-slice kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d two-buffers=%d early-blocks=%d block-warps=%d\n", c.nd, nwarps, smem, grid, c.nseg, db, spread_knob, (int)bw);
     QckLaunch L2 = L;
     L2.hoff = hoff;
     L2.db = db;
     L2.spread = spread_knob;
-    kern<<<(unsigned)grid, nwarps * 32, smem, stream>>>(L2);
+    kern<<<(unsigned)grid, bw ? 384 : nwarps * 32, smem, stream>>>(L2);
     if (launches) ++*launches;
     *done = true;
     return (int)cudaGetLastError();

@@ -104,13 +104,16 @@ def random_pulse_trajectory(
         names = [f"ψ̃{k + 1}" for k in range(n_states)] if len(systems) == 1 else [f"ψ̃_system_{k + 1}" for k in range(len(systems))]
     else:
         names = [state_name] if len(systems) == 1 else [f"{state_name}_system_{k + 1}" for k in range(len(systems))]
-    for name in names:
-        cols = []
-        for _ in range(T):
-            U = _random_unitary(rng, N)
-            v = ket_to_iso(U[:, 0]) if ket else operator_to_iso_vec(U)
-            cols.append(v + 1e-3 * rng.normal(size=v.size))
-        comps[name] = np.stack(cols, axis=1)
+    for name in names:  # all T random unitaries of a component at once (batched QR of complex Ginibre matrices)
+        M = rng.normal(size=(T, N, N)) + 1j * rng.normal(size=(T, N, N))
+        Q, R = np.linalg.qr(M)
+        dg = np.diagonal(R, axis1=1, axis2=2)
+        U = Q * (dg / np.abs(dg))[:, None, :]
+        if ket:
+            v = np.concatenate([U[:, :, 0].real, U[:, :, 0].imag], axis=1)                      # [Re psi; Im psi]
+        else:
+            v = np.concatenate([U.real, U.imag], axis=1).transpose(0, 2, 1).reshape(T, 2 * N * N)  # vec(vcat(Re U, Im U))
+        comps[name] = np.ascontiguousarray((v + 1e-3 * rng.normal(size=v.shape)).T)
     a = rng.uniform(-a_bound, a_bound, size=(nd, T))
     a[:, 0] = 0.0
     a[:, -1] = 0.0

@@ -148,12 +148,15 @@ print("variant ok")
 @pytest.mark.parametrize("name,kw,env", [("cz", {}, {"QCK_RS3": "0"}), ("cz", {}, {"QCK_RS3": "0", "QCK_DMMA": "1"}),
                                          ("cz", {}, {"QCK_ROWSLICE_DENSE": "1"}), ("cz", {}, {"QCK_ROWSLICE_WARPS": "3"}),
                                          ("cz", {}, {"QCK_RS3": "5"}), ("cz", {}, {"QCK_RS3": "7"}),
+                                         ("cz", {}, {"QCK_ROWSLICE_BW": "0"}), ("cz", {}, {"QCK_ROWSLICE_BW": "0", "QCK_ROWSLICE_SPREAD": "0"}),
+                                         ("cz", {}, {"QCK_ROWSLICE_DB": "1", "QCK_ROWSLICE_BW": "0"}),
                                          ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"}),
                                          ("ket", {}, {"QCK_COLUMN": "0"})])
 def test_kernel_variants(name, kw, env):
     """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
     (QCK_RS3=0 / QCK_COLUMN=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives / a smaller CTA, the
-    three-warps-per-knot variant of the row-slice kernel with 5 / 7 knots per CTA."""
+    three-warps-per-knot variant of the row-slice kernel with 5 / 7 knots per CTA, the row-slice kernel without its block warps
+    (with / without early block copies, with two staging buffers)."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ)

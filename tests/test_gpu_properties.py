@@ -192,11 +192,59 @@ def test_edge_cases():
         D.F(Z[:-3])
     with pytest.raises(ValueError):
         D.mu_d2F(Z, mu[:-1])
-    # too many levels for one CTA's shared memory: reported at create
+    # more levels than any kernel holds (> 32): reported at create
     big = wl.random_hermitian_system(40, 2, seed=1)
     tb = wl.random_pulse_trajectory([big], 2, 0.1)
     with pytest.raises(qcknot.QcknotError, match="shared memory|image"):
         qcknot.QuantumDynamics(wl.build_integrators([big], tb), tb)
+
+
+@pytest.mark.parametrize("levels,nd,ket", [(16, 4, False), (24, 2, False), (32, 4, False), (32, 3, True), (20, 1, False)])
+def test_large_levels(levels, nd, ket):
+    """north_star: 'qudit dimensions up to about 32'.  16 levels with four drives, 24 and 32 levels: the large-level kernel
+    (qck_big.cu: operands in shared memory, outputs straight to the value arrays)."""
+    sys_ = wl.random_hermitian_system(levels, nd, seed=levels + nd, scale=0.3)
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.1, seed=2, ket=ket)
+    integrators = wl.build_integrators([sys_], traj, ket=ket)
+    D = qcknot.QuantumDynamics(integrators, traj)
+    O = oracle_dynamics(integrators, traj)
+    assert np.array_equal(D.dF_structure, np.array(O.dF_structure)) and np.array_equal(D.mu_d2F_structure, np.array(O.mu_d2F_structure).reshape(-1, 2))
+    Z, mu = traj.datavec, wl.random_multipliers(D.n_blocks * D.dyn)
+    F, J, H = D.eval_all(Z, mu)
+    assert rel_err(F, O.F(Z)) < TOL and rel_err(J, O.dF(Z)) < TOL and rel_err(H, O.mu_d2F(Z, mu)) < TOL
+    assert np.array_equal(D.dF(Z), J) and np.array_equal(D.F(Z), F) and np.array_equal(D.mu_d2F(Z, mu), H)
+    D.close()
+
+
+_BIG_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import qcknot
+from qcknot import workloads as wl
+from oracle.bridge import oracle_dynamics, rel_err
+for name, kw in (("cz", {{"T": 5}}), ("cz", {{"T": 4, "free_time": False}}), ("sampling", {{"T": 3, "n_systems": 3}})):
+    systems, traj, integrators = wl.config(name, **kw)
+    if name == "sampling":  # 5-level systems so that the large-level kernel is eligible; shared controls -> partial columns
+        systems = wl.sampling_systems(3, levels=5)
+        traj = wl.random_pulse_trajectory(systems, 3, 0.2, a_bound=0.1)
+        integrators = wl.build_integrators(systems, traj)
+    D = qcknot.QuantumDynamics(integrators, traj); O = oracle_dynamics(integrators, traj)
+    Z = traj.datavec; mu = wl.random_multipliers(D.n_blocks * D.dyn)
+    F, J, H = D.eval_all(Z, mu)
+    assert rel_err(F, O.F(Z)) < 1e-10 and rel_err(J, O.dF(Z)) < 1e-10 and rel_err(H, O.mu_d2F(Z, mu)) < 1e-10, name
+print("big ok")
+"""
+
+
+def test_large_level_kernel_on_small_problems():
+    """QCK_BIG=1 forces the large-level kernel from 5 levels on: the CZ problem (9 levels) and a 5-level sampling problem whose
+    shared-control Hessian entries go through the partial columns."""
+    import subprocess, sys
+    root = os.path.dirname(HERE)
+    e = dict(os.environ)
+    e.update({"QCK_BIG": "1", "QCK_RS3": "0"})
+    out = subprocess.run([sys.executable, "-c", _BIG_SCRIPT.format(root=root)], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "big ok" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.parametrize("name,T,integ", [("cz", 2500, "pade"), ("hadamard", 5000, "pade"), ("ket", 3000, "pade"), ("cz", 1300, "exponential"),

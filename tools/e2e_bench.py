@@ -16,6 +16,14 @@ Z = [traj.datavec.copy(), traj.datavec.copy()]
 Z[1] += 1e-6
 mu = [wl.random_multipliers(nb * D.dyn, seed=s) for s in (1, 2)]
 F, J, H = np.empty(nb * D.dyn), np.empty(nb * D.nnzJ), np.empty(nb * D.nnzH)
+import torch
+hb = torch.empty(32 << 20, dtype=torch.float64).pin_memory(); db = torch.empty(32 << 20, dtype=torch.float64, device="cuda:0")
+best = 0.0
+for _ in range(4):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); hb.copy_(db, non_blocking=True); torch.cuda.synchronize()
+    best = max(best, hb.numel() * 8 / (time.perf_counter() - t0) * 1e-9)
+print(f"box: {os.cpu_count()} cpus, pinned D2H {best:.1f} GB/s")
+del hb, db
 for i in range(3):
     D.eval_all(Z[i & 1], mu[i & 1], F, J, H)
 t0 = time.perf_counter()
