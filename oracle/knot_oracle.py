@@ -192,9 +192,11 @@ class _QuantumIntegrator:
             P[:, self.dt_idx] = True
         return P
 
-    def hess_pattern(self):
+    def hess_pattern(self, out=None):
+        """Upper-triangular pattern; with `out` the UNFOLDED entries are marked in the caller's matrix instead (the
+        caller folds once -- a fold per integrator is quadratic in the ensemble size)."""
         zdim, s0, s1, a = self._cols()
-        P = np.zeros((2 * zdim, 2 * zdim), dtype=bool)
+        P = np.zeros((2 * zdim, 2 * zdim), dtype=bool) if out is None else out
         P[np.ix_(s0, a)] = True
         P[np.ix_(a, a)] = True
         if self.hess_next:
@@ -206,8 +208,7 @@ class _QuantumIntegrator:
             P[d, d] = True
             if self.hess_next:
                 P[d, s1] = True
-        P = _to_upper_pattern(P)
-        return P
+        return _to_upper_pattern(P) if out is None else P
 
 
 def _to_upper_pattern(P):
@@ -321,12 +322,12 @@ class _PadeMixin:
             J[:, self.dt_idx] = self._vec(B1 @ W1 - F1 @ W0)
         return J
 
-    def hessian(self, zt, zt1, mu):
+    def hessian(self, zt, zt1, mu, out=None):
         W0, W1, a, dt = self._unpack(zt, zt1)
         zdim, s0, s1, ac = self._cols()
         Mu = mu.reshape(2 * self.N, self.ncols, order="F")
         Gp = self._powers(self.sys.G(a))
-        H = np.zeros((2 * zdim, 2 * zdim))
+        H = np.zeros((2 * zdim, 2 * zdim)) if out is None else out  # `out`: add into the caller's matrix
         Gd = self.sys.G_drives
         for j, Gj in enumerate(Gd):
             dF, dB = self._dFB(Gp, Gj, dt)
@@ -386,13 +387,13 @@ class _ExpMixin:
 
         return top_right(E1, E2) + top_right(E2, E1)
 
-    def hessian(self, zt, zt1, mu):
+    def hessian(self, zt, zt1, mu, out=None):
         W0, W1, a, dt = self._unpack(zt, zt1)
         zdim, s0, s1, ac = self._cols()
         Mu = mu.reshape(2 * self.N, self.ncols, order="F")
         G = self.sys.G(a)
         E = sla.expm(dt * G)
-        H = np.zeros((2 * zdim, 2 * zdim))
+        H = np.zeros((2 * zdim, 2 * zdim)) if out is None else out  # `out`: add into the caller's matrix
         Gd = self.sys.G_drives
         Ls = [sla.expm_frechet(dt * G, dt * Gj, compute_expm=False) for Gj in Gd]
         for j, Gj in enumerate(Gd):
@@ -481,20 +482,20 @@ class DerivativeIntegrator:
             P[:, self.dt_idx] = True
         return P
 
-    def hessian(self, zt, zt1, mu):
+    def hessian(self, zt, zt1, mu, out=None):
         zdim = self.layout.zdim
-        H = np.zeros((2 * zdim, 2 * zdim))
+        H = np.zeros((2 * zdim, 2 * zdim)) if out is None else out  # `out`: add into the caller's matrix
         if self.free_time:
             for j in range(self.dim):
                 _put_upper(H, [self.dx.start + j], [self.dt_idx], -mu[j])
         return H
 
-    def hess_pattern(self):
+    def hess_pattern(self, out=None):
         zdim = self.layout.zdim
-        P = np.zeros((2 * zdim, 2 * zdim), dtype=bool)
+        P = np.zeros((2 * zdim, 2 * zdim), dtype=bool) if out is None else out
         if self.free_time:
             P[np.arange(self.dx.start, self.dx.stop), self.dt_idx] = True
-        return _to_upper_pattern(P)
+        return _to_upper_pattern(P) if out is None else P
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -527,7 +528,8 @@ class QuantumDynamics:
         if eval_hessian:
             HP = np.zeros((2 * zdim, 2 * zdim), dtype=bool)
             for I in self.integrators:
-                HP |= I.hess_pattern()
+                I.hess_pattern(out=HP)  # unfolded marks
+            HP = _to_upper_pattern(HP)
             cols, rows = np.nonzero(HP.T)
             self.hess_knot = list(zip(rows.tolist(), cols.tolist()))
         else:
@@ -572,12 +574,13 @@ class QuantumDynamics:
         out = np.zeros(self.nnzH * (self.T - 1))
         rr = np.array([r for r, _ in self.hess_knot])
         cc = np.array([c for _, c in self.hess_knot])
+        H = np.zeros((2 * self.zdim, 2 * self.zdim))
         for t, zt, zt1 in self._knots(Z):
-            H = np.zeros((2 * self.zdim, 2 * self.zdim))
             mut = mu[t * self.dyn : (t + 1) * self.dyn]
             for I, r0 in zip(self.integrators, self.row_off):
-                H += I.hessian(zt, zt1, mut[r0 : r0 + I.dim])
+                I.hessian(zt, zt1, mut[r0 : r0 + I.dim], out=H)  # integrators add in order, like the dense sum did
             out[t * self.nnzH : (t + 1) * self.nnzH] = H[rr, cc]
+            H[rr, cc] = 0.0  # every entry an integrator touches is inside the pattern
         return out
 
 

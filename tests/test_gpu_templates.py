@@ -103,8 +103,9 @@ def test_config5_full_ensemble_256_systems():
     Z = traj.datavec
     mu = wl.random_multipliers(D.n_blocks * D.dyn)
     F, J, H = D.eval_all(Z, mu)
-    assert rel_err(F, O.F(Z)) < TOL and rel_err(J, O.dF(Z)) < TOL and rel_err(H, O.mu_d2F(Z, mu)) < TOL
+    H_ref = O.mu_d2F(Z, mu)
+    assert rel_err(F, O.F(Z)) < TOL and rel_err(J, O.dF(Z)) < TOL and rel_err(H, H_ref) < TOL
     shared = D.shared_hessian_positions()
     idx = (np.arange(D.n_blocks)[:, None] * D.nnzH + shared[None, :]).reshape(-1)
-    assert entry_err(H[idx], O.mu_d2F(Z, mu)[idx]) < 1e-9  # the entries 256 systems add up in
+    assert entry_err(H[idx], H_ref[idx]) < 1e-9  # the entries 256 systems add up in
     D.close()
