@@ -265,10 +265,10 @@ def pcie_peak_gbs(dev, mb=256):
     for name, (dst, src) in (("d2h", (hbuf, dbuf)), ("h2d", (dbuf, hbuf))):
         best = 0.0
         for _ in range(4):
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(dev)
             best = max(best, n * 8 / (time.perf_counter() - t0) * 1e-9)
         out[name] = best
     return out

@@ -420,8 +420,24 @@ int build(qck_handle* h) {
         // per-phase unit tables for the row-slice kernel (QCK_RS3=1, default: one warp per knot) or its three-warps-per-knot
         // variant (QCK_RS3=5..7 knots per CTA; parity-green, measured slower: profiles/); QCK_RS3=0: the tiled kernel
         static const int rs3_knob = getenv("QCK_RS3") ? atoi(getenv("QCK_RS3")) : 1;
+        c.antiherm = 1;  // every member's Hamiltonians are Hermitian  ->  A(a) = -i H(a) is anti-Hermitian
+        for (int q : C.members) {
+            const Integ& I = h->integ[q];
+            for (int j = -1; j < c.nd && c.antiherm; ++j) {
+                const std::complex<double>* Hm = j < 0 ? I.Hdrift.data() : I.Hdrives.data() + (size_t)j * c.N * c.N;
+                for (int r = 0; r < c.N && c.antiherm; ++r)
+                    for (int k = 0; k <= r; ++k)
+                        if (Hm[r + (size_t)c.N * k] != std::conj(Hm[k + (size_t)c.N * r])) { c.antiherm = 0; break; }
+            }
+        }
         c.rs3 = ((rs3_knob == 1 || (rs3_knob >= 5 && rs3_knob <= 7)) && c.kind == QCK_UNITARY_PADE && c.order == 4 && c.N == 9 && c.nd >= 1 && c.nd <= 4 &&
                  C.member_end - C.member_begin == 1 && h->npart == 0) ? rs3_knob : 0;
+        // exponential unitaries, 9 levels, Hermitian Hamiltonians, one active member: the spectral kernel (qck_expeig.cu) with the same
+        // placement and unit tables as the row-slice kernel (QCK_EXPEIG=0: the scaling-and-squaring kernel)
+        static const int eig_knob = getenv("QCK_EXPEIG") ? atoi(getenv("QCK_EXPEIG")) : 1;
+        c.eig = (eig_knob && c.kind == QCK_UNITARY_EXP && c.N == 9 && c.nd >= 1 && c.nd <= 4 && c.antiherm && C.member_end - C.member_begin == 1 &&
+                 h->npart == 0) ? 1 : 0;
+        if (c.eig) c.rs3 = 1;
         for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
         std::vector<int> qdst((size_t)nm * QO_COUNT, -1);  // per member: first destination of every output quantity
         {
@@ -496,16 +512,6 @@ int build(qck_handle* h) {
         }
         c.W = W;
         c.ell_stride = nd * 2 * N * W;
-        c.antiherm = 1;
-        for (int q : C.members) {
-            const Integ& I = h->integ[q];
-            for (int j = -1; j < nd && c.antiherm; ++j) {
-                const std::complex<double>* Hm = j < 0 ? I.Hdrift.data() : I.Hdrives.data() + (size_t)j * N * N;
-                for (int r = 0; r < N && c.antiherm; ++r)
-                    for (int k = 0; k <= r; ++k)
-                        if (Hm[r + (size_t)N * k] != std::conj(Hm[k + (size_t)N * r])) { c.antiherm = 0; break; }
-            }
-        }
         // {A_i, A_j} = -(H_i H_j + H_j H_i) for A = -iH, pairs ordered by (j, i <= j)
         std::vector<std::vector<std::vector<std::pair<int, std::complex<double>>>>> kk(nm);
         int kk_cap = 0;
@@ -630,7 +636,7 @@ int build(qck_handle* h) {
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
         }
-        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0) {
+        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0 && !c.eig) {  // (the spectral kernel has no tape)
             // reverse-sweep tape of the exponential Hessian: 7 Horner steps x nd jets + 16 squaring levels x (1 + nd) matrices per CTA
             c.tape_levels = 16;
             c.tape_stride = (long long)(7 * nd + c.tape_levels * (1 + nd)) * N * N;
@@ -753,6 +759,7 @@ int qck_check_status(qck_handle* h) {
 namespace {
 
 int eval_host(qck_handle* h, const double* Z, const double* mu, double* F, double* J, double* H) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (!Z) return fail(h, QCK_EINVAL, "Z is NULL");
     if (!h->children.empty()) return qck_multi_eval(h, Z, mu, F, J, H);
@@ -862,6 +869,7 @@ int qck_create_single(const qck_problem_desc* d, qck_handle** out, bool exclude_
 extern "C" {
 
 int qck_create(const qck_problem_desc* d, qck_handle** out) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!out) return fail(nullptr, QCK_EINVAL, "out is NULL");
     *out = nullptr;
     if (!d || !d->integrators || d->n_integrators <= 0) return fail(nullptr, QCK_EINVAL, "empty problem description");
@@ -887,6 +895,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
 }
 
 void qck_destroy(qck_handle* h) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return;
     if (!h->children.empty() || h->nccl) qck_multi_destroy(h);
     qck_objective_free(h);
@@ -936,6 +945,7 @@ int qck_eval_hessian(qck_handle* h, const double* Z, const double* mu, double* H
 int qck_eval_all(qck_handle* h, const double* Z, const double* mu, double* F, double* J, double* H) { return eval_host(h, Z, mu, F, J, H); }
 
 int qck_eval_device(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, double* dF, double* dJ, double* dH, void* stream) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (!h->children.empty()) return fail(h, QCK_EINVAL, "multi-GPU handle: use qck_upload + qck_eval_resident (device pointers belong to one GPU)");
     if (!dZ) return fail(h, QCK_EINVAL, "dZ is NULL");
@@ -950,6 +960,7 @@ int qck_eval_device(qck_handle* h, uint32_t mask, const double* dZ, const double
 }
 
 int qck_device_buffers(qck_handle* h, double** dZ, double** dmu, double** dF, double** dJ, double** dH) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (!h->children.empty()) return fail(h, QCK_EINVAL, "multi-GPU handle: use qck_shard_device_buffers");
     if (dZ) *dZ = h->dZ;
@@ -962,6 +973,7 @@ int qck_device_buffers(qck_handle* h, double** dZ, double** dmu, double** dF, do
 }
 
 int qck_synchronize(qck_handle* h) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (!h->children.empty()) {
         for (qck_handle* c : h->children) {

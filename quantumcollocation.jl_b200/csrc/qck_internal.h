@@ -4,6 +4,23 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Every C-ABI entry point that switches the CUDA device puts one of these on its stack: a library behind somebody else's
+// runtime (CUDA.jl, torch) must not leave the calling thread on another device.
+struct QckDeviceScope {
+    int prev = -1;
+    QckDeviceScope() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            (void)cudaGetLastError();
+        }
+    }
+    ~QckDeviceScope() {
+        if (prev >= 0) (void)cudaSetDevice(prev);
+    }
+    QckDeviceScope(const QckDeviceScope&) = delete;
+    QckDeviceScope& operator=(const QckDeviceScope&) = delete;
+};
+
 #include "../../include/qcknot.h"
 
 #define QCK_TILE 3          // register tile edge of the small complex products (3x3 complex per thread)
@@ -66,6 +83,7 @@ struct QckClassDev {
     int free_time, dt_off, zdim, dyn;
     int antiherm;  // every member's Hamiltonians are Hermitian: A(a) = -i H(a) is anti-Hermitian
     int big;       // the class runs on the large-level kernel (qck_big.cu): operands in shared memory, outputs straight to the arrays
+    int eig;       // exponential class that runs on the spectral kernel (qck_expeig.cu); built with the rs3 placement (rs3 = 1)
     int rs3;       // > 0: built for the three-warps-per-knot kernel (qck_rs3.cu) with this many knots per CTA: parity-matched
                    // image placement, unit table [phase][warp] (see qck_host.cpp)
     double dt_fixed;
@@ -173,6 +191,7 @@ int qck_launch_big(const QckLaunch& L, int sm_count, cudaStream_t stream, int* l
 size_t qck_big_smem(const QckClassDev& c);
 size_t qck_rs3_smem(const QckClassDev& c, int hoff, int kpc);
 int qck_rs3_hoff(const QckClassDev& c);
+int qck_launch_expeig(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 int qck_fused_aux_limit(void);
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,

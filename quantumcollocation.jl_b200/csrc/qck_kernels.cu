@@ -1501,6 +1501,8 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         if (c.big) return (int)cudaErrorInvalidConfiguration;  // (no other kernel can hold this class)
         rc = qck_launch_rs3(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
+        rc = qck_launch_expeig(L, sm_count, stream, launches, &done);
+        if (rc || done) return rc;
         rc = qck_launch_rowslice9(L, sm_count, stream, launches, &done);
         if (!rc && !done && c.rs3) return (int)cudaErrorInvalidConfiguration;  // the class tables were built for the row-slice kernels only
         if (rc || done) return rc;

@@ -287,6 +287,7 @@ int qck_shard_info(const qck_handle* h, int32_t g, int32_t* device, int64_t* blo
 }
 
 int qck_shard_device_buffers(qck_handle* h, int32_t g, double** dZ, double** dmu, double** dF, double** dJ, double** dH) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (h->children.empty()) return g == 0 ? qck_device_buffers(h, dZ, dmu, dF, dJ, dH) : QCK_EINVAL;
     if (g < 0 || g >= (int)h->children.size()) return QCK_EINVAL;
@@ -295,6 +296,7 @@ int qck_shard_device_buffers(qck_handle* h, int32_t g, double** dZ, double** dmu
 
 // H2D of the inputs into every shard's own device buffers (each GPU gets its knots + halo / all knots)
 int qck_upload(qck_handle* h, const double* Z, const double* mu) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !Z) return QCK_EINVAL;
     std::vector<qck_handle*> one{h};
     const std::vector<qck_handle*>& cs = h->children.empty() ? one : h->children;
@@ -318,6 +320,7 @@ int qck_upload(qck_handle* h, const double* Z, const double* mu) {
 // one pass on every GPU over its shard, inputs and outputs in the shards' own device buffers; asynchronous.
 // ENSEMBLE: the Hessian entries on the shared controls are all-reduced (NCCL) so that every GPU holds the sums.
 int qck_eval_resident(qck_handle* h, uint32_t mask) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (h->children.empty()) {
         if (h->device < 0) return qck_fail(h, QCK_ENODEVICE, "structure-only handle");
@@ -393,6 +396,7 @@ int qck_eval_resident(qck_handle* h, uint32_t mask) {
 // KNOT sharding: all-gather of the device-resident segments so that every GPU holds the assembled value arrays
 // (ncclBroadcast per segment inside one group: the segments may differ in length).  Asynchronous on the shards' streams.
 int qck_gather_device(qck_handle* h, uint32_t mask) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (h->children.empty()) return QCK_OK;  // one GPU: the shard buffers are the assembled arrays
     if (h->shard_mode != QCK_SHARD_KNOT) return qck_fail(h, QCK_EINVAL, "qck_gather_device assembles knot-sharded arrays; ensemble shards interleave inside every knot block");
@@ -428,6 +432,7 @@ int qck_gather_device(qck_handle* h, uint32_t mask) {
 }
 
 int qck_gathered_buffers(qck_handle* h, int32_t g, double** dF, double** dJ, double** dH) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h) return QCK_EINVAL;
     if (h->children.empty()) return g == 0 ? qck_device_buffers(h, nullptr, nullptr, dF, dJ, dH) : QCK_EINVAL;
     if (g < 0 || g >= (int)h->children.size()) return QCK_EINVAL;

@@ -330,6 +330,7 @@ void qck_objective_free(qck_handle* h) {
 extern "C" {
 
 int qck_objective_attach(qck_handle* h, const qck_objective_term* terms, int32_t n_terms) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !terms || n_terms <= 0) return QCK_EINVAL;
     if (n_terms > QCK_MAX_OBJ_TERMS) return qck_fail(h, QCK_EINVAL, "at most %d objective terms", QCK_MAX_OBJ_TERMS);
     if (!h->children.empty() && h->shard_mode != QCK_SHARD_KNOT) return qck_fail(h, QCK_EINVAL, "objective terms on a multi-GPU handle need knot sharding");
@@ -385,6 +386,7 @@ int qck_objective_hessian_structure(const qck_handle* h, int64_t* rows, int64_t*
 }
 
 int qck_eval_objective(qck_handle* h, const double* Z, double* value) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !Z || !value || !h->objective) return QCK_EINVAL;
     double total = 0.0;
     for (auto& s : shards_of(h)) {
@@ -410,6 +412,7 @@ int qck_eval_objective(qck_handle* h, const double* Z, double* value) {
 }
 
 int qck_eval_objective_gradient(qck_handle* h, const double* Z, double* grad) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !Z || !grad || !h->objective) return QCK_EINVAL;
     for (auto& s : shards_of(h)) {
         qck_handle* c = s.h;
@@ -434,6 +437,7 @@ int qck_eval_objective_gradient(qck_handle* h, const double* Z, double* grad) {
 }
 
 int qck_eval_objective_hessian(qck_handle* h, const double* Z, double sigma, double* vals) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !Z || !vals || !h->objective) return QCK_EINVAL;
     for (auto& s : shards_of(h)) {
         qck_handle* c = s.h;
@@ -459,6 +463,7 @@ int qck_eval_objective_hessian(qck_handle* h, const double* Z, double sigma, dou
 
 // ---- FinalUnitaryFidelityConstraint: g(Z) = F(U_T) - min_fidelity >= 0 -----------------------------------------------------
 int qck_fidelity_constraint_attach(qck_handle* h, const qck_objective_term* term, double min_fidelity) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !term) return QCK_EINVAL;
     if (term->kind != QCK_OBJ_UNITARY_INFIDELITY) return qck_fail(h, QCK_EINVAL, "the fidelity constraint takes a term of kind QCK_OBJ_UNITARY_INFIDELITY (goal, levels, n_sub)");
     if (!h->children.empty() && h->shard_mode != QCK_SHARD_KNOT) return qck_fail(h, QCK_EINVAL, "the fidelity constraint on a multi-GPU handle needs knot sharding");
@@ -494,6 +499,7 @@ int qck_fidelity_constraint_attach(qck_handle* h, const qck_objective_term* term
 // g (1 value) and, if jac != NULL, the Jacobian row over the final knot's state component (comp_len values; their 1-based
 // columns are (T-1)*zdim + comp_off + 1 ...); hess != NULL: mu * upper triangle (by column) of the constraint's Hessian
 int qck_eval_fidelity_constraint(qck_handle* h, const double* Z, double mu, double* g, double* jac, double* hess) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     if (!h || !Z) return QCK_EINVAL;
     auto sh = shards_of(h);
     qck_handle* c = sh.back().h;

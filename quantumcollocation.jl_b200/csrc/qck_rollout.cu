@@ -212,6 +212,7 @@ const char* qck_rollout_last_error(void) { return g_ro_error.c_str(); }
 //   X_out [n_systems][T][2N*ncols]: per system the dim x T trajectory component, column-major
 int qck_rollout(int32_t device, int32_t ket, int32_t levels, int32_t n_drives, int32_t n_systems, const double* H_drift,
                 const double* H_drives, int64_t T, const double* a, const double* dt, const double* X_init, double* X_out) {
+    QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
     const int N = levels, nd = n_drives, S = n_systems, NN = N * N, ncols = ket ? 1 : N, nx = N * ncols;
     if (N < 1 || N > QCK_RO_MAXN || nd < 0 || S < 1 || T < 1 || !a || !dt || !X_out || !H_drives) return ro_fail(QCK_EINVAL, "qck_rollout: bad arguments (levels <= 16)");
     cudaError_t ce;

@@ -89,6 +89,37 @@ def test_exponential_large_norm():
     check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=True)
 
 
+# ---- 9-level exponential unitaries: the spectral kernel (qck_expeig.cu) ---------------------------------------------------------
+@pytest.mark.parametrize("nd", [1, 2, 3, 4])
+@pytest.mark.parametrize("free_time", [True, False])
+def test_spectral_exponential_dense_drives(nd, free_time):
+    """Jacobi eigen-decomposition + divided differences against scipy expm / expm_frechet / block-triangular second derivatives:
+    dense random Hamiltonians (sparse-row width 9), 1..4 drives, free and fixed timestep; F, F+J and F+J+H calls."""
+    sys_ = wl.random_hermitian_system(9, nd, seed=190 + nd, scale=0.5)
+    traj = wl.random_pulse_trajectory([sys_], 5, 0.25, seed=13 + nd, free_time=free_time)
+    integrators = wl.build_integrators([sys_], traj, integrator="exponential")
+    check([sys_], traj, integrators, eval_hessian=True)
+    check([sys_], traj, integrators, eval_hessian=False)
+
+
+@pytest.mark.parametrize("amp", [0.0, 1e-9, 1e-4, 3e-2])
+def test_spectral_exponential_degenerate_levels(amp):
+    """The CZ drift has exactly degenerate levels; with controls of size amp the spectrum is exactly / nearly / mildly degenerate:
+    first- and second-order divided differences must not cancel (sinc form, series about the mean for close triples)."""
+    systems, traj, integrators = wl.config("cz", T=5, integrator="exponential")
+    a = traj["a"]  # view into the trajectory's data (controls x T)
+    a[:] = amp * np.sign(a) * (1.0 + np.arange(traj.T)[None, :])
+    check(systems, traj, integrators, eval_hessian=True)
+
+
+def test_spectral_exponential_large_norm():
+    """||h A|| ~ 60: no squaring levels, no tape, nothing to overflow -- the phases just wrap."""
+    sys_ = wl.random_hermitian_system(9, 3, seed=31, scale=4.0)
+    traj = wl.random_pulse_trajectory([sys_], 4, 1.5, seed=12)
+    integrators = wl.build_integrators([sys_], traj, integrator="exponential")
+    check([sys_], traj, integrators, eval_hessian=True)
+
+
 @pytest.mark.parametrize("order", [6, 8, 10, 12])
 @pytest.mark.parametrize("name,kw", [("hadamard", {"T": 5}), ("hadamard", {"T": 4, "free_time": False}), ("cz", {"T": 3}), ("ket", {"T": 5})])
 def test_general_pade_orders(order, name, kw):
@@ -151,12 +182,14 @@ print("variant ok")
                                          ("cz", {}, {"QCK_ROWSLICE_BW": "0"}), ("cz", {}, {"QCK_ROWSLICE_BW": "0", "QCK_ROWSLICE_SPREAD": "0"}),
                                          ("cz", {}, {"QCK_ROWSLICE_DB": "1", "QCK_ROWSLICE_BW": "0"}),
                                          ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"}),
-                                         ("ket", {}, {"QCK_COLUMN": "0"})])
+                                         ("ket", {}, {"QCK_COLUMN": "0"}), ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG": "0"}),
+                                         ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG_WARPS": "3"})])
 def test_kernel_variants(name, kw, env):
     """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
     (QCK_RS3=0 / QCK_COLUMN=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives / a smaller CTA, the
     three-warps-per-knot variant of the row-slice kernel with 5 / 7 knots per CTA, the row-slice kernel without its block warps
-    (with / without early block copies, with two staging buffers)."""
+    (with / without early block copies, with two staging buffers), the exponential CZ problem on the scaling-and-squaring kernel
+    instead of the spectral one."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ)

@@ -114,9 +114,11 @@ def test_full_size_cz_through_pipeline_matches_plain_copy():
 
 
 def test_exponential_out_of_range_is_reported():
-    """ADVICE: ||dt*G||_1 > 4096 needs more squarings than the Hessian tape holds: an error, not a silent truncation."""
-    systems, traj, integrators = wl.config("cz", T=4, integrator="exponential")
-    D = qcknot.QuantumDynamics(integrators, traj)
+    """ADVICE: ||dt*G||_1 > 4096 needs more squarings than the Hessian tape of the scaling-and-squaring kernel holds: an error,
+    not a silent truncation.  (5 levels: the class runs on that kernel; the spectral kernel of the 9-level problems has no limit.)"""
+    sys_ = wl.random_hermitian_system(5, 2, seed=3, scale=1.0)
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.2, seed=11)
+    D = qcknot.QuantumDynamics(wl.build_integrators([sys_], traj, integrator="exponential"), traj)
     Z = traj.datavec.copy()
     Z.reshape(traj.T, -1)[1, traj.components["a"]] = 1e6
     with pytest.raises(qcknot.QcknotError, match="4096"):
@@ -136,12 +138,14 @@ def test_knot_sharded_handle_fills_the_callers_arrays(n):
         pytest.skip(f"needs {n} GPUs")
     systems, traj, integrators = wl.config("cz", T=403)
     D1 = qcknot.QuantumDynamics(integrators, traj)
+    torch.cuda.set_device(0)
     Dn = qcknot.QuantumDynamics(integrators, traj, n_gpus=n, shard_mode="knot")
     assert len(Dn.shards()) == n and sorted(s[0] for s in Dn.shards()) == list(range(n))
     Z = traj.datavec.copy()
     mu = wl.random_multipliers(D1.n_blocks * D1.dyn)
     F1, J1, H1 = D1.eval_all(Z, mu)
     Fn, Jn, Hn = Dn.eval_all(Z, mu)
+    assert torch.cuda.current_device() == 0  # the library restores the caller's CUDA device
     assert np.array_equal(F1, Fn) and np.array_equal(J1, Jn) and np.array_equal(H1, Hn)
     assert np.array_equal(Dn.dF_structure, D1.dF_structure) and np.array_equal(Dn.mu_d2F_structure, D1.mu_d2F_structure)
     assert np.array_equal(Dn.dF(Z), J1) and np.array_equal(Dn.F(Z), F1) and np.array_equal(Dn.mu_d2F(Z, mu), H1)
@@ -150,6 +154,7 @@ def test_knot_sharded_handle_fills_the_callers_arrays(n):
     Dn.eval_resident(7)
     Dn.gather_device(7)
     Dn.synchronize()
+    assert torch.cuda.current_device() == 0
     ver, nranks = Dn.nccl_version()
     assert nranks == n and ver >= 21800
     nb = D1.n_blocks
