@@ -33,30 +33,14 @@ namespace {
 // as TMA bulk copies (flush_units_lanes).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int EN = 9, ENN = 81, EN2 = 18, EDIM = 162, EF3 = 165;
-constexpr int kEigBufs = 7;  // mH|T1, mV, vU0|T2, vM|Phi, vW0, vMt, vG  (+ ND buffers B_j)
+constexpr int kEigBufs = 7;       // T1, mV, vU0|T2, vM|Phi, vW0, vMt, vG  (+ ND buffers B_j)
+constexpr int kEigScratch = 86;   // double2 per knot in the eigen scratch: V row-major (81) | l_0 .. l_8 (+ pad)
 
 __device__ __forceinline__ size_t expeig_warp_bytes(int nd, int img_bytes) {
     return (size_t)img_bytes + (size_t)(kEigBufs + nd) * ENN * 16 + (size_t)EF3 * 16 + (size_t)EN * 16 * 2 + (size_t)EN * 8 + 8;
 }
 
-// rotation that diagonalises the Hermitian pivot [[al, be], [conj(be), ga]]:  J = [[c, conj(sg)], [-sg, c]]  (inner rotation)
-__device__ __forceinline__ void jacobi_rot(const double2* __restrict__ H, int p, int q, double& c, double2& sg) {
-    const double al = H[p * EN + p].x, ga = H[q * EN + q].x;
-    const double2 be = H[p * EN + q];
-    const double b2 = be.x * be.x + be.y * be.y;
-    c = 1.0;
-    sg = make_double2(0.0, 0.0);
-    if (b2 > 0.0) {
-        const double d = 0.5 * (ga - al);
-        const double inv_r = rsqrt(fma(d, d, b2));
-        const double u = fma(0.5 * fabs(d), inv_r, 0.5);
-        const double inv_c = rsqrt(u);
-        c = u * inv_c;
-        const double f = copysign(0.5 * inv_r * inv_c, d);
-        sg = make_double2(f * be.x, -f * be.y);
-    }
-}
-// (y1, y2) <- (y1, y2) J  (column rotation of a row vector)
+// (y1, y2) <- (y1, y2) J,  J = [[c, conj(sg)], [-sg, c]]  (column rotation of a row vector)
 __device__ __forceinline__ void rot_right(double2& y1, double2& y2, double c, double2 sg) {
     const double2 a = y1, b = y2;
     y1 = make_double2(c * a.x - (sg.x * b.x - sg.y * b.y), c * a.y - (sg.x * b.y + sg.y * b.x));
@@ -69,9 +53,136 @@ __device__ __forceinline__ void rot_left(double2& z1, double2& z2, double c, dou
     z2 = make_double2(c * b.x + (sg.x * a.x - sg.y * a.y), c * b.y + (sg.x * a.y + sg.y * a.x));
 }
 
+// sorted triples (lo | mid << 4 | hi << 8) of the 165 second-order divided differences, index hi(hi+1)(hi+2)/6 + mid(mid+1)/2 + lo
+__device__ const unsigned short kTriples[EF3] = {
+    0x000, 0x100, 0x110, 0x111, 0x200, 0x210, 0x211, 0x220, 0x221, 0x222, 0x300, 0x310, 0x311, 0x320, 0x321,
+    0x322, 0x330, 0x331, 0x332, 0x333, 0x400, 0x410, 0x411, 0x420, 0x421, 0x422, 0x430, 0x431, 0x432, 0x433,
+    0x440, 0x441, 0x442, 0x443, 0x444, 0x500, 0x510, 0x511, 0x520, 0x521, 0x522, 0x530, 0x531, 0x532, 0x533,
+    0x540, 0x541, 0x542, 0x543, 0x544, 0x550, 0x551, 0x552, 0x553, 0x554, 0x555, 0x600, 0x610, 0x611, 0x620,
+    0x621, 0x622, 0x630, 0x631, 0x632, 0x633, 0x640, 0x641, 0x642, 0x643, 0x644, 0x650, 0x651, 0x652, 0x653,
+    0x654, 0x655, 0x660, 0x661, 0x662, 0x663, 0x664, 0x665, 0x666, 0x700, 0x710, 0x711, 0x720, 0x721, 0x722,
+    0x730, 0x731, 0x732, 0x733, 0x740, 0x741, 0x742, 0x743, 0x744, 0x750, 0x751, 0x752, 0x753, 0x754, 0x755,
+    0x760, 0x761, 0x762, 0x763, 0x764, 0x765, 0x766, 0x770, 0x771, 0x772, 0x773, 0x774, 0x775, 0x776, 0x777,
+    0x800, 0x810, 0x811, 0x820, 0x821, 0x822, 0x830, 0x831, 0x832, 0x833, 0x840, 0x841, 0x842, 0x843, 0x844,
+    0x850, 0x851, 0x852, 0x853, 0x854, 0x855, 0x860, 0x861, 0x862, 0x863, 0x864, 0x865, 0x866, 0x870, 0x871,
+    0x872, 0x873, 0x874, 0x875, 0x876, 0x877, 0x880, 0x881, 0x882, 0x883, 0x884, 0x885, 0x886, 0x887, 0x888,
+};
+
 __device__ __forceinline__ int f3_index(int a, int b, int c) {
     const int lo = min(a, min(b, c)), hi = max(a, max(b, c)), mid = a + b + c - lo - hi;
     return hi * (hi + 1) * (hi + 2) / 6 + mid * (mid + 1) / 2 + lo;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Eigen kernel: H(a_t) = V diag(l) V^H for every knot, one warp per knot, 32+ warps per SM (2.6 KB of shared memory and ~60
+// registers per warp: the rotations' dependent latencies hide behind other knots, which the 7-warp main kernel cannot do).
+// Cyclic Jacobi with the round-robin ordering: round s rotates the 4 disjoint pairs ((s + l) mod 9, (s - l) mod 9), l = 1 .. 4
+// (level s sits out).  H and V are stacked into one 18 x 9 row-major matrix S = [H; V]; a round is
+//   (1) every lane forms the rotation of pair l = lane & 3 from the pivots,   J = [[c, conj(sg)], [-sg, c]]
+//   (2) pass R:  S <- S J    72 tasks (row, pair) of two elements each, same code for the rows of H and of V
+//   (3) pass L:  H <- J^H H  36 tasks (column, pair); the pivot entries are set to their exact values (0 / real)
+// Results go to the class's scratch (V row-major, then the eigenvalues): 1.4 KB per knot, L2-resident for the main kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256, 4) qck_eig9_kernel(const QckLaunch p) {
+    constexpr int N = EN, NN = ENN;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const QckClassDev& c = p.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)(blockDim.x >> 5);
+    double2* const S = reinterpret_cast<double2*>(smem_all) + (size_t)warp * 2 * NN;
+    const int m = p.member_begin;
+    const double2* const gv = c.cmat + (size_t)m * c.cmat_stride;
+    const int* const gc = c.ell_col + (size_t)m * c.icon_stride;
+    const double2* const A0 = gv;
+    const double2* const acv = gv + NN + c.ell_stride + c.kk_cap;
+    const int* const acptr = gc + c.ell_stride + ND * (ND + 1) / 2 + 1 + c.kk_cap;
+    const int* const acj = acptr + NN + 1;
+    const int coff = p.moff_global[1];
+    const int lA = lane & 3, row0 = lane >> 2;
+    for (long long t = (long long)blockIdx.x * nwarps + warp; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
+        const double* zt = p.Z + t * c.zdim;
+        double ctl[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) ctl[j] = zt[coff + j];
+        // H = i A(a) = H_drift + sum_j a_j H_j (row-major), V = I
+        double fro2 = 0.0;
+        for (int e = lane; e < NN; e += 32) {
+            double2 v = __ldg(A0 + e);
+            for (int u = __ldg(acptr + e), u1 = __ldg(acptr + e + 1); u < u1; ++u) {
+                const int jd = __ldg(acj + u);
+                double aj = ctl[0];
+#pragma unroll
+                for (int j = 1; j < ND; ++j) aj = jd == j ? ctl[j] : aj;
+                const double2 d = __ldg(acv + u);
+                v.x = fma(aj, d.x, v.x);
+                v.y = fma(aj, d.y, v.y);
+            }
+            const int r = e % N, col = e / N;  // A0 is column-major
+            S[r * N + col] = make_double2(-v.y, r == col ? 0.0 : v.x);  // i (x + i y) = -y + i x; the diagonal of H is real
+            S[NN + e] = make_double2(r == col ? 1.0 : 0.0, 0.0);
+            fro2 = fma(v.x, v.x, fma(v.y, v.y, fro2));
+        }
+        fro2 = warp_sum(fro2);
+        __syncwarp();
+        int pl = lA + 1, ql = N - 1 - lA;  // pair l of round 0; both move up by one (mod 9) every round
+        for (int sweep = 0; sweep < 12; ++sweep) {
+            double off2 = 0.0;
+            for (int e = lane; e < NN; e += 32) {
+                const double2 v = S[e];
+                if (e % (N + 1)) off2 = fma(v.x, v.x, fma(v.y, v.y, off2));
+            }
+            off2 = warp_sum(off2);
+            if (off2 <= 1e-30 * fro2) break;
+#pragma unroll 1
+            for (int s = 0; s < N; ++s) {
+                double cr = 1.0;
+                double2 sg = make_double2(0.0, 0.0);
+                {
+                    const double al = S[pl * (N + 1)].x, ga = S[ql * (N + 1)].x;
+                    const double2 be = S[pl * N + ql];
+                    const double b2 = be.x * be.x + be.y * be.y;
+                    if (b2 > 0.0) {  // inner rotation: c = cos >= 1/sqrt(2)
+                        const double d = 0.5 * (ga - al);
+                        const double inv_r = rsqrt(fma(d, d, b2));
+                        const double u = fma(0.5 * fabs(d), inv_r, 0.5);
+                        const double inv_c = rsqrt(u);
+                        cr = u * inv_c;
+                        const double f = copysign(0.5 * inv_r * inv_c, d);
+                        sg = make_double2(f * be.x, -f * be.y);
+                    }
+                }
+                __syncwarp();  // every lane has read its pivots
+#pragma unroll
+                for (int it = 0; it < 3; ++it) {
+                    const int rho = row0 + 8 * it;
+                    if (it < 2 || rho < 2 * N) {
+                        double2 a = S[rho * N + pl], b = S[rho * N + ql];
+                        rot_right(a, b, cr, sg);
+                        S[rho * N + pl] = a; S[rho * N + ql] = b;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int gam = row0 + 8 * it;
+                    if (gam < N) {
+                        double2 a = S[pl * N + gam], b = S[ql * N + gam];
+                        rot_left(a, b, cr, sg);
+                        if (gam == pl) { a.y = 0.0; b = make_double2(0.0, 0.0); }
+                        if (gam == ql) { b.y = 0.0; a = make_double2(0.0, 0.0); }
+                        S[pl * N + gam] = a; S[ql * N + gam] = b;
+                    }
+                }
+                __syncwarp();
+                pl = pl + 1 == N ? 0 : pl + 1;
+                ql = ql + 1 == N ? 0 : ql + 1;
+            }
+        }
+        double2* const out = c.tape + (size_t)t * kEigScratch;
+        for (int e = lane; e < NN; e += 32) out[e] = S[NN + e];
+        if (lane < N) reinterpret_cast<double*>(out + NN)[lane] = S[lane * (N + 1)].x;
+        __syncwarp();  // S is rebuilt for the warp's next knot
+    }
 }
 
 template <int ND>
@@ -98,8 +209,8 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
     QckAux* const auxs = reinterpret_cast<QckAux*>(segtab + nrec);
     unsigned char* const wbase = reinterpret_cast<unsigned char*>(auxs + p.n_aux) + (size_t)warp * expeig_warp_bytes(ND, img_bytes);
     double* const stage = reinterpret_cast<double*>(wbase);
-    double2* const mH = reinterpret_cast<double2*>(wbase + img_bytes);  // Hermitian work matrix, row-major; later scratch
-    double2* const mV = mH + NN;    // eigenvectors: V[r][k] = mV[k * N + r]
+    double2* const T1 = reinterpret_cast<double2*>(wbase + img_bytes);  // scratch matrix
+    double2* const mV = T1 + NN;    // eigenvectors, row-major: V[r][k] = mV[r * N + k]
     double2* const vU0 = mV + NN;   // columns of U0: element [c * N + r]; later scratch
     double2* const vM = vU0 + NN;   // multipliers; later Phi[p * N + q]
     double2* const vW0 = vM + NN;   // V^H U0 (column-major)
@@ -110,7 +221,6 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
     double2* const ex = f3 + EF3;      // e^{x_p}
     double2* const hx = ex + N;        // e^{x_p / 2}
     double* const lam = reinterpret_cast<double*>(hx + N);
-    double2* const T1 = mH;
     double2* const T2 = vU0;
     double2* const Phi = vM;
     {
@@ -150,9 +260,6 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
             }
         }
         const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
-        double ctl[ND];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) ctl[j] = zt[coff + j];
         double* const baseF = p.F + t * c.dyn;
         double* const baseJ = p.J + t * p.nnzJ;
         double* const baseH = p.H + t * p.nnzH;
@@ -178,85 +285,16 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                 if (needH) reinterpret_cast<double*>(vM)[o] = inm[q];
             }
         }
-        // ---- H = i A(a) = H_drift + sum_j a_j H_j (row-major), V = I -------------------------------------------------------------
-        double fro2 = 0.0;
-        for (int e = lane; e < NN; e += 32) {
-            double2 v = A0[e];
-            for (int u = acptr[e]; u < acptr[e + 1]; ++u) {
-                const int jd = acj[u];
-                double aj = ctl[0];
-#pragma unroll
-                for (int j = 1; j < ND; ++j) aj = jd == j ? ctl[j] : aj;
-                const double2 d = acv[u];
-                v.x = fma(aj, d.x, v.x);
-                v.y = fma(aj, d.y, v.y);
-            }
-            const int r = e % N, col = e / N;  // A0 is column-major
-            mH[r * N + col] = make_double2(-v.y, r == col ? 0.0 : v.x);  // i * (x + i y) = -y + i x  (the diagonal of H is real)
-            mV[e] = make_double2(r == col ? 1.0 : 0.0, 0.0);
-            fro2 = fma(v.x, v.x, fma(v.y, v.y, fro2));
-        }
-        fro2 = warp_sum(fro2);
-        __syncwarp();
-        // ---- cyclic Jacobi, round-robin ordering: round s pairs (s + k, s - k) mod 9, k = 1 .. 4; level s sits out ---------------------
+        // ---- eigenvectors (row-major) and eigenvalues of H(a_t) from the eigen kernel's scratch ------------------------------------
         {
-            const int kA = (lane >> 2) & 3, lA = lane & 3, rB = lane >> 2;
-            for (int sweep = 0; sweep < 12; ++sweep) {
-                double off2 = 0.0;
-                for (int e = lane; e < NN; e += 32) {
-                    const double2 v = mH[e];
-                    if (e % (N + 1)) off2 = fma(v.x, v.x, fma(v.y, v.y, off2));
-                }
-                off2 = warp_sum(off2);
-                if (off2 <= 1e-30 * fro2) break;
-#pragma unroll 1
-                for (int s = 0; s < N; ++s) {
-                    int pk = s + kA + 1, qk = s - kA - 1, pl = s + lA + 1, ql = s - lA - 1;
-                    pk -= pk >= N ? N : 0; qk += qk < 0 ? N : 0; pl -= pl >= N ? N : 0; ql += ql < 0 ? N : 0;
-                    double ck, cl;
-                    double2 sk, sl;
-                    jacobi_rot(mH, pk, qk, ck, sk);
-                    jacobi_rot(mH, pl, ql, cl, sl);
-                    double2 x11, x12, x21, x22, v1, v2;
-                    x11 = x12 = x21 = x22 = make_double2(0.0, 0.0);
-                    if (lane < 16) {  // the 2 x 2 block (rows of pair k, columns of pair l):  J_k^H X J_l
-                        x11 = mH[pk * N + pl]; x12 = mH[pk * N + ql]; x21 = mH[qk * N + pl]; x22 = mH[qk * N + ql];
-                        rot_right(x11, x12, cl, sl);
-                        rot_right(x21, x22, cl, sl);
-                        rot_left(x11, x21, ck, sk);
-                        rot_left(x12, x22, ck, sk);
-                        if (kA == lA) { x12 = x21 = make_double2(0.0, 0.0); x11.y = 0.0; x22.y = 0.0; }  // the pivot block is now diagonal
-                    } else if (lane < 20) {  // row of the idle level x pair l
-                        x11 = mH[s * N + pl]; x12 = mH[s * N + ql];
-                        rot_right(x11, x12, cl, sl);
-                    } else if (lane < 24) {  // pair l (= lane & 3) x column of the idle level
-                        x11 = mH[pl * N + s]; x21 = mH[ql * N + s];
-                        rot_left(x11, x21, cl, sl);
-                    } else if (lane < 28) {  // last row of V x pair l
-                        x11 = mV[pl * N + (N - 1)]; x12 = mV[ql * N + (N - 1)];
-                        rot_right(x11, x12, cl, sl);
-                    }
-                    v1 = mV[pl * N + rB]; v2 = mV[ql * N + rB];  // rows 0 .. 7 of V x pair l
-                    rot_right(v1, v2, cl, sl);
-                    __syncwarp();  // every lane has read the old pivots and blocks
-                    if (lane < 16) {
-                        mH[pk * N + pl] = x11; mH[pk * N + ql] = x12; mH[qk * N + pl] = x21; mH[qk * N + ql] = x22;
-                    } else if (lane < 20) {
-                        mH[s * N + pl] = x11; mH[s * N + ql] = x12;
-                    } else if (lane < 24) {
-                        mH[pl * N + s] = x11; mH[ql * N + s] = x21;
-                    } else if (lane < 28) {
-                        mV[pl * N + (N - 1)] = x11; mV[ql * N + (N - 1)] = x12;
-                    }
-                    mV[pl * N + rB] = v1; mV[ql * N + rB] = v2;
-                    __syncwarp();
-                }
-            }
+            const double2* scr = c.tape + (size_t)t * kEigScratch;
+            for (int e = lane; e < NN; e += 32) mV[e] = scr[e];
+            if (lane < N) lam[lane] = reinterpret_cast<const double*>(scr + NN)[lane];
         }
+        __syncwarp();
         // ---- spectrum: l_p, e^{x_p / 2}, e^{x_p} ---------------------------------------------------------------------------------------
         if (lane < N) {
-            const double l = mH[lane * N + lane].x;
-            lam[lane] = l;
+            const double l = lam[lane];
             double sn, cs;
             sincos(0.5 * h * l, &sn, &cs);
             hx[lane] = make_double2(cs, -sn);
@@ -269,7 +307,7 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                const double2 v = mV[(k3 + i) * N + k];  // V^H[k3 + i][k] = conj(V[k][k3 + i])
+                const double2 v = mV[k * N + k3 + i];  // V^H[k3 + i][k] = conj(V[k][k3 + i])
                 Vr[i][k] = make_double2(v.x, -v.y);
             }
         auto mv_reg = [&](double2 (&y)[3], const double2* x) {
@@ -311,7 +349,7 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                     for (int i = 0; i < 3; ++i) {  // (A_j V)[k3 + i][cc] from the sparse rows of A_j
                         const int o0 = ((j * 2) * N + k3 + i) * W;
                         double2 u = make_double2(0.0, 0.0);
-                        for (int w = 0; w < W; ++w) cfma(u, ellv[o0 + w], mV[xo + ellc[o0 + w]]);
+                        for (int w = 0; w < W; ++w) cfma(u, ellv[o0 + w], mV[ellc[o0 + w] * N + cc]);
                         T[xo + k3 + i] = u;
                     }
                 }
@@ -337,7 +375,7 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int k = 0; k < N; ++k) Vr[i][k] = mV[k * N + k3 + i];
+            for (int k = 0; k < N; ++k) Vr[i][k] = mV[(k3 + i) * N + k];
         bulk_wait_read();  // the copy engine has finished reading the previous knot's image
         __syncwarp();
         {
@@ -351,7 +389,7 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                 const double l = lam[k];
                 const double2 w = cmul(e, vW0[xo + k]);
                 const double2 wt = make_double2(l * w.y, -l * w.x);  // (-i l) w
-                double2 vc = mV[k * N + cc];
+                double2 vc = mV[cc * N + k];
                 vc.y = -vc.y;
                 const double2 eb = cmul(e, vc);
 #pragma unroll
@@ -414,12 +452,7 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
         if (needH) {
             // second-order divided differences (needs Phi; independent of the staging buffer)
             for (int idx = lane; idx < EF3; idx += 32) {
-                int hi = 0;
-                while ((hi + 1) * (hi + 2) * (hi + 3) / 6 <= idx) ++hi;
-                const int rem = idx - hi * (hi + 1) * (hi + 2) / 6;
-                int mid = 0;
-                while ((mid + 1) * (mid + 2) / 2 <= rem) ++mid;
-                const int lo = rem - mid * (mid + 1) / 2;
+                const int tri = kTriples[idx], lo = tri & 15, mid = (tri >> 4) & 15, hi = tri >> 8;
                 const double t0 = h * lam[lo], t1 = h * lam[mid], t2 = h * lam[hi];
                 const double g01 = fabs(t0 - t1), g02 = fabs(t0 - t2), g12 = fabs(t1 - t2);
                 int u, v, w;
@@ -432,13 +465,12 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                     const double2 a = Phi[u * N + v], b = Phi[v * N + w];
                     const double inv = 1.0 / gap;
                     f = make_double2(-(a.y - b.y) * inv, (a.x - b.x) * inv);
-                } else {  // series about the mean: e^{-i m} sum_k (-i)^k h_k(d0, d1, d2) / (k + 2)!
-                    const double mean = (t0 + t1 + t2) * (1.0 / 3.0), d0 = t0 - mean, d1 = t1 - mean, d2 = t2 - mean;
-                    double pw = 1.0, q2 = 1.0, r3 = 1.0, re = 0.5, im = 0.0, inv_fact = 0.5;
+                } else {  // series about x_lo: e^{x_lo} sum_k (-i)^k h_k(0, d1, d2) / (k + 2)!,  h_k = complete homogeneous polynomial
+                    const double d1 = t1 - t0, d2 = t2 - t0;
+                    double q2 = 1.0, r3 = 1.0, re = 0.5, im = 0.0, inv_fact = 0.5;
 #pragma unroll
-                    for (int k = 1; k <= 13; ++k) {
-                        pw *= d0;
-                        q2 = fma(q2, d1, pw);
+                    for (int k = 1; k <= 15; ++k) {
+                        q2 *= d1;
                         r3 = fma(r3, d2, q2);
                         inv_fact /= (double)(k + 2);
                         const double term = r3 * inv_fact;
@@ -447,9 +479,7 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                         else if ((k & 3) == 3) im += term;
                         else re += term;
                     }
-                    double sn, cs;
-                    sincos(mean, &sn, &cs);
-                    f = cmul(make_double2(cs, -sn), make_double2(re, im));
+                    f = cmul(ex[lo], make_double2(re, im));
                 }
                 f3[idx] = f;
             }
@@ -595,6 +625,8 @@ int qck_launch_expeig(const QckLaunch& L, int sm_count, cudaStream_t stream, int
     if (c.kind != QCK_UNITARY_EXP || c.N != 9 || !c.antiherm || L.member_end - L.member_begin != 1 || c.nd < 1 || c.nd > 4) return (int)cudaErrorInvalidConfiguration;
     typedef void (*kern_t)(const QckLaunch);
     const kern_t kern = c.nd == 1 ? qck_expeig9_kernel<1> : (c.nd == 2 ? qck_expeig9_kernel<2> : (c.nd == 3 ? qck_expeig9_kernel<3> : qck_expeig9_kernel<4>));
+    const kern_t eig = c.nd == 1 ? qck_eig9_kernel<1> : (c.nd == 2 ? qck_eig9_kernel<2> : (c.nd == 3 ? qck_eig9_kernel<3> : qck_eig9_kernel<4>));
+    if (!c.tape || (long long)c.max_ctas < L.n_knots) return (int)cudaErrorInvalidConfiguration;  // eigen scratch: one record per knot
     const int nrec = QCK_SEG_HDR / 4 + c.nseg;
     const int hoff = qck_rs3_hoff(c);
     const size_t jbytes = (size_t)((hoff + 4 + 1) & ~1) * 8, hbytes = (size_t)((c.img_doubles - hoff + 4 + 1) & ~1) * 8;
@@ -624,6 +656,12 @@ int qck_launch_expeig(const QckLaunch& L, int sm_count, cudaStream_t stream, int
     if (dbg) fprintf(stderr, "[qcknot] spectral exponential kernel: N=9 nd=%d warps/CTA=%d smem=%zu B grid=%lld units=%d\n", c.nd, nwarps, smem, grid, c.nseg);
     QckLaunch L2 = L;
     L2.hoff = hoff;
+    {   // eigen-decompositions of all knots first: 8 warps per CTA, 2.6 KB of shared memory per warp
+        long long egrid = (L.n_knots + 7) / 8;
+        if (egrid > (long long)sm_count * 8) egrid = (long long)sm_count * 8;
+        eig<<<(unsigned)egrid, 256, 8 * 2 * ENN * 16, stream>>>(L2);
+        if (launches) ++*launches;
+    }
     kern<<<(unsigned)grid, nwarps * 32, smem, stream>>>(L2);
     if (launches) ++*launches;
     *done = true;

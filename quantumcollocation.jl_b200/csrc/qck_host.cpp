@@ -648,6 +648,18 @@ int build(qck_handle* h) {
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
         }
+        if (c.eig && h->device >= 0) {
+            // spectral kernel: eigenvectors + eigenvalues of every knot (86 double2 each), written by the eigen kernel and read by the
+            // main kernel of the same launch; one region per stream slot like the tapes (slot offset = tape_stride * max_ctas)
+            c.tape_levels = 0;
+            c.tape_stride = 86;
+            c.max_ctas = (int)std::max<long long>(1, h->T - 1);
+            void* tp = nullptr;
+            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas * QCK_TAPE_SLOTS)) != cudaSuccess)
+                return fail(h, QCK_ENOMEM, "eigen scratch allocation failed: %s", cudaGetErrorString(e));
+            C.allocs.push_back(tp);
+            c.tape = static_cast<double2*>(tp);
+        }
     }
 
     // ---- aux entries (derivative integrators inside the active range) ---------------------------------------------------------------
