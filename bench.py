@@ -321,9 +321,13 @@ def extra_records(args, dev, stream, n_gpus, rank0_devices):
 
     # the residual the north_star names: U_{t+1} - exp(-i H dt) U_t (F + J + H, the Hessian is ours: the reference has none)
     rec, _ = dev_arm("cz", args.T, "exponential")
-    # exact count of complex N x N x N products of the implemented algorithm: degree-8 Taylor with nd Frechet jets,
-    # s squarings with the jets, reverse sweep for the second derivatives
-    rec["note"] = "F+J+H; roofline = min(HBM, FP64), see DESIGN.md for the operation count"
+    # spectral algorithm (csrc/qck_expeig.cu): Jacobi eigen-decomposition + divided differences, ~0.30 MFLOP per
+    # 9-level knot (31 product-sized steps of 8 N^3 flop, the second-order contraction, ~27 Jacobi rounds); two launches per pass
+    flops = 0.30e6
+    rec["fp64"] = {"flops_per_eval": flops, "achieved_tflops": flops * rec["evals_per_s"] * 1e-12, "peak_tflops": FP64_PEAK_TFLOPS,
+                   "frac": flops * rec["evals_per_s"] * 1e-12 / FP64_PEAK_TFLOPS}
+    rec["note"] = ("F+J+H through the eigen + spectral kernels; roofline = min(HBM, FP64): neither binds (dependent latency at 8 warps "
+                   "per SM); the scaling-and-squaring kernel this replaces needs 1.48 MFLOP per knot and ran at 4.7 M evals/s")
     out["exponential"] = rec
     rec, _ = dev_arm("cz", 100000, "pade")
     out["cz_T100000"] = rec

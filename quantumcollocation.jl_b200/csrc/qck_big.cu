@@ -33,10 +33,12 @@ __device__ __forceinline__ double big_block_sum(double v, double* sh) {  // resu
     return s;
 }
 
-// C[r][c] = sum_k op(A)[r][k] B[k][c],  op = conjugate transpose when adj.  A: N x N, B: N x nc, column-major (ld = N).
+// C[r][c] = sum_k op(A)[r][k] B[k][c],  op = conjugate transpose when adj == 1; adj == 2: A is anti-Hermitian, A^H = -A, so the
+// product runs on the plain (bank-conflict-free) loads and is negated (the transposed loads of a column-major A put all the
+// lanes of a quarter-warp on one bank: 7.7-way conflicts in the first profile).  A: N x N, B: N x nc, column-major (ld = N).
 // The epilogue gets two vertically adjacent results at a time: epi(r, c, C[r][c], C[r+1][c], second row valid).
 template <class Epi>
-__device__ __forceinline__ void big_mm(const double2* __restrict__ A, bool adj, const double2* __restrict__ B, int N, int nc, Epi epi) {
+__device__ __forceinline__ void big_mm(const double2* __restrict__ A, int adj, const double2* __restrict__ B, int N, int nc, Epi epi) {
     const int ntr = (N + 1) >> 1, ntc = (nc + 1) >> 1;
     for (int tile = threadIdx.x; tile < ntr * ntc; tile += blockDim.x) {
         const int r0 = 2 * (tile % ntr), c0 = 2 * (tile / ntr);
@@ -45,10 +47,14 @@ __device__ __forceinline__ void big_mm(const double2* __restrict__ A, bool adj, 
         const int r1 = r1ok ? r0 + 1 : r0, c1 = c1ok ? c0 + 1 : c0;
         for (int k = 0; k < N; ++k) {
             double2 x0, x1;
-            if (adj) { x0 = A[k + N * r0]; x0.y = -x0.y; x1 = A[k + N * r1]; x1.y = -x1.y; }
+            if (adj == 1) { x0 = A[k + N * r0]; x0.y = -x0.y; x1 = A[k + N * r1]; x1.y = -x1.y; }
             else { x0 = A[r0 + N * k]; x1 = A[r1 + N * k]; }
             const double2 y0 = B[k + N * c0], y1 = B[k + N * c1];
             cfma(a00, x0, y0); cfma(a01, x0, y1); cfma(a10, x1, y0); cfma(a11, x1, y1);
+        }
+        if (adj == 2) {
+            a00 = make_double2(-a00.x, -a00.y); a01 = make_double2(-a01.x, -a01.y);
+            a10 = make_double2(-a10.x, -a10.y); a11 = make_double2(-a11.x, -a11.y);
         }
         epi(r0, c0, a00, a10, r1ok);  // rows r0, r0 + 1 of one column: neighbours in every iso-vector quantity
         if (c1ok) epi(r0, c1, a01, a11, r1ok);
@@ -73,6 +79,7 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
     double* const red = reinterpret_cast<double*>(T2 + NN);
     const bool needF = p.mask & QCK_EVAL_F, needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
     const bool free_time = c.free_time;
+    const int adjH = c.antiherm ? 2 : 1;  // A^H products: Hermitian Hamiltonians take the negated plain product
     const int nact = p.member_end - p.member_begin;
     const long long n_items = p.n_knots * nact;
     auto rdot = [](double2 x, double2 y) { return x.x * y.x + x.y * y.y; };
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
                 T1[e] = make_double2(-0.5 * s.x + c2h * acc.x, -0.5 * s.y + c2h * acc.y);
             }
         });
-        if (needH) big_mm(mA, true, mM, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+        if (needH) big_mm(mA, adjH, mM, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
             mW1[r + N * col] = a0;
             if (two) mW1[r + 1 + N * col] = a1;
         });
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
                     s_ah += -0.5 * rdot(z1, mS[e]) + c2h * rdot(z1, mX2[e]);
                 }
                 __syncthreads();
-                big_mm(mA, true, T1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+                big_mm(mA, adjH, T1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
                     double2 k0[2], k1[2];
                     for (int i = 0; i < (two ? 2 : 1); ++i) {
                         const int e = r + i + N * col;
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(256) qck_big_kernel(const QckLaunch p) {
         }
         // ---- S5: state x dt, a_i x a_j ------------------------------------------------------------------------------------------------------
         if (needH) {
-            if (free_time) big_mm(mA, true, mW1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
+            if (free_time) big_mm(mA, adjH, mW1, N, nc, [&](int r, int col, double2 a0, double2 a1, bool two) {
                 double2 k0[2], k1[2];
                 for (int i = 0; i < (two ? 2 : 1); ++i) {
                     const double2 acc = i ? a1 : a0, w1 = mW1[r + i + N * col];

@@ -33,7 +33,7 @@ namespace {
 // as TMA bulk copies (flush_units_lanes).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int EN = 9, ENN = 81, EN2 = 18, EDIM = 162, EF3 = 165;
-constexpr int kEigBufs = 7;       // T1, mV, vU0|T2, vM|Phi, vW0, vMt, vG  (+ ND buffers B_j)
+constexpr int kEigBufs = 6;       // T1|Gamma, mV, vU0|T2, vM|Phi, vW0|T3, vMt  (+ ND buffers B_j)
 constexpr int kEigScratch = 86;   // double2 per knot in the eigen scratch: V row-major (81) | l_0 .. l_8 (+ pad)
 
 __device__ __forceinline__ size_t expeig_warp_bytes(int nd, int img_bytes) {
@@ -78,13 +78,13 @@ __device__ __forceinline__ int f3_index(int a, int b, int c) {
 // registers per warp: the rotations' dependent latencies hide behind other knots, which the 7-warp main kernel cannot do).
 // Cyclic Jacobi with the round-robin ordering: round s rotates the 4 disjoint pairs ((s + l) mod 9, (s - l) mod 9), l = 1 .. 4
 // (level s sits out).  H and V are stacked into one 18 x 9 row-major matrix S = [H; V]; a round is
-//   (1) every lane forms the rotation of pair l = lane & 3 from the pivots,   J = [[c, conj(sg)], [-sg, c]]
+//   (1) every lane forms the rotation of pair l = lane >> 3 from the pivots,  J = [[c, conj(sg)], [-sg, c]]
 //   (2) pass R:  S <- S J    72 tasks (row, pair) of two elements each, same code for the rows of H and of V
 //   (3) pass L:  H <- J^H H  36 tasks (column, pair); the pivot entries are set to their exact values (0 / real)
 // Results go to the class's scratch (V row-major, then the eigenvalues): 1.4 KB per knot, L2-resident for the main kernel.
 // ------------------------------------------------------------------------------------------------------------
 template <int ND>
-__global__ void __launch_bounds__(256, 4) qck_eig9_kernel(const QckLaunch p) {
+__global__ void __launch_bounds__(256, 5) qck_eig9_kernel(const QckLaunch p) {
     constexpr int N = EN, NN = ENN;
     extern __shared__ __align__(16) unsigned char smem_all[];
     const QckClassDev& c = p.c;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256, 4) qck_eig9_kernel(const QckLaunch p) {
     const int* const acptr = gc + c.ell_stride + ND * (ND + 1) / 2 + 1 + c.kk_cap;
     const int* const acj = acptr + NN + 1;
     const int coff = p.moff_global[1];
-    const int lA = lane & 3, row0 = lane >> 2;
+    const int lA = lane >> 3, row0 = lane & 7;  // pair and row / column of this lane: a quarter-warp shares one pair (no bank conflicts)
     for (long long t = (long long)blockIdx.x * nwarps + warp; t < p.n_knots; t += (long long)gridDim.x * nwarps) {
         const double* zt = p.Z + t * c.zdim;
         double ctl[ND];
@@ -215,14 +215,15 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
     double2* const vM = vU0 + NN;   // multipliers; later Phi[p * N + q]
     double2* const vW0 = vM + NN;   // V^H U0 (column-major)
     double2* const vMt = vW0 + NN;  // V^H M  (column-major)
-    double2* const vG = vMt + NN;   // Gamma = W0 Mt^H, row-major
-    double2* const vB = vG + NN;    // B_j = V^H A_j V, row-major, j = 0 .. ND-1
+    double2* const vB = vMt + NN;   // B_j = V^H A_j V, row-major, j = 0 .. ND-1
     double2* const f3 = vB + ND * NN;  // exp[x_a, x_b, x_c], a <= b <= c
     double2* const ex = f3 + EF3;      // e^{x_p}
     double2* const hx = ex + N;        // e^{x_p / 2}
     double* const lam = reinterpret_cast<double*>(hx + N);
     double2* const T2 = vU0;
     double2* const Phi = vM;
+    double2* const vG = T1;   // Gamma = W0 Mt^H, row-major (phase 2: T1 is free)
+    double2* const T3 = vW0;  // phase 2 scratch once Gamma is formed
     {
         const double2* gv = c.cmat + (size_t)m * c.cmat_stride;
         const int* gc = c.ell_col + (size_t)m * c.icon_stride;
@@ -260,6 +261,12 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
             }
         }
         const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
+        double u1r[3], u1i[3];  // this lane's elements of U1
+        {
+            const double* z1 = zt + c.zdim + soff + cc * n2 + k3;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { u1r[i] = z1[i]; u1i[i] = z1[i + N]; }
+        }
         double* const baseF = p.F + t * c.dyn;
         double* const baseJ = p.J + t * p.nnzJ;
         double* const baseH = p.H + t * p.nnzH;
@@ -275,6 +282,11 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
             if (needH)
                 for (int b = lane * 16; b < dim; b += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(mn + b));
         }
+        double2 vin[3];  // eigenvectors (row-major) of H(a_t) from the eigen kernel's scratch
+        const double2* const scr = c.tape + (size_t)t * kEigScratch;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) vin[q] = lane + 32 * q < NN ? scr[lane + 32 * q] : make_double2(0.0, 0.0);
+        const double lam_in = lane < N ? reinterpret_cast<const double*>(scr + NN)[lane] : 0.0;
 #pragma unroll
         for (int q = 0; q < NLD; ++q) {
             const int idx = lane + 32 * q;
@@ -285,16 +297,13 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                 if (needH) reinterpret_cast<double*>(vM)[o] = inm[q];
             }
         }
-        // ---- eigenvectors (row-major) and eigenvalues of H(a_t) from the eigen kernel's scratch ------------------------------------
-        {
-            const double2* scr = c.tape + (size_t)t * kEigScratch;
-            for (int e = lane; e < NN; e += 32) mV[e] = scr[e];
-            if (lane < N) lam[lane] = reinterpret_cast<const double*>(scr + NN)[lane];
-        }
-        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (lane + 32 * q < NN) mV[lane + 32 * q] = vin[q];
         // ---- spectrum: l_p, e^{x_p / 2}, e^{x_p} ---------------------------------------------------------------------------------------
         if (lane < N) {
-            const double l = lam[lane];
+            const double l = lam_in;
+            lam[lane] = l;
             double sn, cs;
             sincos(0.5 * h * l, &sn, &cs);
             hx[lane] = make_double2(cs, -sn);
@@ -398,11 +407,9 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                     if (needJ) { cfma(yT[i], Vr[i][k], wt); cfma(yB[i], Vr[i][k], eb); }
                 }
             }
-            const double* z1 = zt + c.zdim + soff + cc * n2 + k3;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double ur = act ? z1[i] : 0.0, ui = act ? z1[i + N] : 0.0;
-                put(imgF, QO_R, i, make_double2(ur - yE[i].x, ui - yE[i].y));
+                put(imgF, QO_R, i, make_double2(u1r[i] - yE[i].x, u1i[i] - yE[i].y));
                 if (needJ) put(imgJ, QO_TH, i, make_double2(-yT[i].x, -yT[i].y));
             }
             if (needJ && act) {  // -iso(E), stored once, written N times (kron(I_N, .))
@@ -419,9 +426,17 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
         }
         if (needJ) {
 #pragma unroll 1
-            for (int j = 0; j < ND; ++j) {  // d/da_j = -V ((h B_j o Phi) W0)
-                double2* const T = (j & 1) ? T2 : T1;
+            for (int j = 0; j < ND; ++j) {  // d/da_j = -V (Lt_j W0),  Lt_j = h B_j o Phi
                 const double2* const Bj = vB + j * NN;
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int o = (k3 + i) * N + cc;
+                        const double2 l = cmul(Bj[o], Phi[o]);
+                        T1[o] = make_double2(h * l.x, h * l.y);
+                    }
+                }
+                __syncwarp();
                 double2 acc[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) acc[i] = make_double2(0.0, 0.0);
@@ -429,15 +444,15 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                 for (int q = 0; q < N; ++q) {
                     const double2 w = vW0[xo + q];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) cfma(acc[i], cmul(Bj[(k3 + i) * N + q], Phi[(k3 + i) * N + q]), w);
+                    for (int i = 0; i < 3; ++i) cfma(acc[i], T1[(k3 + i) * N + q], w);
                 }
                 if (act) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) T[xo + k3 + i] = make_double2(h * acc[i].x, h * acc[i].y);
+                    for (int i = 0; i < 3; ++i) T2[xo + k3 + i] = acc[i];
                 }
                 __syncwarp();
                 double2 y[3];
-                mv_reg(y, T + xo);
+                mv_reg(y, T2 + xo);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) put(imgJ, QO_TA + j, i, make_double2(-y[i].x, -y[i].y));
             }
@@ -518,9 +533,26 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                 for (int i = 0; i < 3; ++i) put(imgH, QO_KH0, i, make_double2(-y[i].x, -y[i].y));
             }
 #pragma unroll 1
-            for (int j = 0; j < ND; ++j) {  // state x a_j = -V ((h B_j o Phi)^H Mt)
-                double2* const T = (j & 1) ? T2 : T1;
+            for (int j = 0; j < ND; ++j) {  // state x a_j = -V (Lt_j^H Mt),  Lt_j = h B_j o Phi
                 const double2* const Bj = vB + j * NN;
+                double sp = 0.0;
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        // element (p = k3 + i, q = cc); a_j x dt takes  B_j,pq Gamma_qp e^{x_q} - i l_p Lt_j,pq Gamma_qp  from here
+                        const int pp = k3 + i, o = pp * N + cc;
+                        const double2 bq = Bj[o];
+                        const double2 l0 = cmul(bq, Phi[o]);
+                        const double2 l = make_double2(h * l0.x, h * l0.y);
+                        T2[o] = l;
+                        const double2 g = vG[cc * N + pp], e = ex[cc];
+                        const double lp = lam[pp];
+                        const double2 fac = cmul(bq, e);  // B e^{x_q}
+                        const double2 tot = make_double2(fac.x + lp * l.y, fac.y - lp * l.x);  // ... - i l_p Lt
+                        sp -= tot.x * g.x - tot.y * g.y;
+                    }
+                }
+                __syncwarp();
                 double2 acc[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) acc[i] = make_double2(0.0, 0.0);
@@ -529,30 +561,20 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
                     const double2 mv = vMt[xo + q];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        double2 l = cmul(Bj[q * N + k3 + i], Phi[q * N + k3 + i]);
+                        double2 l = T2[q * N + k3 + i];
                         l.y = -l.y;
                         cfma(acc[i], l, mv);
                     }
                 }
                 if (act) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) T[xo + k3 + i] = make_double2(h * acc[i].x, h * acc[i].y);
+                    for (int i = 0; i < 3; ++i) T3[xo + k3 + i] = acc[i];
                 }
                 __syncwarp();
                 double2 y[3];
-                mv_reg(y, T + xo);
-                double sp = 0.0;
+                mv_reg(y, T3 + xo);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    put(imgH, QO_KA0 + j, i, make_double2(-y[i].x, -y[i].y));
-                    // a_j x dt, element (p = k3 + i, q = cc):  B_j,pq Gamma_qp (e^{x_q} - i h l_p Phi_pq)
-                    const int pp = k3 + i;
-                    const double2 ph = Phi[pp * N + cc], e = ex[cc];
-                    const double hl = h * lam[pp];
-                    const double2 fac = make_double2(e.x + hl * ph.y, e.y - hl * ph.x);
-                    const double2 bg = cmul(Bj[pp * N + cc], vG[cc * N + pp]);
-                    if (act) sp -= bg.x * fac.x - bg.y * fac.y;
-                }
+                for (int i = 0; i < 3; ++i) put(imgH, QO_KA0 + j, i, make_double2(-y[i].x, -y[i].y));
                 sp = warp_sum(sp);
                 if (lane == 0 && c.pl_base[QO_HAH + j] >= 0) imgH[c.pl_base[QO_HAH + j]] = sp;
             }

@@ -216,6 +216,22 @@ def test_large_levels(levels, nd, ket):
     D.close()
 
 
+def test_large_levels_non_hermitian():
+    """Non-Hermitian generators (an effective Hamiltonian with loss): A^H products must take the conjugate-transpose path, not the
+    anti-Hermitian shortcut."""
+    rng = np.random.default_rng(21)
+    mk = lambda: 0.15 * (rng.normal(size=(18, 18)) + 1j * rng.normal(size=(18, 18)))
+    sys_ = qcknot.QuantumSystem(mk(), [mk(), mk()])
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.1, seed=4)
+    integrators = wl.build_integrators([sys_], traj)
+    D = qcknot.QuantumDynamics(integrators, traj)
+    O = oracle_dynamics(integrators, traj)
+    Z, mu = traj.datavec, wl.random_multipliers(D.n_blocks * D.dyn)
+    F, J, H = D.eval_all(Z, mu)
+    assert rel_err(F, O.F(Z)) < TOL and rel_err(J, O.dF(Z)) < TOL and rel_err(H, O.mu_d2F(Z, mu)) < TOL
+    D.close()
+
+
 _BIG_SCRIPT = r"""
 import sys, numpy as np
 sys.path.insert(0, {root!r})
