@@ -450,13 +450,23 @@ def main():
             mue = [wl.random_multipliers(nbe * D.dyn, seed=1234), wl.random_multipliers(nbe * D.dyn, seed=99)]
         Fh, Jh, Hh = np.empty(nbe * D.dyn), np.empty(nbe * D.nnzJ), np.empty(nbe * max(D.nnzH, 1))
         link = pcie_peak_gbs(dev)
+        # pageable caller arrays first (everything staged by the library), then the same arrays page-locked with qck_host_register
+        # (what the Julia shim does once with Ipopt's value buffers): F and the Hessian values then leave by DMA
+        # straight to their final place; the headline is the registered run
+        pg_s, pg_steps, _ = time_e2e(De, Ze, mue, Fh, Jh, Hh, 0.5 * args.min_seconds)
+        for arr in (Fh, Jh, Hh):
+            qcknot.host_register(arr)
         e2e_s, e2e_steps, st = time_e2e(De, Ze, mue, Fh, Jh, Hh, args.min_seconds)
+        for arr in (Fh, Jh, Hh):
+            qcknot.host_unregister(arr)
         moved = st["h2d_bytes"] + st["d2h_bytes"]
         written = Fh.nbytes + Jh.nbytes + Hh.nbytes
         e2e = {"value": nbe / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(st["h2d_bytes"]),
                "d2h_bytes_per_step": int(st["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_s * 1e3,
                "caller": "one host thread calling qck_eval_all" + (f" on one handle with n_gpus={n_gpus} (knot-sharded)" if n_gpus > 1 else ""),
-               "inputs": "pageable numpy arrays, two alternating trajectories (no cache hits)",
+               "inputs": "pageable numpy arrays for Z and mu, two alternating trajectories (no cache hits); output arrays page-locked once "
+                         "with qck_host_register",
+               "pageable_outputs": {"value": nbe / pg_s, "ms_per_step": pg_s * 1e3, "steps": pg_steps},
                "timing": "host wall clock around synchronous calls",
                "pcie": {"bytes_per_step": int(moved), "achieved_gbs": moved / e2e_s * 1e-9, "links": n_gpus,
                         "d2h_achieved_gbs": st["d2h_bytes"] / e2e_s * 1e-9,

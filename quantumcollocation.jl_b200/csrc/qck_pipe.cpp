@@ -328,6 +328,16 @@ void expand_knots(const std::vector<QckOwnSeg>& segs, const double* comp, long l
     _mm_sfence();  // the non-temporal stores are globally visible before this work item is reported done
 }
 
+// page-locked host memory the copy engine can write directly (qck_host_register / cudaHostRegister / cudaHostAlloc)?
+bool is_page_locked(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 double now_ms() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -371,11 +381,27 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     P.z_staged = false;  // (set again when every chunk has been staged)
 
     // ---- 2./3. chunk pipeline ----------------------------------------------------------------------------------------------------
-    const long long ck = P.chunk_knots, pk = P.piece_knots;
-    const int nchunks = (int)((nk + ck - 1) / ck);
-    int stride = 0, coff[3] = {0, 0, 0};  // compact row of this call: the requested arrays side by side
+    // DIRECT ARRAYS: a requested array without repeated blocks (F, the Hessian values) whose caller buffer is page-locked
+    // (qck_host_register, cudaHostRegister, cudaHostAlloc) needs no host work at all: the copy engine writes its runs straight to
+    // their final place, chunk by chunk, and the array leaves the compact row -- no pack, no staging slot, no expansion, and the
+    // host memory system sees its bytes once instead of three times.  (Measured and NOT done for the kron blocks of the Jacobian:
+    // strided 2-D copies of 2.6 KB rows reach 24-37 GB/s of a 57 GB/s link, profiles/r02_e2e_pipeline.txt.)
+    static const bool no_direct = getenv("QCK_NO_DIRECT") != nullptr;
+    bool dirA[3] = {false, false, false};
+    for (int a = 0; a < 3; ++a) {
+        if (!outs[a] || no_direct || P.cC[a] == 0 || h->own[a].size() > 4) continue;
+        bool rep = false;
+        for (auto& g : h->own[a]) rep = rep || g.nrep > 1 || g.len < 128;
+        dirA[a] = !rep && is_page_locked(outs[a]) && is_page_locked(outs[a] + nk * nnz[a] - 1);
+    }
+    int stride = 0, coff[3] = {0, 0, 0};  // compact row of this call: the requested arrays (minus the direct ones) side by side
     for (int a = 0; a < 3; ++a)
-        if (outs[a]) { coff[a] = stride; stride += P.cC[a]; }
+        if (outs[a] && !dirA[a]) { coff[a] = stride; stride += P.cC[a]; }
+    // transfer pieces: as many knots as fit a ring slot with THIS call's compact row (a single-array callback moves half the bytes
+    // per knot of the fused call: same piece size in bytes, half the per-piece overheads)
+    const long long ck = P.chunk_knots;
+    const long long pk = stride > 0 ? std::min(ck, std::max<long long>(P.piece_knots, P.slot_doubles / stride)) : ck;
+    const int nchunks = (int)((nk + ck - 1) / ck);
     struct Piece { int chunk; long long k0, kn; };
     std::vector<Piece> pieces;
     for (int c = 0; c < nchunks; ++c) {
@@ -403,7 +429,7 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     }
     for (int q = 0; q < npieces; ++q)
         for (int a = 0; a < 3; ++a)
-            if (outs[a] && P.cC[a] > 0) nitems[nchunks + q] += (int)((pieces[q].kn + per[a] - 1) / per[a]);
+            if (outs[a] && P.cC[a] > 0 && !dirA[a]) nitems[nchunks + q] += (int)((pieces[q].kn + per[a] - 1) / per[a]);
     QckJob job;
     job.init(nitems);
     double* const pinZ = P.pinZ; double* const pinMu = P.pinMu; double* const pinC = P.pinC;
@@ -430,7 +456,7 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
         const double* slot_h = pinC + (long long)(q % n_slots) * slot_doubles;
         int i = item;
         for (int a = 0; a < 3; ++a) {
-            if (!outs[a] || cC[a] == 0) continue;
+            if (!outs[a] || cC[a] == 0 || dirA[a]) continue;
             const int na = (int)((pc.kn + per[a] - 1) / per[a]);
             if (i < na) {
                 expand_knots(h->own[a], slot_h + coff[a], stride, outs[a] + pc.k0 * nnz[a], nnz[a], i * per[a], std::min(pc.kn, (i + 1) * per[a]));
@@ -465,9 +491,19 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
         }
         double* region = P.dC + (long long)(c & 1) * P.chunk_doubles;
         for (int a = 0; a < 3; ++a) {
-            if (!outs[a] || P.cC[a] == 0) continue;
+            if (!outs[a] || P.cC[a] == 0 || dirA[a]) continue;
             int e = qck_launch_pack(dfull[a] + k0 * nnz[a], region + coff[a], P.d_src[a], P.cC[a], stride, nnz[a], kn, st, &launches);
             if (e) return qck_fail(h, QCK_ECUDA, "pack kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+        }
+        for (int a = 0; a < 3; ++a) {  // direct arrays: this chunk's rows straight into the caller's array
+            if (!dirA[a]) continue;
+            for (auto& g : h->own[a]) {
+                double* dst = outs[a] + k0 * nnz[a] + g.full;
+                const double* src = dfull[a] + k0 * nnz[a] + g.full;
+                if (g.len == nnz[a]) QCK_CUDA_TRY(h, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)g.len * kn, cudaMemcpyDeviceToHost, st));
+                else QCK_CUDA_TRY(h, cudaMemcpy2DAsync(dst, sizeof(double) * nnz[a], src, sizeof(double) * nnz[a], sizeof(double) * g.len, (size_t)kn, cudaMemcpyDeviceToHost, st));
+                P.d2h_bytes += sizeof(double) * (long long)g.len * kn;
+            }
         }
         if (outs[2] && P.dShared) {  // ensemble child: local partial sums of the shared Hessian entries travel separately
             const int ns = (int)h->sh_pos.size();
@@ -489,7 +525,7 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
         const double* region = P.dC + (long long)(pc.chunk & 1) * P.chunk_doubles;
         double* slot_h = P.pinC + (long long)(q % P.n_slots) * P.slot_doubles;
         const long long rel = pc.k0 - (long long)pc.chunk * ck;
-        QCK_CUDA_TRY(h, cudaMemcpyAsync(slot_h, region + rel * stride, sizeof(double) * pc.kn * stride, cudaMemcpyDeviceToHost, st));
+        if (stride > 0) QCK_CUDA_TRY(h, cudaMemcpyAsync(slot_h, region + rel * stride, sizeof(double) * pc.kn * stride, cudaMemcpyDeviceToHost, st));
         P.d2h_bytes += sizeof(double) * pc.kn * stride;
         QCK_CUDA_TRY(h, cudaEventRecord(P.ev[q % P.n_slots], st));
         return QCK_OK;
@@ -535,7 +571,7 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     if (timing) {
         const double t_end = now_ms();
         fprintf(stderr, "[qcknot pipe] dev %d need %u compute %u: first piece after %.2f ms, last event after %.2f ms, done after %.2f ms (%d chunks, %d pieces of %d knots, ring %d)\n",
-                h->device, need, compute, t_first - t_begin, t_loop - t_begin, t_end - t_begin, nchunks, npieces, P.piece_knots, P.n_slots);
+                h->device, need, compute, t_first - t_begin, t_loop - t_begin, t_end - t_begin, nchunks, npieces, (int)pk, P.n_slots);
     }
     return h->uses_status ? qck_check_status(h) : QCK_OK;
 }

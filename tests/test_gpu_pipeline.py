@@ -68,6 +68,45 @@ def test_host_arrays_bit_identical_to_plain_copy(name, kw, chunk, monkeypatch):
     D.close()
 
 
+@pytest.mark.parametrize("name,kw,chunk", [("cz", {"T": 301}, None), ("cz", {"T": 1000}, "70"), ("hadamard", {"T": 777}, "100"),
+                                           ("cz", {"T": 130, "integrator": "exponential"}, "64"), ("ket", {"T": 500}, "128"),
+                                           ("sampling", {"T": 40, "n_systems": 6}, "64")])
+def test_page_locked_outputs_take_the_direct_path(name, kw, chunk, monkeypatch):
+    """Caller arrays registered with qck_host_register: arrays without repeated blocks (F, the Hessian values) are written by the
+    copy engine straight to their final place, chunk by chunk (no pack, no staging, no host copy); the Jacobian keeps the packed
+    path.  Same bytes over the link, bit-identical arrays, single-array callbacks included."""
+    if chunk:
+        monkeypatch.setenv("QCK_CHUNK_KNOTS", chunk)
+    systems, traj, integrators = wl.config(name, **kw)
+    D = qcknot.QuantumDynamics(integrators, traj)
+    Z = traj.datavec[: traj.T * D.zdim].copy()
+    mu = wl.random_multipliers(D.n_blocks * D.dyn)
+    Fr, Jr, Hr = _device_reference(D, Z, mu)
+    nb = D.n_blocks
+    F, J, H = np.full(nb * D.dyn, np.nan), np.full(nb * D.nnzJ, np.nan), np.full(nb * D.nnzH, np.nan)
+    for a in (F, J, H):
+        qcknot.host_register(a)
+    try:
+        D.eval_all(Z, mu, F, J, H)
+        assert np.array_equal(F, Fr) and np.array_equal(J, Jr) and np.array_equal(H, Hr)
+        n_comp = sum(int(D.compact_map(a)[:, 2].sum()) for a in (0, 1, 2))
+        assert D.transfer_stats()["d2h_bytes"] == 8 * nb * n_comp
+        J[:] = np.nan
+        H[:] = np.nan
+        D.dF(Z, out=J)  # cached on the device: copies only
+        assert np.array_equal(J, Jr) and D.transfer_stats()["h2d_bytes"] == 0
+        D.mu_d2F(Z, mu, out=H)  # a call whose only array goes the direct way (no transfer pieces at all)
+        assert np.array_equal(H, Hr) and D.transfer_stats()["d2h_bytes"] == 8 * nb * int(D.compact_map(2)[:, 2].sum())
+        Z2 = Z + 1e-7
+        F2, J2, H2 = D.eval_all(Z2, mu)  # pageable outputs on the same handle: the packed path
+        D.eval_all(Z2, mu, F, J, H)
+        assert np.array_equal(F, F2) and np.array_equal(J, J2) and np.array_equal(H, H2)
+    finally:
+        for a in (F, J, H):
+            qcknot.host_unregister(a)
+    D.close()
+
+
 def test_unchanged_z_is_uploaded_and_evaluated_once():
     """'the same Z is presented to F, dF, mu d2F in succession'."""
     systems, traj, integrators = wl.config("cz", T=200)

@@ -33,6 +33,18 @@ dt = (time.perf_counter() - t0) / steps
 st = D.transfer_stats()
 print(f"T={T} gpus={n_gpus}: eval_all {dt*1e3:.2f} ms/step  {nb/dt*1e-6:.3f} M evals/s  h2d {st['h2d_bytes']*1e-6:.1f} MB d2h {st['d2h_bytes']*1e-6:.1f} MB "
       f"pcie {(st['h2d_bytes']+st['d2h_bytes'])/dt*1e-9:.1f} GB/s  out {(F.nbytes+J.nbytes+H.nbytes)/dt*1e-9:.1f} GB/s host-written")
+# the same with page-locked (registered) output arrays: the library's direct path (no staging, no pack kernel)
+for a in (F, J, H):
+    qcknot.host_register(a)
+for i in range(3):
+    D.eval_all(Z[i & 1], mu[i & 1], F, J, H)
+t0 = time.perf_counter()
+for i in range(steps):
+    D.eval_all(Z[i & 1], mu[i & 1], F, J, H)
+dt = (time.perf_counter() - t0) / steps
+print(f"  registered outputs: eval_all {dt*1e3:.2f} ms/step  {nb/dt*1e-6:.3f} M evals/s  d2h {D.transfer_stats()['d2h_bytes']*1e-6:.1f} MB")
+for a in (F, J, H):
+    qcknot.host_unregister(a)
 for name, fn in (("F", lambda i: D.F(Z[i & 1], out=F)), ("J", lambda i: D.dF(Z[i & 1], out=J)), ("H", lambda i: D.mu_d2F(Z[i & 1], mu[i & 1], out=H))):
     fn(0); fn(1)
     t0 = time.perf_counter()
