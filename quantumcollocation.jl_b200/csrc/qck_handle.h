@@ -110,6 +110,10 @@ struct QckPipe {
     long long slot_doubles = 0, chunk_doubles = 0;
     int cC[3] = {0, 0, 0};             // compact doubles per knot of F, J, H
     const int* d_src[3] = {nullptr, nullptr, nullptr};  // compact index -> position inside the knot block
+    // variant for page-locked caller arrays: long unrepeated runs leave by direct (1-D / 2-D) copies, the compact row holds the rest
+    std::vector<QckOwnSeg> own_staged[3], own_direct[3];
+    int cS[3] = {0, 0, 0};
+    const int* d_src_staged[3] = {nullptr, nullptr, nullptr};
     // cache of the last inputs ("the same Z is presented to F, dF, mu d2F in succession")
     bool z_staged = false, z_on_device = false, mu_on_device = false;
     unsigned valid_mask = 0;           // value arrays on the device that belong to the staged Z (and mu for H)

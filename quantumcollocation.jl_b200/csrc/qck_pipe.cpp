@@ -295,6 +295,29 @@ int pipe_init(qck_handle* h) {
         QCK_CUDA_TRY(h, cudaMemcpy(d, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
         P.d_src[a] = d;
     }
+    for (int a = 0; a < 3; ++a) {  // split for page-locked caller arrays: runs of >= 4 KB without repetition go direct
+        int c = 0;
+        for (auto& g : h->own[a]) {
+            if (g.nrep == 1 && g.len >= 512) P.own_direct[a].push_back(g);
+            else { P.own_staged[a].push_back({g.full, c, g.len, g.nrep}); c += g.len; }
+        }
+        P.cS[a] = c;
+        if (P.own_direct[a].empty() || P.own_direct[a].size() > 4) {  // nothing to gain (or hundreds of copies per chunk): one variant only
+            P.own_direct[a].clear();
+            P.own_staged[a] = h->own[a];
+            P.cS[a] = P.cC[a];
+            P.d_src_staged[a] = P.d_src[a];
+            continue;
+        }
+        if (c == 0) continue;
+        std::vector<int> src;
+        for (auto& g : P.own_staged[a])
+            for (int k = 0; k < g.len; ++k) src.push_back(g.full + k);
+        int* d = nullptr;
+        QCK_CUDA_TRY(h, cudaMalloc((void**)&d, sizeof(int) * src.size()));
+        QCK_CUDA_TRY(h, cudaMemcpy(d, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
+        P.d_src_staged[a] = d;
+    }
     if (h->exclude_shared && !h->sh_pos.empty()) {
         const long long n = nk * (long long)h->sh_pos.size();
         QCK_CUDA_TRY(h, cudaHostAlloc((void**)&P.pinShared, sizeof(double) * n, cudaHostAllocPortable));
@@ -381,22 +404,27 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     P.z_staged = false;  // (set again when every chunk has been staged)
 
     // ---- 2./3. chunk pipeline ----------------------------------------------------------------------------------------------------
-    // DIRECT ARRAYS: a requested array without repeated blocks (F, the Hessian values) whose caller buffer is page-locked
-    // (qck_host_register, cudaHostRegister, cudaHostAlloc) needs no host work at all: the copy engine writes its runs straight to
-    // their final place, chunk by chunk, and the array leaves the compact row -- no pack, no staging slot, no expansion, and the
-    // host memory system sees its bytes once instead of three times.  (Measured and NOT done for the kron blocks of the Jacobian:
-    // strided 2-D copies of 2.6 KB rows reach 24-37 GB/s of a 57 GB/s link, profiles/r02_e2e_pipeline.txt.)
+    // DIRECT RUNS: when a requested array's caller buffer is page-locked (qck_host_register, cudaHostRegister, cudaHostAlloc), its
+    // long runs without repetition (all of F and of the Hessian values, the middle 834 doubles of a CZ knot's Jacobian) need no host
+    // work at all: the copy engine writes them straight to their final place, chunk by chunk (1-D copies, or 2-D copies of >= 4 KB
+    // rows), and they leave the compact row -- no pack, no staging slot, no expansion; the host memory system sees those bytes once
+    // instead of three times.  (Measured and NOT done for the kron blocks: strided 2-D copies of 2.6 KB rows in pieces reach 24-37
+    // GB/s of a 57 GB/s link, profiles/r02_e2e_pipeline.txt.)
     static const bool no_direct = getenv("QCK_NO_DIRECT") != nullptr;
-    bool dirA[3] = {false, false, false};
-    for (int a = 0; a < 3; ++a) {
-        if (!outs[a] || no_direct || P.cC[a] == 0 || h->own[a].size() > 4) continue;
-        bool rep = false;
-        for (auto& g : h->own[a]) rep = rep || g.nrep > 1 || g.len < 128;
-        dirA[a] = !rep && is_page_locked(outs[a]) && is_page_locked(outs[a] + nk * nnz[a] - 1);
-    }
-    int stride = 0, coff[3] = {0, 0, 0};  // compact row of this call: the requested arrays (minus the direct ones) side by side
+    bool dirA[3] = {false, false, false};  // this call uses the (staged | direct) split of the array
     for (int a = 0; a < 3; ++a)
-        if (outs[a] && !dirA[a]) { coff[a] = stride; stride += P.cC[a]; }
+        dirA[a] = outs[a] && !no_direct && !P.own_direct[a].empty() && is_page_locked(outs[a]) && is_page_locked(outs[a] + nk * nnz[a] - 1);
+    const std::vector<QckOwnSeg>* segsA[3];
+    int cA[3];
+    const int* srcA[3];
+    for (int a = 0; a < 3; ++a) {
+        segsA[a] = dirA[a] ? &P.own_staged[a] : &h->own[a];
+        cA[a] = dirA[a] ? P.cS[a] : P.cC[a];
+        srcA[a] = dirA[a] ? P.d_src_staged[a] : P.d_src[a];
+    }
+    int stride = 0, coff[3] = {0, 0, 0};  // compact row of this call: the staged runs of the requested arrays side by side
+    for (int a = 0; a < 3; ++a)
+        if (outs[a]) { coff[a] = stride; stride += cA[a]; }
     // transfer pieces: as many knots as fit a ring slot with THIS call's compact row (a single-array callback moves half the bytes
     // per knot of the fused call: same piece size in bytes, half the per-piece overheads)
     const long long ck = P.chunk_knots;
@@ -429,14 +457,13 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     }
     for (int q = 0; q < npieces; ++q)
         for (int a = 0; a < 3; ++a)
-            if (outs[a] && P.cC[a] > 0 && !dirA[a]) nitems[nchunks + q] += (int)((pieces[q].kn + per[a] - 1) / per[a]);
+            if (outs[a] && cA[a] > 0) nitems[nchunks + q] += (int)((pieces[q].kn + per[a] - 1) / per[a]);
     QckJob job;
     job.init(nitems);
     double* const pinZ = P.pinZ; double* const pinMu = P.pinMu; double* const pinC = P.pinC;
     const long long slot_doubles = P.slot_doubles;
     const int n_slots = P.n_slots;
-    const int* const cC = P.cC;
-    job.fn = [&, pinZ, pinMu, pinC, slot_doubles, n_slots, cC](int piece, int item) {
+    job.fn = [&, pinZ, pinMu, pinC, slot_doubles, n_slots](int piece, int item) {
         if (piece < nchunks) {  // staging
             long long o, e;
             z_range(piece, o, e);
@@ -452,14 +479,16 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
             return;
         }
         const int q = piece - nchunks;
+        static const bool skip_expand = getenv("QCK_DIAG_SKIP_EXPAND") != nullptr;  // diagnosis only: transport without the host half
+        if (skip_expand) return;
         const Piece& pc = pieces[q];
         const double* slot_h = pinC + (long long)(q % n_slots) * slot_doubles;
         int i = item;
         for (int a = 0; a < 3; ++a) {
-            if (!outs[a] || cC[a] == 0 || dirA[a]) continue;
+            if (!outs[a] || cA[a] == 0) continue;
             const int na = (int)((pc.kn + per[a] - 1) / per[a]);
             if (i < na) {
-                expand_knots(h->own[a], slot_h + coff[a], stride, outs[a] + pc.k0 * nnz[a], nnz[a], i * per[a], std::min(pc.kn, (i + 1) * per[a]));
+                expand_knots(*segsA[a], slot_h + coff[a], stride, outs[a] + pc.k0 * nnz[a], nnz[a], i * per[a], std::min(pc.kn, (i + 1) * per[a]));
                 return;
             }
             i -= na;
@@ -491,13 +520,13 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
         }
         double* region = P.dC + (long long)(c & 1) * P.chunk_doubles;
         for (int a = 0; a < 3; ++a) {
-            if (!outs[a] || P.cC[a] == 0 || dirA[a]) continue;
-            int e = qck_launch_pack(dfull[a] + k0 * nnz[a], region + coff[a], P.d_src[a], P.cC[a], stride, nnz[a], kn, st, &launches);
+            if (!outs[a] || cA[a] == 0) continue;
+            int e = qck_launch_pack(dfull[a] + k0 * nnz[a], region + coff[a], srcA[a], cA[a], stride, nnz[a], kn, st, &launches);
             if (e) return qck_fail(h, QCK_ECUDA, "pack kernel launch: %s", cudaGetErrorString((cudaError_t)e));
         }
-        for (int a = 0; a < 3; ++a) {  // direct arrays: this chunk's rows straight into the caller's array
+        for (int a = 0; a < 3; ++a) {  // direct runs: this chunk's rows straight into the caller's array
             if (!dirA[a]) continue;
-            for (auto& g : h->own[a]) {
+            for (auto& g : P.own_direct[a]) {
                 double* dst = outs[a] + k0 * nnz[a] + g.full;
                 const double* src = dfull[a] + k0 * nnz[a] + g.full;
                 if (g.len == nnz[a]) QCK_CUDA_TRY(h, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)g.len * kn, cudaMemcpyDeviceToHost, st));
@@ -660,7 +689,9 @@ void qck_pipe_destroy(qck_handle* h) {
     if (P.pinShared) cudaFreeHost(P.pinShared);
     if (P.dC) cudaFree(P.dC);
     if (P.dShared) cudaFree(P.dShared);
-    for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a) {
+        if (P.d_src_staged[a] && P.d_src_staged[a] != P.d_src[a]) cudaFree(const_cast<int*>(P.d_src_staged[a]));
         if (P.d_src[a]) cudaFree(const_cast<int*>(P.d_src[a]));
+    }
     P = QckPipe{};
 }
