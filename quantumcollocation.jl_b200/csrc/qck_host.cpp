@@ -438,6 +438,10 @@ int build(qck_handle* h) {
         c.eig = (eig_knob && c.kind == QCK_UNITARY_EXP && c.N == 9 && c.nd >= 1 && c.nd <= 4 && c.antiherm && C.member_end - C.member_begin == 1 &&
                  h->npart == 0) ? 1 : 0;
         if (c.eig) c.rs3 = 1;
+        // exponential unitaries and kets of 2..4 levels with Hermitian Hamiltonians: the spectral column kernels (qck_colexp.cu;
+        // QCK_COLEXP=0: the scaling-and-squaring kernel)
+        static const int colexp_knob = getenv("QCK_COLEXP") ? atoi(getenv("QCK_COLEXP")) : 1;
+        c.colexp = (colexp_knob && (c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && c.N >= 2 && c.N <= 4 && c.nd >= 1 && c.nd <= 4 && c.antiherm) ? 1 : 0;
         for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
         std::vector<int> qdst((size_t)nm * QO_COUNT, -1);  // per member: first destination of every output quantity
         {
@@ -604,7 +608,7 @@ int build(qck_handle* h) {
         }
         // column kernel (levels <= 4): dense drive matrices A_j = -i H_j, row-major, and the per-member destinations
         c.dense_aj = nullptr; c.qdst = nullptr;
-        if ((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && (N <= 4 || c.big)) {
+        if (((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && (N <= 4 || c.big)) || c.colexp) {
             std::vector<double2> daj((size_t)nm * nd * N * N);
             for (int m2 = 0; m2 < nm; ++m2) {
                 const Integ& I = h->integ[C.members[m2]];
@@ -636,7 +640,7 @@ int build(qck_handle* h) {
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
         }
-        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0 && !c.eig) {  // (the spectral kernel has no tape)
+        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0 && !c.eig && !c.colexp) {  // (the spectral kernels have no tape)
             // reverse-sweep tape of the exponential Hessian: 7 Horner steps x nd jets + 16 squaring levels x (1 + nd) matrices per CTA
             c.tape_levels = 16;
             c.tape_stride = (long long)(7 * nd + c.tape_levels * (1 + nd)) * N * N;
@@ -645,6 +649,17 @@ int build(qck_handle* h) {
             // (QCK_TAPE_SLOTS copies: launches on the handle's own stream and on the two pipeline streams may overlap)
             if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas * QCK_TAPE_SLOTS)) != cudaSuccess)
                 return fail(h, QCK_ENOMEM, "tape allocation failed: %s", cudaGetErrorString(e));
+            C.allocs.push_back(tp);
+            c.tape = static_cast<double2*>(tp);
+        }
+        if (c.colexp && h->device >= 0) {
+            // spectral column kernels: eigenvectors + eigenvalues of every (knot, active member) item, one region per stream slot
+            c.tape_levels = 0;
+            c.tape_stride = (long long)qck_colexp_scratch_rec(N);
+            c.max_ctas = (int)std::max<long long>(1, (h->T - 1) * (long long)std::max(1, C.member_end - C.member_begin));
+            void* tp = nullptr;
+            if ((e = cudaMalloc(&tp, sizeof(double2) * (size_t)c.tape_stride * c.max_ctas * QCK_TAPE_SLOTS)) != cudaSuccess)
+                return fail(h, QCK_ENOMEM, "eigen scratch allocation failed: %s", cudaGetErrorString(e));
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
         }

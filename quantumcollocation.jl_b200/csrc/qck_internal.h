@@ -83,6 +83,7 @@ struct QckClassDev {
     int free_time, dt_off, zdim, dyn;
     int antiherm;  // every member's Hamiltonians are Hermitian: A(a) = -i H(a) is anti-Hermitian
     int big;       // the class runs on the large-level kernel (qck_big.cu): operands in shared memory, outputs straight to the arrays
+    int colexp;    // exponential class of 2..4 levels that runs on the spectral column kernels (qck_colexp.cu)
     int eig;       // exponential class that runs on the spectral kernel (qck_expeig.cu); built with the rs3 placement (rs3 = 1)
     int rs3;       // > 0: built for the three-warps-per-knot kernel (qck_rs3.cu) with this many knots per CTA: parity-matched
                    // image placement, unit table [phase][warp] (see qck_host.cpp)
@@ -192,6 +193,8 @@ size_t qck_big_smem(const QckClassDev& c);
 size_t qck_rs3_smem(const QckClassDev& c, int hoff, int kpc);
 int qck_rs3_hoff(const QckClassDev& c);
 int qck_launch_expeig(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+int qck_launch_colexp(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+size_t qck_colexp_scratch_rec(int N);
 int qck_fused_aux_limit(void);
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,

@@ -1506,6 +1506,8 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         rc = qck_launch_rowslice9(L, sm_count, stream, launches, &done);
         if (!rc && !done && c.rs3) return (int)cudaErrorInvalidConfiguration;  // the class tables were built for the row-slice kernels only
         if (rc || done) return rc;
+        rc = qck_launch_colexp(L, sm_count, stream, launches, &done);
+        if (rc || done) return rc;
         rc = qck_launch_column(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
     }

@@ -120,6 +120,40 @@ def test_spectral_exponential_large_norm():
     check([sys_], traj, integrators, eval_hessian=True)
 
 
+# ---- 2..4-level exponential unitaries and kets: the spectral column kernels (qck_colexp.cu) -----------------------------------------
+@pytest.mark.parametrize("levels,nd,ket", [(2, 1, False), (2, 3, False), (3, 2, False), (3, 4, False), (4, 1, False), (4, 2, False), (4, 4, False),
+                                           (2, 2, True), (3, 3, True), (4, 2, True), (4, 4, True)])
+@pytest.mark.parametrize("free_time", [True, False])
+def test_spectral_column_exponential(levels, nd, ket, free_time):
+    """One lane per item diagonalises H(a_t) (Jacobi in registers), one lane per column evaluates the divided-difference forms:
+    dense random Hamiltonians, every level count / drive count / state kind the kernels are instantiated for."""
+    sys_ = wl.random_hermitian_system(levels, nd, seed=300 + 10 * levels + nd, scale=0.6)
+    traj = wl.random_pulse_trajectory([sys_], 7, 0.3, seed=21 + nd, free_time=free_time, ket=ket, n_states=2 if ket else 1)
+    integrators = wl.build_integrators([sys_], traj, integrator="exponential", ket=ket)
+    check([sys_], traj, integrators, eval_hessian=True)
+    check([sys_], traj, integrators, eval_hessian=False)
+
+
+@pytest.mark.parametrize("amp", [0.0, 1e-9, 1e-3])
+def test_spectral_column_exponential_degenerate_levels(amp):
+    """Hadamard problem without drift: H(a) = a_x X + a_y Y has the levels +-|a| -- exactly degenerate at a = 0, nearly so for tiny
+    controls; a 4-level ensemble whose members share the controls goes through the partial columns."""
+    systems, traj, integrators = wl.config("hadamard", T=9, integrator="exponential")
+    a = traj["a"]
+    a[:] = amp * np.sign(a + 1e-30) * (1.0 + np.arange(traj.T)[None, :])
+    check(systems, traj, integrators, eval_hessian=True)
+    systems, traj, integrators = wl.config("sampling", T=4, n_systems=5, integrator="exponential")
+    a = traj["a"]
+    a[:] = amp * np.sign(a + 1e-30)
+    check(systems, traj, integrators, eval_hessian=True)
+
+
+def test_spectral_column_exponential_large_norm():
+    sys_ = wl.random_hermitian_system(4, 2, seed=5, scale=5.0)
+    traj = wl.random_pulse_trajectory([sys_], 5, 2.0, seed=6)
+    check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=True)
+
+
 @pytest.mark.parametrize("order", [6, 8, 10, 12])
 @pytest.mark.parametrize("name,kw", [("hadamard", {"T": 5}), ("hadamard", {"T": 4, "free_time": False}), ("cz", {"T": 3}), ("ket", {"T": 5})])
 def test_general_pade_orders(order, name, kw):
@@ -183,7 +217,9 @@ print("variant ok")
                                          ("cz", {}, {"QCK_ROWSLICE_DB": "1", "QCK_ROWSLICE_BW": "0"}),
                                          ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"}),
                                          ("ket", {}, {"QCK_COLUMN": "0"}), ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG": "0"}),
-                                         ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG_WARPS": "3"})])
+                                         ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG_WARPS": "3"}),
+                                         ("hadamard", {"integrator": "exponential"}, {"QCK_COLEXP": "0"}),
+                                         ("sampling", {"n_systems": 4, "integrator": "exponential"}, {"QCK_COLEXP": "0"})])
 def test_kernel_variants(name, kw, env):
     """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
     (QCK_RS3=0 / QCK_COLUMN=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives / a smaller CTA, the
