@@ -335,6 +335,11 @@ def extra_records(args, dev, stream, n_gpus, rank0_devices):
     rec["note"] = ("F+J+H through the eigen + spectral kernels; roofline = min(HBM, FP64): neither binds (dependent latency at 8 warps "
                    "per SM); the scaling-and-squaring kernel this replaces needs 1.48 MFLOP per knot and ran at 4.7 M evals/s")
     out["exponential"] = rec
+    # the same residual on the small configurations (spectral column kernels, csrc/qck_colexp.cu)
+    rec, _ = dev_arm("hadamard", 100000, "exponential")
+    out["hadamard_exponential_T100000"] = rec
+    rec, _ = dev_arm("sampling", 200, "exponential", systems=256)
+    out["sampling_exponential_256_T200"] = rec
     rec, _ = dev_arm("cz", 100000, "pade")
     out["cz_T100000"] = rec
     rec, _ = dev_arm("sampling", 200, "pade", systems=256)
