@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # (source, extra flags, object tag): the rs3 kernel file is compiled once per drive count, in parallel
-UNITS = [("csrc/qck_kernels.cu", [], ""), ("csrc/qck_rowslice.cu", [], ""), ("csrc/qck_column.cu", [], ""), ("csrc/qck_big.cu", [], ""), ("csrc/qck_expeig.cu", [], ""), ("csrc/qck_colexp.cu", [], ""), ("csrc/qck_pack.cu", [], ""),
+UNITS = [("csrc/qck_kernels.cu", [], ""), ("csrc/qck_rowslice.cu", [], ""), ("csrc/qck_column.cu", [], ""), ("csrc/qck_big.cu", [], ""), ("csrc/qck_expeig.cu", [], ""), ("csrc/qck_colexp.cu", [], ""), ("csrc/qck_genexp.cu", [], ""), ("csrc/qck_pack.cu", [], ""),
          ("csrc/qck_objective.cu", [], ""), ("csrc/qck_rollout.cu", [], ""),
          ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=1"], ".nd1"), ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=2"], ".nd2"),
          ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=3"], ".nd3"), ("csrc/qck_rs3.cu", ["-DQCK_RS3_ND=4"], ".nd4"),

@@ -442,6 +442,11 @@ int build(qck_handle* h) {
         // QCK_COLEXP=0: the scaling-and-squaring kernel)
         static const int colexp_knob = getenv("QCK_COLEXP") ? atoi(getenv("QCK_COLEXP")) : 1;
         c.colexp = (colexp_knob && (c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && c.N >= 2 && c.N <= 4 && c.nd >= 1 && c.nd <= 4 && c.antiherm) ? 1 : 0;
+        // every other exponential class with Hermitian Hamiltonians up to 16 levels (5..8, 10..16 levels, 9-level kets and ensembles):
+        // the generic spectral kernel (qck_genexp.cu; QCK_GENEXP=0: the scaling-and-squaring kernel)
+        static const int genexp_knob = getenv("QCK_GENEXP") ? atoi(getenv("QCK_GENEXP")) : 1;
+        c.genexp = (genexp_knob && !c.eig && !c.colexp && (c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && c.N >= 5 && c.N <= 16 && c.nd >= 1 &&
+                    c.nd <= 4 && c.antiherm && qck_genexp_warp_bytes(c.N, c.kind == QCK_KET_EXP ? 1 : c.N, c.nd) <= 227 * 1024) ? 1 : 0;
         for (int q2 = 0; q2 < QO_COUNT; ++q2) { c.pl_base[q2] = -1; c.pl_stride[q2] = 0; }
         std::vector<int> qdst((size_t)nm * QO_COUNT, -1);  // per member: first destination of every output quantity
         {
@@ -553,7 +558,7 @@ int build(qck_handle* h) {
             if (c.rs3 < 5) c.rs3 = 1;
         }
         c.big = big_ok && !c.rs3 && (big_knob || (size_t)c.sm_bytes > 227 * 1024 - 4096 || c.img_doubles >= 32000) ? 1 : 0;
-        if (!c.rs3 && !c.big && (size_t)c.sm_bytes > 227 * 1024 - 4096)
+        if (!c.rs3 && !c.big && !c.genexp && (size_t)c.sm_bytes > 227 * 1024 - 4096)
             return fail(h, QCK_EINVAL, "levels=%d with %d drives needs %d bytes of shared memory per knot; this build supports at most %d", c.N, c.nd, c.sm_bytes, 227 * 1024 - 4096);
         c.cmat_stride = N * N + c.ell_stride + kk_cap + ac_cap;
         std::vector<double2> cmat((size_t)nm * c.cmat_stride, make_double2(0.0, 0.0));
@@ -608,7 +613,7 @@ int build(qck_handle* h) {
         }
         // column kernel (levels <= 4): dense drive matrices A_j = -i H_j, row-major, and the per-member destinations
         c.dense_aj = nullptr; c.qdst = nullptr;
-        if (((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && (N <= 4 || c.big)) || c.colexp) {
+        if (((c.kind == QCK_UNITARY_PADE || c.kind == QCK_KET_PADE) && c.order == 4 && (N <= 4 || c.big)) || c.colexp || c.genexp) {
             std::vector<double2> daj((size_t)nm * nd * N * N);
             for (int m2 = 0; m2 < nm; ++m2) {
                 const Integ& I = h->integ[C.members[m2]];
@@ -640,7 +645,7 @@ int build(qck_handle* h) {
             C.allocs.push_back(tp);
             c.tape = static_cast<double2*>(tp);
         }
-        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0 && !c.eig && !c.colexp) {  // (the spectral kernels have no tape)
+        if ((c.kind == QCK_UNITARY_EXP || c.kind == QCK_KET_EXP) && h->eval_hessian && h->device >= 0 && !c.eig && !c.colexp && !c.genexp) {  // (the spectral kernels have no tape)
             // reverse-sweep tape of the exponential Hessian: 7 Horner steps x nd jets + 16 squaring levels x (1 + nd) matrices per CTA
             c.tape_levels = 16;
             c.tape_stride = (long long)(7 * nd + c.tape_levels * (1 + nd)) * N * N;

@@ -83,6 +83,7 @@ struct QckClassDev {
     int free_time, dt_off, zdim, dyn;
     int antiherm;  // every member's Hamiltonians are Hermitian: A(a) = -i H(a) is anti-Hermitian
     int big;       // the class runs on the large-level kernel (qck_big.cu): operands in shared memory, outputs straight to the arrays
+    int genexp;    // exponential class that runs on the generic spectral kernel (qck_genexp.cu): 5..16 levels, 9-level kets / ensembles
     int colexp;    // exponential class of 2..4 levels that runs on the spectral column kernels (qck_colexp.cu)
     int eig;       // exponential class that runs on the spectral kernel (qck_expeig.cu); built with the rs3 placement (rs3 = 1)
     int rs3;       // > 0: built for the three-warps-per-knot kernel (qck_rs3.cu) with this many knots per CTA: parity-matched
@@ -195,6 +196,8 @@ int qck_rs3_hoff(const QckClassDev& c);
 int qck_launch_expeig(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 int qck_launch_colexp(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 size_t qck_colexp_scratch_rec(int N);
+int qck_launch_genexp(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
+size_t qck_genexp_warp_bytes(int N, int nc, int nd);
 int qck_fused_aux_limit(void);
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,

@@ -1508,6 +1508,8 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         if (rc || done) return rc;
         rc = qck_launch_colexp(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
+        rc = qck_launch_genexp(L, sm_count, stream, launches, &done);
+        if (rc || done) return rc;
         rc = qck_launch_column(L, sm_count, stream, launches, &done);
         if (rc || done) return rc;
     }

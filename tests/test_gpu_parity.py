@@ -154,6 +154,33 @@ def test_spectral_column_exponential_large_norm():
     check([sys_], traj, wl.build_integrators([sys_], traj, integrator="exponential"), eval_hessian=True)
 
 
+# ---- every other Hermitian exponential class up to 16 levels: the generic spectral kernel (qck_genexp.cu) ---------------------------
+@pytest.mark.parametrize("levels,nd,ket", [(5, 2, False), (6, 1, False), (7, 3, False), (8, 4, False), (10, 2, False), (12, 2, False), (16, 2, False),
+                                           (5, 2, True), (8, 3, True), (9, 4, True), (16, 1, True)])
+@pytest.mark.parametrize("free_time", [True, False])
+def test_generic_spectral_exponential(levels, nd, ket, free_time):
+    """One warp per item, run-time level count (odd and even: the two round-robin orderings of the Jacobi sweeps), unitaries and
+    kets, 1..4 drives."""
+    sys_ = wl.random_hermitian_system(levels, nd, seed=500 + 10 * levels + nd, scale=0.4)
+    traj = wl.random_pulse_trajectory([sys_], 4, 0.25, seed=31 + nd, free_time=free_time, ket=ket, n_states=2 if ket else 1)
+    integrators = wl.build_integrators([sys_], traj, integrator="exponential", ket=ket)
+    check([sys_], traj, integrators, eval_hessian=True)
+    if levels in (5, 8):
+        check([sys_], traj, integrators, eval_hessian=False)
+
+
+def test_generic_spectral_exponential_ensemble_and_degenerate():
+    """Three 9-level systems sharing the controls (shared-control Hessian entries through the partial columns); the CZ drift with
+    vanishing controls as a 9-level KET problem (exactly degenerate levels)."""
+    sy = [wl.random_hermitian_system(9, 2, seed=s, scale=0.4) for s in (11, 12, 13)]
+    traj = wl.random_pulse_trajectory(sy, 4, 0.2, seed=3)
+    check(sy, traj, wl.build_integrators(sy, traj, integrator="exponential"), eval_hessian=True)
+    cz = wl.two_transmon_cz_system()
+    traj = wl.random_pulse_trajectory([cz], 4, 1.0, seed=4, ket=True, n_states=2)
+    traj["a"][:] = 0.0
+    check([cz], traj, wl.build_integrators([cz], traj, integrator="exponential", ket=True), eval_hessian=True)
+
+
 @pytest.mark.parametrize("order", [6, 8, 10, 12])
 @pytest.mark.parametrize("name,kw", [("hadamard", {"T": 5}), ("hadamard", {"T": 4, "free_time": False}), ("cz", {"T": 3}), ("ket", {"T": 5})])
 def test_general_pade_orders(order, name, kw):
@@ -216,10 +243,11 @@ print("variant ok")
                                          ("cz", {}, {"QCK_ROWSLICE_BW": "0"}), ("cz", {}, {"QCK_ROWSLICE_BW": "0", "QCK_ROWSLICE_SPREAD": "0"}),
                                          ("cz", {}, {"QCK_ROWSLICE_DB": "1", "QCK_ROWSLICE_BW": "0"}),
                                          ("hadamard", {}, {"QCK_COLUMN": "0"}), ("sampling", {"n_systems": 5}, {"QCK_COLUMN": "0"}),
-                                         ("ket", {}, {"QCK_COLUMN": "0"}), ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG": "0"}),
+                                         ("ket", {}, {"QCK_COLUMN": "0"}), ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG": "0", "QCK_GENEXP": "0"}),
                                          ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG_WARPS": "3"}),
                                          ("hadamard", {"integrator": "exponential"}, {"QCK_COLEXP": "0"}),
-                                         ("sampling", {"n_systems": 4, "integrator": "exponential"}, {"QCK_COLEXP": "0"})])
+                                         ("sampling", {"n_systems": 4, "integrator": "exponential"}, {"QCK_COLEXP": "0"}),
+                                         ("cz", {"integrator": "exponential"}, {"QCK_EXPEIG": "0", "QCK_GENEXP": "1"})])
 def test_kernel_variants(name, kw, env):
     """The launch knobs are read once per process, so each variant runs in its own interpreter: the tiled DFMA kernel
     (QCK_RS3=0 / QCK_COLUMN=0), its FP64 tensor-core (DMMA) variant, the row-slice kernel with dense drives / a smaller CTA, the

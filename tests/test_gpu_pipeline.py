@@ -154,8 +154,11 @@ def test_full_size_cz_through_pipeline_matches_plain_copy():
 
 def test_exponential_out_of_range_is_reported():
     """ADVICE: ||dt*G||_1 > 4096 needs more squarings than the Hessian tape of the scaling-and-squaring kernel holds: an error,
-    not a silent truncation.  (5 levels: the class runs on that kernel; the spectral kernel of the 9-level problems has no limit.)"""
-    sys_ = wl.random_hermitian_system(5, 2, seed=3, scale=1.0)
+    not a silent truncation.  (A non-Hermitian generator: the class runs on that kernel; the spectral kernels of the Hermitian
+    classes have no such limit.)"""
+    rng = np.random.default_rng(3)
+    mk = lambda: 0.3 * (rng.normal(size=(5, 5)) + 1j * rng.normal(size=(5, 5)))
+    sys_ = qcknot.QuantumSystem(mk(), [mk(), mk()])
     traj = wl.random_pulse_trajectory([sys_], 4, 0.2, seed=11)
     D = qcknot.QuantumDynamics(wl.build_integrators([sys_], traj, integrator="exponential"), traj)
     Z = traj.datavec.copy()
