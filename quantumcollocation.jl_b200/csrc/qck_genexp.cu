@@ -16,8 +16,8 @@ namespace {
 __host__ __device__ inline int ge_tet(int n) { return n * (n + 1) * (n + 2) / 6; }
 // double2 units of one warp's shared memory
 __host__ __device__ inline size_t ge_warp_units(int N, int nc, int nd) {
-    const int NN = N * N, NS = N * nc;
-    return (size_t)2 * NN /* S = [H; V] */ + 4 * NS /* U0|T2, M, W0, Mt */ + (size_t)nd * NN + 3 * NN /* Phi, Gamma, T3 */ + ge_tet(N) + 2 * N /* ex, hx */ +
+    const int NL = N * (N | 1), NS = N * nc;  // square matrices: odd leading dimension (no bank conflicts on column walks)
+    return (size_t)2 * NL /* S = [H; V] */ + 4 * NS /* U0|T2, M, W0, Mt */ + (size_t)nd * NL + 3 * NL /* Phi, Gamma, T3 */ + ge_tet(N) + 2 * N /* ex, hx */ +
            (N + 1) / 2 /* lam */ + 2 * ((N + 1) / 2) /* rotations */ + 2;
 }
 
@@ -26,20 +26,21 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
     extern __shared__ __align__(16) unsigned char smem_all[];
     const QckClassDev& c = p.c;
     const int N = c.N, nc = KET ? 1 : N, NN = N * N, NS = N * nc, n2 = 2 * N, blk = n2 * n2, W = c.W, P = N / 2;
+    const int LD = N | 1, NL = N * LD;  // square matrices in shared memory: element (r, k) at r * LD + k, LD odd
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)(blockDim.x >> 5);
     const bool needF = p.mask & QCK_EVAL_F, needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
     const bool free_time = c.free_time;
     double2* const S = reinterpret_cast<double2*>(smem_all) + (size_t)warp * wunits;  // rows 0..N-1: H, rows N..2N-1: V (row-major)
-    double2* const mV = S + NN;
-    double2* const vU0 = mV + NN;      // columns of U0: [c * N + r]; later scratch T2
+    double2* const mV = S + NL;
+    double2* const vU0 = mV + NL;      // columns of U0: [c * N + r]; later scratch T2
     double2* const vM = vU0 + NS;
     double2* const vW0 = vM + NS;      // V^H U0
     double2* const vMt = vW0 + NS;     // V^H M
     double2* const vB = vMt + NS;      // B_j = V^H A_j V, row-major
-    double2* const Phi = vB + ND * NN;
-    double2* const vG = Phi + NN;      // Gamma = W0 Mt^H, row-major
-    double2* const T3 = vG + NN;       // Lt_j = h B_j o Phi
-    double2* const f3 = T3 + NN;
+    double2* const Phi = vB + ND * NL;
+    double2* const vG = Phi + NL;      // Gamma = W0 Mt^H, row-major
+    double2* const T3 = vG + NL;       // Lt_j = h B_j o Phi
+    double2* const f3 = T3 + NL;
     double2* const ex = f3 + ge_tet(N);
     double2* const hx = ex + N;
     double* const lam = reinterpret_cast<double*>(hx + N);
@@ -102,8 +103,8 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 v.y = fma(aj, d.y, v.y);
             }
             const int r = e % N, col = e / N;  // A0 is column-major
-            S[r * N + col] = make_double2(-v.y, r == col ? 0.0 : v.x);
-            mV[e] = make_double2(r == col ? 1.0 : 0.0, 0.0);
+            S[r * LD + col] = make_double2(-v.y, r == col ? 0.0 : v.x);
+            mV[r * LD + col] = make_double2(r == col ? 1.0 : 0.0, 0.0);
             fro2 = fma(v.x, v.x, fma(v.y, v.y, fro2));
         }
         fro2 = warp_sum(fro2);
@@ -114,8 +115,9 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
             for (int sweep = 0; sweep < 14; ++sweep) {
                 double off2 = 0.0;
                 for (int e = lane; e < NN; e += 32) {
-                    const double2 v = S[e];
-                    if (e % (N + 1)) off2 = fma(v.x, v.x, fma(v.y, v.y, off2));
+                    const int r = e / N, k = e - r * N;
+                    const double2 v = S[r * LD + k];
+                    if (r != k) off2 = fma(v.x, v.x, fma(v.y, v.y, off2));
                 }
                 off2 = warp_sum(off2);
                 if (off2 <= 1e-30 * fro2) break;
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                     if (lane < P) {  // rotation of pair `lane` from the pivots: J = [[c, conj(sg)], [-sg, c]], inner rotation
                         int pp, qq;
                         pair_of(lane, pp, qq);
-                        const double al = S[pp * (N + 1)].x, ga = S[qq * (N + 1)].x;
-                        const double2 be = S[pp * N + qq];
+                        const double al = S[pp * LD + pp].x, ga = S[qq * LD + qq].x;
+                        const double2 be = S[pp * LD + qq];
                         const double b2 = be.x * be.x + be.y * be.y;
                         double cr = 1.0;
                         double2 sg = make_double2(0.0, 0.0);
@@ -152,9 +154,9 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                         pair_of(l, pp, qq);
                         const double cr = rot[2 * l].x;
                         const double2 sg = rot[2 * l + 1];
-                        const double2 a = S[rho * N + pp], b = S[rho * N + qq];
-                        S[rho * N + pp] = make_double2(cr * a.x - (sg.x * b.x - sg.y * b.y), cr * a.y - (sg.x * b.y + sg.y * b.x));
-                        S[rho * N + qq] = make_double2(cr * b.x + (sg.x * a.x + sg.y * a.y), cr * b.y + (sg.x * a.y - sg.y * a.x));
+                        const double2 a = S[rho * LD + pp], b = S[rho * LD + qq];
+                        S[rho * LD + pp] = make_double2(cr * a.x - (sg.x * b.x - sg.y * b.y), cr * a.y - (sg.x * b.y + sg.y * b.x));
+                        S[rho * LD + qq] = make_double2(cr * b.x + (sg.x * a.x + sg.y * a.y), cr * b.y + (sg.x * a.y - sg.y * a.x));
                     }
                     __syncwarp();
                     for (int task = lane; task < N * P; task += 32) {  // pass L: H <- J^H H; the pivots take their exact values
@@ -163,13 +165,13 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                         pair_of(l, pp, qq);
                         const double cr = rot[2 * l].x;
                         const double2 sg = rot[2 * l + 1];
-                        const double2 a = S[pp * N + gam], b = S[qq * N + gam];
+                        const double2 a = S[pp * LD + gam], b = S[qq * LD + gam];
                         double2 za = make_double2(cr * a.x - (sg.x * b.x + sg.y * b.y), cr * a.y - (sg.x * b.y - sg.y * b.x));
                         double2 zb = make_double2(cr * b.x + (sg.x * a.x - sg.y * a.y), cr * b.y + (sg.x * a.y + sg.y * a.x));
                         if (gam == pp) { za.y = 0.0; zb = make_double2(0.0, 0.0); }
                         if (gam == qq) { zb.y = 0.0; za = make_double2(0.0, 0.0); }
-                        S[pp * N + gam] = za;
-                        S[qq * N + gam] = zb;
+                        S[pp * LD + gam] = za;
+                        S[qq * LD + gam] = zb;
                     }
                     __syncwarp();
                 }
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
         }
         // ---- spectrum ------------------------------------------------------------------------------------------------------------------
         if (lane < N) {
-            const double l = S[lane * (N + 1)].x;
+            const double l = S[lane * LD + lane].x;
             lam[lane] = l;
             double sn, cs;
             sincos(0.5 * h * l, &sn, &cs);
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
             const int k = e % N, col = e / N;
             double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
             for (int r = 0; r < N; ++r) {
-                const double2 v = mV[r * N + k];
+                const double2 v = mV[r * LD + k];
                 const double2 vc = make_double2(v.x, -v.y);
                 cfma(a0, vc, vU0[col * N + r]);
                 if (needH) cfma(a1, vc, vM[col * N + r]);
@@ -207,19 +209,19 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                     double2 acc = make_double2(0.0, 0.0);
                     for (int w = 0; w < W; ++w) {
                         const double2 v = __ldg(ellv + o + w);
-                        if (v.x != 0.0 || v.y != 0.0) cfma(acc, v, mV[__ldg(ellc + o + w) * N + k]);
+                        if (v.x != 0.0 || v.y != 0.0) cfma(acc, v, mV[__ldg(ellc + o + w) * LD + k]);
                     }
-                    T1[e] = acc;
+                    T1[r * LD + k] = acc;
                 }
                 __syncwarp();
                 for (int e = lane; e < NN; e += 32) {
                     const int pp = e / N, q = e - pp * N;
                     double2 acc = make_double2(0.0, 0.0);
                     for (int r = 0; r < N; ++r) {
-                        const double2 v = mV[r * N + pp];
-                        cfma(acc, make_double2(v.x, -v.y), T1[r * N + q]);
+                        const double2 v = mV[r * LD + pp];
+                        cfma(acc, make_double2(v.x, -v.y), T1[r * LD + q]);
                     }
-                    vB[j * NN + e] = acc;
+                    vB[j * NL + pp * LD + q] = acc;
                 }
                 __syncwarp();
             }
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 const double dl = 0.5 * h * (lam[pp] - lam[q]);
                 const double sc = dl == 0.0 ? 1.0 : sin(dl) / dl;
                 const double2 g = cmul(hx[pp], hx[q]);
-                Phi[e] = make_double2(sc * g.x, sc * g.y);
+                Phi[pp * LD + q] = make_double2(sc * g.x, sc * g.y);
             }
             __syncwarp();
         }
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
             double2 yE = make_double2(0.0, 0.0), yT = make_double2(0.0, 0.0);
             for (int k = 0; k < N; ++k) {
                 const double2 w = cmul(ex[k], vW0[col * N + k]);
-                const double2 v = mV[r * N + k];
+                const double2 v = mV[r * LD + k];
                 cfma(yE, v, w);
                 cfma(yT, v, make_double2(lam[k] * w.y, -lam[k] * w.x));  // (-i l) e^x w0
             }
@@ -254,10 +256,10 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 const int r = e / N, cI = e - r * N;
                 double2 acc = make_double2(0.0, 0.0);
                 for (int k = 0; k < N; ++k) {
-                    const double2 v = mV[cI * N + k];
-                    cfma(acc, mV[r * N + k], cmul(ex[k], make_double2(v.x, -v.y)));
+                    const double2 v = mV[cI * LD + k];
+                    cfma(acc, mV[r * LD + k], cmul(ex[k], make_double2(v.x, -v.y)));
                 }
-                T1[e] = acc;  // E[r][cI]
+                T1[r * LD + cI] = acc;  // E[r][cI]
             }
             __syncwarp();
             const int dF = qd[QO_ISOF];
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 for (int e = lane; e < blk; e += 32) {
                     const int col2 = e / n2, row2 = e - col2 * n2;
                     const int r = row2 < N ? row2 : row2 - N, cI = col2 < N ? col2 : col2 - N;
-                    const double2 ev = T1[r * N + cI];
+                    const double2 ev = T1[r * LD + cI];
                     const double val = (row2 < N) == (col2 < N) ? -ev.x : (row2 >= N ? -ev.y : ev.y);
                     for (int cb = 0; cb < nc; ++cb) oJ[dF + cb * blk + e] = val;
                 }
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                     const double2 mv = vMt[col * N + pp];
                     cfma(acc, vW0[col * N + r], make_double2(mv.x, -mv.y));
                 }
-                vG[e] = acc;
+                vG[r * LD + pp] = acc;
             }
             for (int idx = lane; idx < ge_tet(N); idx += 32) {  // second-order divided differences of the sorted triples
                 int hi = 0;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 else { u = mid; w = hi; v = lo; gap = t1 - t2; }
                 double2 f;
                 if (fabs(gap) >= 0.4) {
-                    const double2 a = Phi[u * N + v], b = Phi[v * N + w];
+                    const double2 a = Phi[u * LD + v], b = Phi[v * LD + w];
                     const double inv = 1.0 / gap;
                     f = make_double2(-(a.y - b.y) * inv, (a.x - b.x) * inv);
                 } else {
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 for (int e = lane; e < NS; e += 32) {  // state x dt = -V (conj(-i l e^x) . Mt)
                     const int r = e % N, col = e / N;
                     double2 y = make_double2(0.0, 0.0);
-                    for (int k = 0; k < N; ++k) cfma(y, mV[r * N + k], cmul(make_double2(lam[k] * ex[k].y, lam[k] * ex[k].x), vMt[col * N + k]));
+                    for (int k = 0; k < N; ++k) cfma(y, mV[r * LD + k], cmul(make_double2(lam[k] * ex[k].y, lam[k] * ex[k].x), vMt[col * N + k]));
                     putH(QO_KH0, r, col, make_double2(-y.x, -y.y));
                 }
             __syncwarp();
@@ -335,18 +337,19 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
         // ---- drive terms -----------------------------------------------------------------------------------------------------------------
         if (needJ || needH) {
             for (int j = 0; j < ND; ++j) {
-                const double2* Bj = vB + j * NN;
+                const double2* Bj = vB + j * NL;
                 double s_ah = 0.0;
                 for (int e = lane; e < NN; e += 32) {  // Lt_j = h B_j o Phi; a_j x dt takes (B_j,pq e^{x_q} - i l_p Lt_pq) Gamma_qp from here
                     const int pp = e / N, q = e - pp * N;
-                    const double2 b = Bj[e];
-                    const double2 l0 = cmul(b, Phi[e]);
+                    const int ei = pp * LD + q;
+                    const double2 b = Bj[ei];
+                    const double2 l0 = cmul(b, Phi[ei]);
                     const double2 l = make_double2(h * l0.x, h * l0.y);
-                    T3[e] = l;
+                    T3[ei] = l;
                     if (needH && free_time) {
                         const double2 be = cmul(b, ex[q]);
                         const double2 tot = make_double2(be.x + lam[pp] * l.y, be.y - lam[pp] * l.x);
-                        const double2 g = vG[q * N + pp];
+                        const double2 g = vG[q * LD + pp];
                         s_ah -= tot.x * g.x - tot.y * g.y;
                     }
                 }
@@ -355,14 +358,14 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                     for (int e = lane; e < NS; e += 32) {
                         const int pp = e % N, col = e / N;
                         double2 acc = make_double2(0.0, 0.0);
-                        for (int q = 0; q < N; ++q) cfma(acc, T3[pp * N + q], vW0[col * N + q]);
+                        for (int q = 0; q < N; ++q) cfma(acc, T3[pp * LD + q], vW0[col * N + q]);
                         T2[e] = acc;
                     }
                     __syncwarp();
                     for (int e = lane; e < NS; e += 32) {
                         const int r = e % N, col = e / N;
                         double2 y = make_double2(0.0, 0.0);
-                        for (int k = 0; k < N; ++k) cfma(y, mV[r * N + k], T2[col * N + k]);
+                        for (int k = 0; k < N; ++k) cfma(y, mV[r * LD + k], T2[col * N + k]);
                         putJ(QO_TA + j, r, col, make_double2(-y.x, -y.y));
                     }
                     __syncwarp();
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                         const int q = e % N, col = e / N;
                         double2 acc = make_double2(0.0, 0.0);
                         for (int pp = 0; pp < N; ++pp) {
-                            const double2 l = T3[pp * N + q];
+                            const double2 l = T3[pp * LD + q];
                             cfma(acc, make_double2(l.x, -l.y), vMt[col * N + pp]);
                         }
                         T2[e] = acc;
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                     for (int e = lane; e < NS; e += 32) {
                         const int r = e % N, col = e / N;
                         double2 y = make_double2(0.0, 0.0);
-                        for (int k = 0; k < N; ++k) cfma(y, mV[r * N + k], T2[col * N + k]);
+                        for (int k = 0; k < N; ++k) cfma(y, mV[r * LD + k], T2[col * N + k]);
                         putH(QO_KA0 + j, r, col, make_double2(-y.x, -y.y));
                     }
                     if (free_time) put_scalar(QO_HAH + j, warp_sum(s_ah));
@@ -403,13 +406,13 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 for (int i = 0; i < ND; ++i) K[i] = make_double2(0.0, 0.0);
                 for (int pp = 0; pp < N; ++pp) {
                     const int lo = min(pp, min(q, r)), hi = max(pp, max(q, r)), mid = pp + q + r - lo - hi;
-                    const double2 gf = cmul(vG[r * N + pp], f3[hi * (hi + 1) * (hi + 2) / 6 + mid * (mid + 1) / 2 + lo]);
+                    const double2 gf = cmul(vG[r * LD + pp], f3[hi * (hi + 1) * (hi + 2) / 6 + mid * (mid + 1) / 2 + lo]);
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) cfma(K[i], gf, vB[i * NN + pp * N + q]);
+                    for (int i = 0; i < ND; ++i) cfma(K[i], gf, vB[i * NL + pp * LD + q]);
                 }
 #pragma unroll
                 for (int j = 0; j < ND; ++j) {
-                    const double2 bj = vB[j * NN + e];
+                    const double2 bj = vB[j * NL + q * LD + r];
 #pragma unroll
                     for (int i = 0; i < ND; ++i) s_aa[i][j] += bj.x * K[i].x - bj.y * K[i].y;
                 }
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(256) qck_genexp_kernel(const QckLaunch p, int 
                 double v = 0.0;
                 if (lane < N) {
                     const double l = lam[lane];
-                    const double2 e = ex[lane], g = vG[lane * (N + 1)];
+                    const double2 e = ex[lane], g = vG[lane * LD + lane];
                     v = l * l * (e.x * g.x - e.y * g.y);
                 }
                 put_scalar(QO_HHH, warp_sum(v));
