@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(256, 1) qck_expeig9_kernel(const QckLaunch p) 
     const QckClassDev& c = p.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)(blockDim.x >> 5);
     const bool act = lane < 3 * N;
-    const int cc = act ? lane / 3 : 0, k3 = act ? 3 * (lane - 3 * (lane / 3)) : 0;  // column, first row of this lane
+    // (idle lanes 27..31 shadow lane 24: their reads then broadcast with column 8 instead of adding a bank conflict against column 0)
+    const int cc = act ? lane / 3 : N - 1, k3 = act ? 3 * (lane - 3 * (lane / 3)) : 0;  // column, first row of this lane
     const bool needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
     const bool needT = needJ || needH;
     const bool free_time = c.free_time;
