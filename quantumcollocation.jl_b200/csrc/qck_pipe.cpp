@@ -384,6 +384,66 @@ int qck_pipe_eval(qck_handle* h, const double* Z, const double* mu, double* F, d
     unsigned need = (outs[0] ? QCK_EVAL_F : 0) | (outs[1] ? QCK_EVAL_J : 0) | (outs[2] ? QCK_EVAL_H : 0);
     P.h2d_bytes = P.d2h_bytes = 0;
     if (!need) return QCK_OK;
+    {   // SMALL PROBLEMS (README scale: Hadamard, T = 50): the whole call is one piece of less than 1 MB -- one stream, no host threads,
+        // no events; what is left is the launch and PCIe latency itself
+        static const bool no_small = getenv("QCK_NO_SMALL_PATH") != nullptr;
+        const long long out_doubles = nk * (nnz[0] + nnz[1] + nnz[2]);
+        if (!no_small && !P.dShared && nk <= P.piece_knots && out_doubles <= (128ll << 10)) {
+            static const bool no_cache = getenv("QCK_NO_CACHE") != nullptr;
+            static const bool speculate = getenv("QCK_NO_SPECULATE") == nullptr;
+            const size_t zb = sizeof(double) * (size_t)h->T * h->zdim, mb = sizeof(double) * (size_t)nk * h->dyn;
+            const bool z_same = !no_cache && P.z_staged && P.z_on_device && memcmp(P.pinZ, Z, zb) == 0;
+            if (!z_same) { P.z_on_device = false; P.valid_mask = 0; }
+            bool mu_same = true;
+            if (need & QCK_EVAL_H) {
+                mu_same = !no_cache && P.mu_on_device && memcmp(P.pinMu, mu, mb) == 0;
+                if (!mu_same) { P.mu_on_device = false; P.valid_mask &= ~QCK_EVAL_H; }
+            }
+            unsigned compute = need & ~P.valid_mask;
+            if (speculate && (compute & QCK_EVAL_F) && !(P.valid_mask & QCK_EVAL_J) && !(need & QCK_EVAL_H)) compute |= QCK_EVAL_J;
+            if (!compute) ++P.cache_hits;
+            cudaStream_t st = P.st[0];
+            P.z_staged = false;
+            if (!z_same) {
+                memcpy(P.pinZ, Z, zb);
+                QCK_CUDA_TRY(h, cudaMemcpyAsync(h->dZ, P.pinZ, zb, cudaMemcpyHostToDevice, st));
+                P.h2d_bytes += (long long)zb;
+            }
+            if ((need & QCK_EVAL_H) && !mu_same) {
+                memcpy(P.pinMu, mu, mb);
+                QCK_CUDA_TRY(h, cudaMemcpyAsync(h->dmu, P.pinMu, mb, cudaMemcpyHostToDevice, st));
+                P.h2d_bytes += (long long)mb;
+            }
+            int launches = 0, stride = 0, coff[3] = {0, 0, 0};
+            for (int a = 0; a < 3; ++a)
+                if (outs[a]) { coff[a] = stride; stride += P.cC[a]; }
+            int err = compute ? qck_run(h, compute, 0, nk, h->dZ, h->dmu, h->dF, h->dJ, h->dH, st, 1) : QCK_OK;
+            for (int a = 0; a < 3 && err == QCK_OK; ++a) {
+                if (!outs[a] || P.cC[a] == 0) continue;
+                const int e = qck_launch_pack(dfull[a], P.dC + coff[a], P.d_src[a], P.cC[a], stride, nnz[a], nk, st, &launches);
+                if (e) err = qck_fail(h, QCK_ECUDA, "pack kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+            }
+            if (err == QCK_OK && stride > 0) {
+                cudaError_t ce = cudaMemcpyAsync(P.pinC, P.dC, sizeof(double) * (size_t)nk * stride, cudaMemcpyDeviceToHost, st);
+                if (ce != cudaSuccess) err = qck_fail(h, QCK_ECUDA, "D2H copy: %s", cudaGetErrorString(ce));
+                P.d2h_bytes += (long long)sizeof(double) * nk * stride;
+            }
+            const cudaError_t cs = cudaStreamSynchronize(st);
+            if (err == QCK_OK && cs != cudaSuccess) err = qck_fail(h, QCK_ECUDA, "stream: %s", cudaGetErrorString(cs));
+            h->launches += launches;
+            if (err != QCK_OK) {
+                P.valid_mask = 0; P.z_on_device = false; P.mu_on_device = false;
+                return err;
+            }
+            for (int a = 0; a < 3; ++a)
+                if (outs[a] && P.cC[a] > 0) expand_knots(h->own[a], P.pinC + coff[a], stride, outs[a], nnz[a], 0, nk);
+            P.z_staged = true;
+            P.z_on_device = true;
+            if ((need & QCK_EVAL_H) && !mu_same) P.mu_on_device = true;
+            P.valid_mask |= compute;
+            return h->uses_status ? qck_check_status(h) : QCK_OK;
+        }
+    }
 
     // ---- 1. what is already on the device?  ("the same Z is presented to F, dF, mu d2F in succession") -----------
     static const bool no_cache = getenv("QCK_NO_CACHE") != nullptr;

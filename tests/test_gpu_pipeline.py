@@ -107,9 +107,11 @@ def test_page_locked_outputs_take_the_direct_path(name, kw, chunk, monkeypatch):
     D.close()
 
 
-def test_unchanged_z_is_uploaded_and_evaluated_once():
-    """'the same Z is presented to F, dF, mu d2F in succession'."""
-    systems, traj, integrators = wl.config("cz", T=200)
+@pytest.mark.parametrize("name,T", [("cz", 200), ("hadamard", 60)])
+def test_unchanged_z_is_uploaded_and_evaluated_once(name, T):
+    """'the same Z is presented to F, dF, mu d2F in succession'.  (Hadamard, T = 60: the single-piece path of small
+    problems, same cache rules.)"""
+    systems, traj, integrators = wl.config(name, T=T)
     D = qcknot.QuantumDynamics(integrators, traj)
     Z = traj.datavec.copy()
     mu = wl.random_multipliers(D.n_blocks * D.dyn)
