@@ -18,7 +18,9 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int ce_tet(int n) { return n * (n + 1) * (n + 2) / 6; }
 __host__ __device__ constexpr int ce_rec(int n) { return n * n + (n + 1) / 2; }          // double2 per item in the scratch: V | eigenvalues
-__host__ __device__ constexpr int ce_item(int n, int nd) { return nd * n * n + n * n + ce_tet(n); }  // double2 per item in shared memory
+// double2 per item in shared memory; odd, so that the items of a warp start on different banks (256 B per item put all 16 two-level
+// items of a warp on the same banks: 81 % of the shared-memory wavefronts were conflicts)
+__host__ __device__ constexpr int ce_item(int n, int nd) { return (nd * n * n + n * n + ce_tet(n)) | 1; }
 
 __device__ __forceinline__ void ce_rot(double al, double ga, double2 be, double& c, double2& sg) {
     const double b2 = be.x * be.x + be.y * be.y;
