@@ -215,9 +215,11 @@ __attribute__((target("avx512f"))) void stream_copy_avx512(double* dst, const do
     for (; i + 8 <= n; i += 8) _mm512_stream_pd(dst + i, _mm512_loadu_pd(src + i));
     for (; i < n; ++i) _mm_stream_si64(reinterpret_cast<long long*>(dst + i), reinterpret_cast<const long long*>(src)[i]);
 }
+void stream_copy_plain(double* dst, const double* src, size_t n) { memcpy(dst, src, n * sizeof(double)); }  // cacheable stores (A/B knob)
 typedef void (*stream_copy_fn)(double*, const double*, size_t);
 stream_copy_fn pick_stream_copy() {
-    const char* e = getenv("QCK_STREAM_ISA");  // "sse2" | "avx2" | "avx512" (development knob)
+    const char* e = getenv("QCK_STREAM_ISA");  // "sse2" | "avx2" | "avx512" | "plain" (development knob)
+    if (e && !strcmp(e, "plain")) return stream_copy_plain;
     __builtin_cpu_init();
     const bool a512 = __builtin_cpu_supports("avx512f"), a2 = __builtin_cpu_supports("avx2");
     if (e && !strcmp(e, "sse2")) return stream_copy_sse2;
