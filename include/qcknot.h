@@ -63,6 +63,18 @@ extern "C" {
 #define QCK_SHARD_KNOT 0
 #define QCK_SHARD_ENSEMBLE 1
 
+/* intra-knot order of the structure entries (and of the value arrays).  The reference's Core is not part of the repository, so
+ * its order cannot be read off; the candidates are policies of qck_create:
+ *   QCK_ORDER_CSC             union pattern of all integrators, column-major (default; the order every kernel writes in)
+ *   QCK_ORDER_ROW_MAJOR       union pattern, row-major
+ *   QCK_ORDER_PER_INTEGRATOR  the integrators' own entry lists one after the other (column-major inside an integrator); a
+ *                             Hessian position that several integrators touch appears once per integrator, each entry holding
+ *                             that integrator's contribution -- the consumer sums duplicates (test/test_utils.jl:14-27)
+ * Orders other than CSC are served by one extra gather pass on the device (single-GPU handles). */
+#define QCK_ORDER_CSC 0
+#define QCK_ORDER_ROW_MAJOR 1
+#define QCK_ORDER_PER_INTEGRATOR 2
+
 /* error codes */
 #define QCK_OK 0
 #define QCK_EINVAL 1    /* bad argument / unsupported configuration */
@@ -105,6 +117,8 @@ typedef struct qck_problem_desc {
     int32_t shard_mode;   /* QCK_SHARD_KNOT | QCK_SHARD_ENSEMBLE (n_gpus > 1) */
     int32_t host_threads; /* host threads for staging / expansion of the value arrays; 0 = all hardware threads (max 32) */
     const int32_t* devices; /* optional: explicit device ordinals, n_gpus entries (NULL = consecutive from `device`) */
+    int32_t structure_order; /* QCK_ORDER_CSC (0, default) | QCK_ORDER_ROW_MAJOR | QCK_ORDER_PER_INTEGRATOR */
+    int32_t reserved;
 } qck_problem_desc;
 
 typedef struct qck_handle qck_handle;

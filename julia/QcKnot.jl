@@ -35,7 +35,9 @@ struct ProblemDesc             # qck_problem_desc
     integrators::Ptr{IntegratorDesc}
     shard_mode::Int32; host_threads::Int32
     devices::Ptr{Int32}
+    structure_order::Int32; reserved::Int32   # QCK_ORDER_CSC = 0 | QCK_ORDER_ROW_MAJOR = 1 | QCK_ORDER_PER_INTEGRATOR = 2
 end
+const STRUCTURE_ORDERS = Dict(:csc => Int32(0), :row_major => Int32(1), :per_integrator => Int32(2))
 
 # entry points, resolved once per process
 struct Lib
@@ -101,12 +103,15 @@ end
 #   QcKnot.describe(I::QuantumStateExponentialIntegrator, traj) = QcKnot.describe_ket_exponential(I, traj)
 
 """
-    B200Dynamics(integrators, traj; eval_hessian=true, device=0, n_gpus=1, shard_mode=:knot)
+    B200Dynamics(integrators, traj; eval_hessian=true, device=0, n_gpus=1, shard_mode=:knot, structure_order=:csc)
 
 Same call shape as `QuantumDynamics(integrators, traj)`; evaluates on `n_gpus` B200s through libqcknot.so
 (`shard_mode = :knot` splits the knot range, `:ensemble` the sampled systems of a UnitarySamplingProblem).
+`structure_order` picks the intra-knot order of `∂F_structure` / `μ∂²F_structure` and of the value vectors (`:csc`, `:row_major`
+or `:per_integrator`): set it to whatever `QuantumDynamics(integrators, traj).∂F_structure` of the installed Core shows.
 """
-function B200Dynamics(integrators, traj; eval_hessian::Bool=true, device::Integer=0, n_gpus::Integer=1, shard_mode::Symbol=:knot)
+function B200Dynamics(integrators, traj; eval_hessian::Bool=true, device::Integer=0, n_gpus::Integer=1, shard_mode::Symbol=:knot,
+                      structure_order::Symbol=:csc)
     L = lib()
     keep = Any[]
     descs = map(integrators) do I
@@ -121,7 +126,8 @@ function B200Dynamics(integrators, traj; eval_hessian::Bool=true, device::Intege
     dt_off = free_time ? Int32(first(traj.components[traj.timestep]) - 1) : Int32(-1)
     pd = ProblemDesc(traj.T, traj.dim, dt_off, free_time ? 0.0 : Float64(traj.timestep), length(descs),
                      eval_hessian, device, 0, -1, n_gpus, pointer(descs),
-                     shard_mode === :ensemble ? QCK_SHARD_ENSEMBLE : QCK_SHARD_KNOT, 0, C_NULL)
+                     shard_mode === :ensemble ? QCK_SHARD_ENSEMBLE : QCK_SHARD_KNOT, 0, C_NULL,
+                     STRUCTURE_ORDERS[structure_order], 0)
     href = Ref{Ptr{Cvoid}}(C_NULL)
     rc = GC.@preserve keep descs ccall(L.create, Cint, (Ref{ProblemDesc}, Ref{Ptr{Cvoid}}), pd, href)
     rc == 0 || error("qck_create ($rc): " * last_error(C_NULL))

@@ -16,7 +16,7 @@ _CLS = {
 }
 
 
-def oracle_dynamics(integrators, traj, eval_hessian: bool = True) -> ko.QuantumDynamics:
+def oracle_dynamics(integrators, traj, eval_hessian: bool = True, structure_order: str = "csc") -> ko.QuantumDynamics:
     comps = {n: (r.start, len(r)) for n, r in traj.components.items()}
     layout = ko.Layout(comps, traj.T, traj.timestep if traj.free_time else None,
                        0.0 if traj.free_time else traj.timestep, traj.global_dim)
@@ -29,7 +29,7 @@ def oracle_dynamics(integrators, traj, eval_hessian: bool = True) -> ko.QuantumD
             sys_ = ko.QuantumSystem(I.system.H_drift, I.system.H_drives)
             kw = {"order": I.order} if getattr(I, "order", 0) else {}
             out.append(_CLS[name](I.state_name, I.control_name, sys_, layout, **kw))
-    return ko.QuantumDynamics(out, layout, eval_hessian=eval_hessian)
+    return ko.QuantumDynamics(out, layout, eval_hessian=eval_hessian, structure_order=structure_order)
 
 
 def rel_err(a, b) -> float:

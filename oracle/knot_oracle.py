@@ -509,7 +509,13 @@ class QuantumDynamics:
     Structures are lists of 1-based (row, col) tuples like the reference's Vector{Tuple{Int,Int}}.
     """
 
-    def __init__(self, integrators: Sequence, layout: Layout, eval_hessian: bool = True):
+    def __init__(self, integrators: Sequence, layout: Layout, eval_hessian: bool = True, structure_order: str = "csc"):
+        """structure_order: intra-knot order of the entries -- the Core's order is [DEP-RECALL], so every candidate is a policy:
+        "csc" (union pattern, column-major), "row_major" (union pattern, row-major) or "per_integrator" (the integrators'
+        own entry lists one after the other, column-major inside each; a Hessian position two integrators touch appears twice
+        and the consumer sums the duplicates, test/test_utils.jl:14-27)."""
+        assert structure_order in ("csc", "row_major", "per_integrator")
+        self.structure_order = structure_order
         self.integrators = list(integrators)
         self.layout = layout
         self.zdim = layout.zdim
@@ -517,23 +523,43 @@ class QuantumDynamics:
         self.row_off = np.cumsum([0] + [I.dim for I in self.integrators])
         self.dyn = int(self.row_off[-1])
         zdim = self.zdim
-        # per-knot patterns (union over integrators) in CSC order
-        JP = np.zeros((self.dyn, 2 * zdim), dtype=bool)
-        for I, r0 in zip(self.integrators, self.row_off):
-            JP[r0 : r0 + I.dim] |= I.jac_pattern()
-        cols, rows = np.nonzero(JP.T)  # column-major walk
-        self.jac_knot = list(zip(rows.tolist(), cols.tolist()))
-        self.nnzJ = len(self.jac_knot)
+
+        def walk(P):  # entries of a boolean pattern in this policy's order (per_integrator: column-major inside the integrator)
+            if structure_order == "row_major":
+                rows, cols = np.nonzero(P)
+            else:
+                cols, rows = np.nonzero(P.T)
+            return list(zip(rows.tolist(), cols.tolist()))
+
         self.eval_hessian = eval_hessian
-        if eval_hessian:
-            HP = np.zeros((2 * zdim, 2 * zdim), dtype=bool)
-            for I in self.integrators:
-                I.hess_pattern(out=HP)  # unfolded marks
-            HP = _to_upper_pattern(HP)
-            cols, rows = np.nonzero(HP.T)
-            self.hess_knot = list(zip(rows.tolist(), cols.tolist()))
+        self.hess_owner = None  # per_integrator: which integrator's contribution an entry holds
+        if structure_order == "per_integrator":
+            self.jac_knot = []
+            for I, r0 in zip(self.integrators, self.row_off):
+                JP = np.zeros((self.dyn, 2 * zdim), dtype=bool)
+                JP[r0 : r0 + I.dim] = I.jac_pattern()
+                self.jac_knot += walk(JP)
+            self.hess_knot, self.hess_owner = [], []
+            if eval_hessian:
+                for q, I in enumerate(self.integrators):
+                    HP = np.zeros((2 * zdim, 2 * zdim), dtype=bool)
+                    I.hess_pattern(out=HP)
+                    e = walk(_to_upper_pattern(HP))
+                    self.hess_knot += e
+                    self.hess_owner += [q] * len(e)
         else:
-            self.hess_knot = []
+            JP = np.zeros((self.dyn, 2 * zdim), dtype=bool)
+            for I, r0 in zip(self.integrators, self.row_off):
+                JP[r0 : r0 + I.dim] |= I.jac_pattern()
+            self.jac_knot = walk(JP)
+            if eval_hessian:
+                HP = np.zeros((2 * zdim, 2 * zdim), dtype=bool)
+                for I in self.integrators:
+                    I.hess_pattern(out=HP)  # unfolded marks
+                self.hess_knot = walk(_to_upper_pattern(HP))
+            else:
+                self.hess_knot = []
+        self.nnzJ = len(self.jac_knot)
         self.nnzH = len(self.hess_knot)
         self.dF_structure = [
             (r + t * self.dyn + 1, c + t * zdim + 1) for t in range(self.T - 1) for (r, c) in self.jac_knot
@@ -575,8 +601,17 @@ class QuantumDynamics:
         rr = np.array([r for r, _ in self.hess_knot])
         cc = np.array([c for _, c in self.hess_knot])
         H = np.zeros((2 * self.zdim, 2 * self.zdim))
+        owner = None if self.hess_owner is None else np.array(self.hess_owner)
         for t, zt, zt1 in self._knots(Z):
             mut = mu[t * self.dyn : (t + 1) * self.dyn]
+            if owner is not None:  # per_integrator: every integrator's own contribution, never summed
+                blk = out[t * self.nnzH : (t + 1) * self.nnzH]
+                for q, (I, r0) in enumerate(zip(self.integrators, self.row_off)):
+                    sel = owner == q
+                    I.hessian(zt, zt1, mut[r0 : r0 + I.dim], out=H)
+                    blk[sel] = H[rr[sel], cc[sel]]
+                    H[rr[sel], cc[sel]] = 0.0
+                continue
             for I, r0 in zip(self.integrators, self.row_off):
                 I.hessian(zt, zt1, mut[r0 : r0 + I.dim], out=H)  # integrators add in order, like the dense sum did
             out[t * self.nnzH : (t + 1) * self.nnzH] = H[rr, cc]

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("QCK_LIB") or os.path.join(HERE, "libqcknot.so")  # QC
 QCK_UNITARY_PADE, QCK_UNITARY_EXP, QCK_KET_PADE, QCK_KET_EXP, QCK_DERIVATIVE = range(5)
 QCK_EVAL_F, QCK_EVAL_J, QCK_EVAL_H = 1, 2, 4
 QCK_SHARD_KNOT, QCK_SHARD_ENSEMBLE = 0, 1
+QCK_ORDER_CSC, QCK_ORDER_ROW_MAJOR, QCK_ORDER_PER_INTEGRATOR = 0, 1, 2
 QCK_OBJ_QUADRATIC_REGULARIZER, QCK_OBJ_UNITARY_INFIDELITY, QCK_OBJ_MINIMUM_TIME = 0, 1, 2
 
 EXPORTS = [
@@ -41,6 +42,7 @@ class ProblemDesc(C.Structure):
         ("integ_begin", C.c_int32), ("integ_end", C.c_int32), ("n_gpus", C.c_int32),
         ("integrators", C.POINTER(IntegratorDesc)),
         ("shard_mode", C.c_int32), ("host_threads", C.c_int32), ("devices", C.POINTER(C.c_int32)),
+        ("structure_order", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -120,8 +120,21 @@ struct QckPipe {
     long long h2d_bytes = 0, d2h_bytes = 0, cache_hits = 0;  // statistics of the last host-buffer call
 };
 
+// Structure-order policy other than CSC (qck_problem_desc.structure_order): the caller-visible structure and the gather tables
+// from the canonical (CSC) value arrays the kernels write.
+struct QckPublicOrder {
+    int order = 0;                         // QCK_ORDER_*
+    long long nnzJ = 0, nnzH = 0;          // caller-visible values per knot block
+    std::vector<int32_t> Jr, Jc, Hr, Hc;   // caller-visible per-knot structure, 0-based
+    std::vector<int> srcJ, srcH;           // caller-visible position -> canonical position (H: >= canonical nnzH = partial column)
+    std::vector<long long> shared;         // caller-visible positions with several contributors (empty for PER_INTEGRATOR)
+    const int *d_srcJ = nullptr, *d_srcH = nullptr;
+    double *dJ = nullptr, *dH = nullptr;   // caller-order device arrays of the host-buffer path
+};
+
 struct qck_handle {
     std::string err;
+    QckPublicOrder pub;
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     long long T = 0;
@@ -169,6 +182,7 @@ int qck_run(qck_handle* h, uint32_t mask, long long k0, long long nk, const doub
             double* dH, cudaStream_t st, int slot);  // pointers are array bases; blocks [k0, k0 + nk) are evaluated;
                                                       // slot < QCK_TAPE_SLOTS: scratch set of the stream (launches on different slots may overlap)
 #define QCK_TAPE_SLOTS 3
+int qck_reorder(qck_handle* h, uint32_t mask, double* dJ_out, double* dH_out, cudaStream_t st);  // canonical h->dJ / h->dH (+ partial columns) -> caller order
 int qck_check_status(qck_handle* h);  // after a synchronisation: turns device-side error bits into QCK_ERANGE
 int qck_create_single(const qck_problem_desc* d, qck_handle** out, bool exclude_shared);
 // qck_pipe.cpp

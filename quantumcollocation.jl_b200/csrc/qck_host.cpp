@@ -395,6 +395,43 @@ int build(qck_handle* h) {
         for (auto& v : cols) { for (int cidx : v) h->sh_cols.push_back(cidx); h->sh_ptr.push_back((int)h->sh_cols.size()); }
     }
 
+    // ---- structure-order policy (qck_problem_desc.structure_order): caller-visible order + gather tables from the CSC arrays ---------
+    if (h->pub.order != QCK_ORDER_CSC) {
+        QckPublicOrder& P = h->pub;
+        if (h->ib != 0 || h->ie != nI || h->exclude_shared)
+            return fail(h, QCK_EINVAL, "structure_order other than CSC needs an unsharded handle (all integrators, one GPU)");
+        const long long zz = 2LL * zdim;
+        std::vector<size_t> ord(JE.size());
+        for (size_t k = 0; k < ord.size(); ++k) ord[k] = k;
+        auto jrow = [&](size_t k) { return JE[k].key % h->dyn; };
+        auto jcol = [&](size_t k) { return JE[k].key / h->dyn; };
+        if (P.order == QCK_ORDER_ROW_MAJOR)
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return jrow(a) != jrow(b) ? jrow(a) < jrow(b) : jcol(a) < jcol(b); });
+        else  // per integrator, column-major inside (JE is in CSC order already)
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return JE[a].contrib < JE[b].contrib; });
+        for (size_t k : ord) { P.srcJ.push_back((int)k); P.Jr.push_back((int32_t)jrow(k)); P.Jc.push_back((int32_t)jcol(k)); }
+        P.nnzJ = (long long)P.srcJ.size();
+        if (P.order == QCK_ORDER_ROW_MAJOR) {
+            std::vector<int> pos((size_t)h->nnzH);
+            for (size_t k = 0; k < pos.size(); ++k) pos[k] = (int)k;
+            std::stable_sort(pos.begin(), pos.end(), [&](int a, int b) { return h->Hr[a] != h->Hr[b] ? h->Hr[a] < h->Hr[b] : h->Hc[a] < h->Hc[b]; });
+            std::vector<int> where((size_t)h->nnzH);
+            for (size_t k = 0; k < pos.size(); ++k) { P.srcH.push_back(pos[k]); P.Hr.push_back(h->Hr[pos[k]]); P.Hc.push_back(h->Hc[pos[k]]); where[pos[k]] = (int)k; }
+            for (long long sp : h->shared_positions) P.shared.push_back(where[(size_t)sp]);
+            std::sort(P.shared.begin(), P.shared.end());
+        } else {
+            std::vector<size_t> ho(HE.size());
+            for (size_t k = 0; k < ho.size(); ++k) ho[k] = k;
+            std::stable_sort(ho.begin(), ho.end(), [&](size_t a, size_t b) { return HE[a].contrib != HE[b].contrib ? HE[a].contrib < HE[b].contrib : HE[a].key < HE[b].key; });
+            for (size_t k : ho) {
+                if (hdst[k] < 0) return fail(h, QCK_EINVAL, "internal: Hessian entry without a destination");
+                P.srcH.push_back((int)hdst[k]);  // canonical position, or nnzH + partial column (this integrator's own contribution)
+                P.Hr.push_back((int32_t)(HE[k].key % zz)); P.Hc.push_back((int32_t)(HE[k].key / zz));
+            }
+        }
+        P.nnzH = (long long)P.srcH.size();
+    }
+
     // ---- per-class image placement, segments and constants ---------------------------------------------------------------------
     for (size_t ci = 0; ci < h->classes.size(); ++ci) {
         ClassHost& C = h->classes[ci];
@@ -788,7 +825,43 @@ int qck_check_status(qck_handle* h) {
     return fail(h, QCK_ERANGE, "device reported status 0x%x", st);
 }
 
+// canonical h->dJ / h->dH (+ the partial columns) -> caller-order arrays, on stream st
+int qck_reorder(qck_handle* h, uint32_t mask, double* dJ_out, double* dH_out, cudaStream_t st) {
+    const QckPublicOrder& P = h->pub;
+    const long long nk = h->T - 1;
+    int launches = 0, rc = 0;
+    if ((mask & QCK_EVAL_J) && dJ_out) rc = qck_launch_reorder(h->dJ, nullptr, dJ_out, P.d_srcJ, (int)P.nnzJ, h->nnzJ, 0, nk, st, &launches);
+    if (!rc && (mask & QCK_EVAL_H) && dH_out && h->eval_hessian)
+        rc = qck_launch_reorder(h->dH, h->dpartial, dH_out, P.d_srcH, (int)P.nnzH, h->nnzH, h->npart, nk, st, &launches);
+    h->launches += launches;
+    return rc ? fail(h, QCK_ECUDA, "reorder kernel launch: %s", cudaGetErrorString((cudaError_t)rc)) : QCK_OK;
+}
+
 namespace {
+
+// Host-buffer path under a structure-order policy other than CSC: one pass into the handle's canonical device arrays, a gather
+// into caller order on the device, plain copies out (no compact transport: the kron blocks are not contiguous in these orders).
+int eval_host_reordered(qck_handle* h, const double* Z, const double* mu, double* F, double* J, double* H) {
+    const long long nk = h->T - 1;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->pipe.valid_mask = 0; h->pipe.z_staged = false; h->pipe.z_on_device = false; h->pipe.mu_on_device = false;
+    if (!h->eval_hessian) H = nullptr;
+    uint32_t mask = (F ? QCK_EVAL_F : 0u) | (J ? QCK_EVAL_J : 0u) | (H ? QCK_EVAL_H : 0u);
+    if (!mask) return QCK_OK;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * h->T * h->zdim, cudaMemcpyHostToDevice, st));
+    if (H) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * nk * h->dyn, cudaMemcpyHostToDevice, st));
+    int rc = qck_run(h, mask, 0, nk, h->dZ, h->dmu, F ? h->dF : nullptr, J ? h->dJ : nullptr, H ? h->dH : nullptr, st, 0);
+    if (rc) return rc;
+    if ((rc = qck_reorder(h, mask, h->pub.dJ, h->pub.dH, st))) return rc;
+    if (F) CUDA_TRY(h, cudaMemcpyAsync(F, h->dF, sizeof(double) * nk * h->dyn, cudaMemcpyDeviceToHost, st));
+    if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->pub.dJ, sizeof(double) * nk * h->pub.nnzJ, cudaMemcpyDeviceToHost, st));
+    if (H) CUDA_TRY(h, cudaMemcpyAsync(H, h->pub.dH, sizeof(double) * nk * h->pub.nnzH, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->pipe.h2d_bytes = (long long)sizeof(double) * (h->T * h->zdim + (H ? nk * h->dyn : 0));
+    h->pipe.d2h_bytes = (long long)sizeof(double) * ((F ? nk * h->dyn : 0) + (J ? nk * h->pub.nnzJ : 0) + (H ? nk * h->pub.nnzH : 0));
+    return h->uses_status ? qck_check_status(h) : QCK_OK;
+}
 
 int eval_host(qck_handle* h, const double* Z, const double* mu, double* F, double* J, double* H) {
     QckDeviceScope device_scope;  // the caller's current CUDA device is restored on return
@@ -797,6 +870,7 @@ int eval_host(qck_handle* h, const double* Z, const double* mu, double* F, doubl
     if (!h->children.empty()) return qck_multi_eval(h, Z, mu, F, J, H);
     if (h->device < 0) return fail(h, QCK_ENODEVICE, "structure-only handle (device=-1): libqcknot has no CPU evaluation path");
     if (H && h->eval_hessian && !mu) return fail(h, QCK_EINVAL, "the Hessian needs the multipliers mu");
+    if (h->pub.order != QCK_ORDER_CSC) return eval_host_reordered(h, Z, mu, F, J, H);
     return qck_pipe_eval(h, Z, mu, F, J, H);
 }
 
@@ -835,6 +909,8 @@ int qck_create_single(const qck_problem_desc* d, qck_handle** out, bool exclude_
     h->eval_hessian = d->eval_hessian ? 1 : 0;
     h->exclude_shared = exclude_shared;
     h->host_threads = d->host_threads;
+    h->pub.order = d->structure_order;
+    if (h->pub.order < QCK_ORDER_CSC || h->pub.order > QCK_ORDER_PER_INTEGRATOR) { fail(h, QCK_EINVAL, "unknown structure_order %d", d->structure_order); return bail(QCK_EINVAL); }
     h->ib = d->integ_begin; h->ie = d->integ_end;
     if (h->ie < 0) { h->ie = d->n_integrators; }  // integ_end < 0: every integrator; begin == end: none (an empty shard launches nothing)
     if (h->ib < 0 || h->ie > d->n_integrators || h->ib > h->ie) { fail(h, QCK_EINVAL, "bad integrator range [%d,%d)", h->ib, h->ie); return bail(QCK_EINVAL); }
@@ -892,6 +968,19 @@ int qck_create_single(const qck_problem_desc* d, qck_handle** out, bool exclude_
         cudaMemset(p, 0, 16);
         h->d_status = static_cast<int*>(p);
     }
+    if (h->pub.order != QCK_ORDER_CSC) {  // caller-order arrays + gather tables of the structure-order policy
+        QckPublicOrder& P = h->pub;
+        if ((ce = upload(h, P.srcJ, &P.d_srcJ, h->allocs)) != cudaSuccess || (ce = upload(h, P.srcH, &P.d_srcH, h->allocs)) != cudaSuccess) {
+            fail(h, QCK_ECUDA, "uploading the structure-order tables: %s", cudaGetErrorString(ce)); return bail(QCK_ECUDA);
+        }
+        struct { double** p; long long n; } pb[] = {{&P.dJ, nk * std::max<long long>(P.nnzJ, 1)}, {&P.dH, nk * std::max<long long>(P.nnzH, 1)}};
+        for (auto& b : pb) {
+            void* q = nullptr;
+            if ((ce = cudaMalloc(&q, sizeof(double) * (size_t)b.n)) != cudaSuccess) { fail(h, QCK_ENOMEM, "device allocation of %lld doubles failed: %s", b.n, cudaGetErrorString(ce)); return bail(QCK_ENOMEM); }
+            h->allocs.push_back(q);
+            *b.p = static_cast<double*>(q);
+        }
+    }
     for (auto& C : h->classes) h->uses_status = h->uses_status || (C.dev.tape != nullptr && C.dev.tape_levels > 0);
     if ((ce = cudaDeviceSynchronize()) != cudaSuccess) { fail(h, QCK_ECUDA, "%s", cudaGetErrorString(ce)); return bail(QCK_ECUDA); }
     *out = h;
@@ -914,6 +1003,7 @@ int qck_create(const qck_problem_desc* d, qck_handle** out) {
         return qck_create_single(&d1, out, false);
     }
     if (d->shard_mode != QCK_SHARD_KNOT && d->shard_mode != QCK_SHARD_ENSEMBLE) return fail(nullptr, QCK_EINVAL, "unknown shard_mode %d", d->shard_mode);
+    if (d->structure_order != QCK_ORDER_CSC) return fail(nullptr, QCK_EINVAL, "structure_order other than CSC is served on single-GPU handles only (n_gpus = %d)", d->n_gpus);
     // the parent holds sizes + structures of the whole problem; one child per GPU does the work
     qck_problem_desc dp = *d;
     dp.device = -1; dp.n_gpus = 1; dp.integ_begin = 0; dp.integ_end = -1;
@@ -942,28 +1032,35 @@ void qck_destroy(qck_handle* h) {
 
 int qck_sizes(const qck_handle* h, int64_t* dyn, int64_t* nnzJ, int64_t* nnzH) {
     if (!h) return QCK_EINVAL;
+    const bool re = h->pub.order != QCK_ORDER_CSC;
     if (dyn) *dyn = h->dyn;
-    if (nnzJ) *nnzJ = h->nnzJ;
-    if (nnzH) *nnzH = h->nnzH;
+    if (nnzJ) *nnzJ = re ? h->pub.nnzJ : h->nnzJ;
+    if (nnzH) *nnzH = re ? h->pub.nnzH : h->nnzH;
     return QCK_OK;
 }
 
 int qck_jacobian_structure(const qck_handle* h, int64_t knot_offset, int64_t* rows, int64_t* cols) {
     if (!h || !rows || !cols) return QCK_EINVAL;
+    const bool re = h->pub.order != QCK_ORDER_CSC;
+    const std::vector<int32_t>&Jr = re ? h->pub.Jr : h->Jr, &Jc = re ? h->pub.Jc : h->Jc;
+    const long long nnz = (long long)Jr.size();
     for (long long t = 0; t < h->T - 1; ++t)
-        for (long long k = 0; k < h->nnzJ; ++k) {
-            rows[t * h->nnzJ + k] = h->Jr[k] + (t + knot_offset) * h->dyn + 1;
-            cols[t * h->nnzJ + k] = h->Jc[k] + (t + knot_offset) * h->zdim + 1;
+        for (long long k = 0; k < nnz; ++k) {
+            rows[t * nnz + k] = Jr[k] + (t + knot_offset) * h->dyn + 1;
+            cols[t * nnz + k] = Jc[k] + (t + knot_offset) * h->zdim + 1;
         }
     return QCK_OK;
 }
 
 int qck_hessian_structure(const qck_handle* h, int64_t knot_offset, int64_t* rows, int64_t* cols) {
     if (!h || !rows || !cols) return QCK_EINVAL;
+    const bool re = h->pub.order != QCK_ORDER_CSC;
+    const std::vector<int32_t>&Hr = re ? h->pub.Hr : h->Hr, &Hc = re ? h->pub.Hc : h->Hc;
+    const long long nnz = (long long)Hr.size();
     for (long long t = 0; t < h->T - 1; ++t)
-        for (long long k = 0; k < h->nnzH; ++k) {
-            rows[t * h->nnzH + k] = h->Hr[k] + (t + knot_offset) * h->zdim + 1;
-            cols[t * h->nnzH + k] = h->Hc[k] + (t + knot_offset) * h->zdim + 1;
+        for (long long k = 0; k < nnz; ++k) {
+            rows[t * nnz + k] = Hr[k] + (t + knot_offset) * h->zdim + 1;
+            cols[t * nnz + k] = Hc[k] + (t + knot_offset) * h->zdim + 1;
         }
     return QCK_OK;
 }
@@ -987,8 +1084,14 @@ int qck_eval_device(qck_handle* h, uint32_t mask, const double* dZ, const double
     if (!(m & QCK_EVAL_F)) dF = nullptr;
     if (!(m & QCK_EVAL_J)) dJ = nullptr;
     if (!(m & QCK_EVAL_H)) dH = nullptr;
-    if (dZ == h->dZ || dmu == h->dmu || dF == h->dF || dJ == h->dJ || dH == h->dH) { h->pipe.valid_mask = 0; h->pipe.z_on_device = false; h->pipe.mu_on_device = false; }
-    return qck_run(h, m, 0, h->T - 1, dZ, dmu, dF, dJ, dH, stream ? static_cast<cudaStream_t>(stream) : h->stream, 0);
+    if (dZ == h->dZ || dmu == h->dmu || dF == h->dF || dJ == h->dJ || dH == h->dH || h->pub.order != QCK_ORDER_CSC) { h->pipe.valid_mask = 0; h->pipe.z_on_device = false; h->pipe.mu_on_device = false; }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    if (h->pub.order != QCK_ORDER_CSC) {  // kernels write the handle's canonical arrays; one gather pass into the caller's
+        if (dJ == h->dJ || dH == h->dH) return fail(h, QCK_EINVAL, "structure_order: dJ / dH must not be the handle's canonical buffers");
+        int rc = qck_run(h, m, 0, h->T - 1, dZ, dmu, dF, dJ ? h->dJ : nullptr, dH ? h->dH : nullptr, st, 0);
+        return rc ? rc : qck_reorder(h, m, dJ, dH, st);
+    }
+    return qck_run(h, m, 0, h->T - 1, dZ, dmu, dF, dJ, dH, st, 0);
 }
 
 int qck_device_buffers(qck_handle* h, double** dZ, double** dmu, double** dF, double** dJ, double** dH) {
@@ -998,8 +1101,8 @@ int qck_device_buffers(qck_handle* h, double** dZ, double** dmu, double** dF, do
     if (dZ) *dZ = h->dZ;
     if (dmu) *dmu = h->dmu;
     if (dF) *dF = h->dF;
-    if (dJ) *dJ = h->dJ;
-    if (dH) *dH = h->dH;
+    if (dJ) *dJ = h->pub.order != QCK_ORDER_CSC ? h->pub.dJ : h->dJ;  // (caller-order arrays under a structure-order policy)
+    if (dH) *dH = h->pub.order != QCK_ORDER_CSC ? h->pub.dH : h->dH;
     h->pipe.valid_mask = 0; h->pipe.z_on_device = false; h->pipe.mu_on_device = false;  // the caller may overwrite them
     return QCK_OK;
 }
@@ -1022,8 +1125,9 @@ int qck_synchronize(qck_handle* h) {
 
 int qck_shared_hessian_positions(const qck_handle* h, int64_t* count, int64_t* pos) {
     if (!h || !count) return QCK_EINVAL;
-    *count = (int64_t)h->shared_positions.size();
-    if (pos) for (size_t k = 0; k < h->shared_positions.size(); ++k) pos[k] = h->shared_positions[k];
+    const std::vector<long long>& sp = h->pub.order != QCK_ORDER_CSC ? h->pub.shared : h->shared_positions;
+    *count = (int64_t)sp.size();
+    if (pos) for (size_t k = 0; k < sp.size(); ++k) pos[k] = sp[k];
     return QCK_OK;
 }
 

@@ -199,6 +199,8 @@ size_t qck_colexp_scratch_rec(int N);
 int qck_launch_genexp(const QckLaunch& L, int sm_count, cudaStream_t stream, int* launches, bool* done);
 size_t qck_genexp_warp_bytes(int N, int nc, int nd);
 int qck_fused_aux_limit(void);
+int qck_launch_reorder(const double* arr, const double* partial, double* out, const int* src, int C, long long nnz, int npart, long long nk,
+                       cudaStream_t stream, int* launches);  // out[t*C + i] = src[i] < nnz ? arr[t*nnz + src[i]] : partial[t*npart + src[i] - nnz]
 int qck_pick_threads(const QckClassDev& c);  // CTA size of the quantum kernel for this class  // more aux entries than this go through the stand-alone aux kernel
 int qck_launch_reduce(const QckReduce& R, double* H, const double* partial, long long n_knots, long long nnzH,
                       int npart, cudaStream_t stream, int* launches);

@@ -325,8 +325,10 @@ int qck_eval_resident(qck_handle* h, uint32_t mask) {
     if (h->children.empty()) {
         if (h->device < 0) return qck_fail(h, QCK_ENODEVICE, "structure-only handle");
         QCK_CUDA_TRY(h, cudaSetDevice(h->device));
-        return qck_run(h, mask, 0, h->T - 1, h->dZ, h->dmu, (mask & QCK_EVAL_F) ? h->dF : nullptr, (mask & QCK_EVAL_J) ? h->dJ : nullptr,
-                       (mask & QCK_EVAL_H) ? h->dH : nullptr, h->stream, 0);
+        int rc = qck_run(h, mask, 0, h->T - 1, h->dZ, h->dmu, (mask & QCK_EVAL_F) ? h->dF : nullptr, (mask & QCK_EVAL_J) ? h->dJ : nullptr,
+                         (mask & QCK_EVAL_H) ? h->dH : nullptr, h->stream, 0);
+        if (!rc && h->pub.order != QCK_ORDER_CSC) rc = qck_reorder(h, mask, h->pub.dJ, h->pub.dH, h->stream);  // qck_device_buffers returns these
+        return rc;
     }
     const bool shared = h->shard_mode == QCK_SHARD_ENSEMBLE && (mask & QCK_EVAL_H) && h->eval_hessian && !h->sh_pos.empty();
     if (shared) {

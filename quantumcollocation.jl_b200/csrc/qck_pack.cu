@@ -26,6 +26,20 @@ __global__ void __launch_bounds__(256) qck_unpack_kernel(double* __restrict__ ar
     }
 }
 
+// structure-order policies other than CSC: caller-order array from the canonical one (and, for per-integrator duplicates, from
+// the partial columns of the shared Hessian positions)
+__global__ void __launch_bounds__(256) qck_reorder_kernel(const double* __restrict__ arr, const double* __restrict__ partial, double* __restrict__ out,
+                                                          const int* __restrict__ src, int C, long long nnz, int npart, long long nk) {
+    for (long long t = blockIdx.x; t < nk; t += gridDim.x) {
+        const double* a = arr + t * nnz;
+        double* o = out + t * C;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            const int s = __ldg(src + i);
+            o[i] = s < nnz ? a[s] : partial[t * npart + (s - nnz)];
+        }
+    }
+}
+
 // few positions per knot (shared Hessian entries): one thread per (knot, position)
 __global__ void __launch_bounds__(256) qck_pack_small_kernel(const double* __restrict__ arr, double* __restrict__ out, const int* __restrict__ src,
                                                              int C, long long ostride, long long nnz, long long nk) {
@@ -76,6 +90,14 @@ int qck_launch_peer_reduce(const QckPeerReduce& R, double* H, long long n_knots,
     long long grid = (total + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
     qck_peer_reduce_kernel<<<(unsigned)grid, 256, 0, stream>>>(R, H, n_knots, nnzH);
+    if (launches) ++*launches;
+    return (int)cudaGetLastError();
+}
+
+int qck_launch_reorder(const double* arr, const double* partial, double* out, const int* src, int C, long long nnz, int npart, long long nk,
+                       cudaStream_t stream, int* launches) {
+    if (C <= 0 || nk <= 0) return 0;
+    qck_reorder_kernel<<<(unsigned)std::min<long long>(nk, 148 * 8), 256, 0, stream>>>(arr, partial, out, src, C, nnz, npart, nk);
     if (launches) ++*launches;
     return (int)cudaGetLastError();
 }

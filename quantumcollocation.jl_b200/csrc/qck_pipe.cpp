@@ -698,6 +698,7 @@ extern "C" {
 // what crosses PCIe for value array `arr` (0 F, 1 J, 2 H): runs (full offset, compact offset, length, repeats) per knot block
 int qck_compact_map(const qck_handle* h, int32_t arr, int64_t* count, int32_t* segs) {
     if (!h || arr < 0 || arr > 2 || !count) return QCK_EINVAL;
+    if (h->pub.order != QCK_ORDER_CSC) return QCK_EINVAL;  // the compact transport exists for the CSC order only
     const qck_handle* src = h;
     *count = (int64_t)src->own[arr].size();
     if (segs)
@@ -711,7 +712,7 @@ int qck_compact_map(const qck_handle* h, int32_t arr, int64_t* count, int32_t* s
 // the host half of the host-buffer path on its own (works on structure-only handles: no device involved): expands `nk` knot
 // blocks of the compact layout into `out` with the library's host threads, exactly as qck_eval_* do after the D2H copy
 int qck_expand_host(const qck_handle* h, int32_t arr, const double* compact, double* out, int64_t nk) {
-    if (!h || arr < 0 || arr > 2 || !compact || !out || nk < 0) return QCK_EINVAL;
+    if (!h || arr < 0 || arr > 2 || !compact || !out || nk < 0 || h->pub.order != QCK_ORDER_CSC) return QCK_EINVAL;
     long long C = 0;
     for (auto& g : h->own[arr]) C += g.len;
     const long long nnz = arr == 0 ? h->dyn : (arr == 1 ? h->nnzJ : h->nnzH);

@@ -40,6 +40,11 @@ class QuantumDynamics:
     n_gpus, shard_mode        n_gpus > 1: this ONE object drives GPUs device .. device+n_gpus-1 (or `devices`), the knot blocks
                               ("knot") or the quantum integrators ("ensemble") partitioned inside libqcknot; F/dF/mu_d2F fill
                               the caller's single arrays exactly as with one GPU.
+    structure_order           intra-knot order of the structure entries and value arrays: "csc" (default: union pattern,
+                              column-major), "row_major" (union pattern, row-major) or "per_integrator" (the integrators' own
+                              lists one after the other; shared Hessian positions appear once per integrator and the consumer
+                              sums the duplicates, test/test_utils.jl:14-27).  The Core's own order is not visible in the
+                              reference repository, so it is a policy of qck_create rather than a constant.
     """
 
     def __init__(
@@ -54,6 +59,7 @@ class QuantumDynamics:
         shard_mode: str = "knot",
         devices: Optional[Sequence[int]] = None,
         host_threads: int = 0,
+        structure_order: str = "csc",
     ):
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -101,10 +107,14 @@ class QuantumDynamics:
                 raise ValueError("devices must list n_gpus ordinals")
             devs = (C.c_int32 * self.n_gpus)(*[int(x) for x in devices])
             self._keep.append(devs)
+        orders = {"csc": _lib.QCK_ORDER_CSC, "row_major": _lib.QCK_ORDER_ROW_MAJOR, "per_integrator": _lib.QCK_ORDER_PER_INTEGRATOR}
+        if structure_order not in orders:
+            raise ValueError(f"structure_order must be one of {sorted(orders)}")
+        self.structure_order = structure_order
         pd = _lib.ProblemDesc(self.T, self.zdim, dt_off, dt_fixed, len(self.integrators), int(self.eval_hessian),
                               int(device), int(q0), int(q1), self.n_gpus, descs,
                               _lib.QCK_SHARD_ENSEMBLE if shard_mode == "ensemble" else _lib.QCK_SHARD_KNOT,
-                              int(host_threads), devs)
+                              int(host_threads), devs, orders[structure_order], 0)
         rc = self._lib.qck_create(C.byref(pd), C.byref(self._h))
         if rc != 0:
             msg = self._lib.qck_last_error(None).decode()

@@ -35,6 +35,53 @@ def check(systems, traj, integrators, eval_hessian=True):
     D.close()
 
 
+@pytest.mark.parametrize("order", ["row_major", "per_integrator"])
+@pytest.mark.parametrize("name,kw", [("hadamard", {"T": 9}), ("hadamard", {"T": 6, "integrator": "exponential"}), ("cz", {"T": 5}),
+                                     ("ket", {"T": 6, "free_time": False}), ("sampling", {"T": 4, "n_systems": 5})])
+def test_structure_order_policies(name, kw, order):
+    """Non-default structure orders (qck_problem_desc.structure_order): values against the oracle's restatement of the same policy,
+    through the host-buffer entry points and the device-resident one; the assembled sparse matrices equal the CSC handle's."""
+    import torch
+    systems, traj, integrators = wl.config(name, **kw)
+    D = qcknot.QuantumDynamics(integrators, traj, structure_order=order)
+    O = oracle_dynamics(integrators, traj, structure_order=order)
+    assert np.array_equal(D.dF_structure, np.array(O.dF_structure).reshape(-1, 2))
+    assert np.array_equal(D.mu_d2F_structure, np.array(O.mu_d2F_structure).reshape(-1, 2))
+    Z = traj.datavec
+    mu = wl.random_multipliers(D.n_blocks * D.dyn)
+    F, J, H = D.eval_all(Z, mu)
+    for got, want in ((F, O.F(Z)), (J, O.dF(Z)), (H, O.mu_d2F(Z, mu))):
+        assert rel_err(got, want) < TOL and entry_err(got, want) < ENTRY_TOL
+    assert np.array_equal(J, D.dF(Z)) and np.array_equal(H, D.mu_d2F(Z, mu)) and np.array_equal(F, D.F(Z))
+    # same matrices as the default order, bit for bit (Jacobian) / after summing duplicates (Hessian)
+    C0 = qcknot.QuantumDynamics(integrators, traj)
+    F0, J0, H0 = C0.eval_all(Z, mu)
+    assert np.array_equal(F, F0)
+    key = lambda st: np.lexsort((st[:, 0], st[:, 1]))
+    assert np.array_equal(J[key(D.dF_structure)], J0[key(C0.dF_structure)])
+    if order == "row_major":
+        assert np.array_equal(H[key(D.mu_d2F_structure)], H0[key(C0.mu_d2F_structure)])
+    else:
+        n = traj.T * traj.dim
+        dense = lambda v, st: np.bincount(((st[:, 0] - 1) * n + st[:, 1] - 1), weights=v, minlength=0)
+        a, b = dense(H, D.mu_d2F_structure), dense(H0, C0.mu_d2F_structure)
+        m = max(len(a), len(b))
+        a, b = np.pad(a, (0, m - len(a))), np.pad(b, (0, m - len(b)))
+        assert rel_err(a, b) < 1e-13
+    # device-resident entry point writes the caller's arrays in the same order
+    dev = torch.device("cuda:0")
+    dZ, dmu = torch.from_numpy(Z).to(dev), torch.from_numpy(mu).to(dev)
+    dF = torch.empty(len(F), dtype=torch.float64, device=dev)
+    dJ = torch.empty(len(J), dtype=torch.float64, device=dev)
+    dH = torch.empty(max(len(H), 1), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    D.eval_device(7, dZ.data_ptr(), dmu.data_ptr(), dF.data_ptr(), dJ.data_ptr(), dH.data_ptr(), 0)
+    D.synchronize()
+    assert np.array_equal(dJ.cpu().numpy(), J) and np.array_equal(dH.cpu().numpy()[: len(H)], H) and np.array_equal(dF.cpu().numpy(), F)
+    for x in (D, C0):
+        x.close()
+
+
 @pytest.mark.parametrize("free_time", [True, False])
 def test_hadamard_pade(free_time):
     check(*wl.config("hadamard", T=12, free_time=free_time))

@@ -54,6 +54,37 @@ def test_structures_bit_exact_vs_oracle(name, kw):
         D.close()
 
 
+@pytest.mark.parametrize("order", ["row_major", "per_integrator"])
+@pytest.mark.parametrize("name,kw", [("hadamard", {}), ("cz", {"T": 4}), ("ket", {"T": 5, "free_time": False}),
+                                     ("sampling", {"T": 3, "n_systems": 5})])
+def test_structure_order_policies_vs_oracle(name, kw, order):
+    """qck_problem_desc.structure_order: the caller-visible structures of the non-default policies, bit-exact against the oracle's
+    restatement of the same policy; every policy describes the same sparse matrices (the Core's own order is [DEP-RECALL])."""
+    systems, traj, integrators = wl.config(name, **kw)
+    D = qcknot.QuantumDynamics(integrators, traj, device=-1, structure_order=order)
+    O = oracle_dynamics(integrators, traj, structure_order=order)
+    C0 = qcknot.QuantumDynamics(integrators, traj, device=-1)
+    assert (D.dyn, D.nnzJ, D.nnzH) == (O.dyn, O.nnzJ, O.nnzH)
+    assert np.array_equal(D.dF_structure, np.array(O.dF_structure, dtype=np.int64).reshape(-1, 2))
+    assert np.array_equal(D.mu_d2F_structure, np.array(O.mu_d2F_structure, dtype=np.int64).reshape(-1, 2))
+    assert sorted(map(tuple, D.dF_structure)) == sorted(map(tuple, C0.dF_structure))
+    assert set(map(tuple, D.mu_d2F_structure)) == set(map(tuple, C0.mu_d2F_structure))
+    if order == "row_major":
+        assert D.nnzH == C0.nnzH
+    else:  # duplicates exactly where several integrators share a Hessian position (shared controls / timestep)
+        assert D.nnzH >= C0.nnzH and (D.nnzH > C0.nnzH) == (len(C0.shared_hessian_positions()) > 0)
+    for x in (D, C0):
+        x.close()
+
+
+def test_structure_order_rejected_on_multi_gpu_and_unknown():
+    systems, traj, integrators = wl.config("hadamard", T=9)
+    with pytest.raises(ValueError):
+        qcknot.QuantumDynamics(integrators, traj, device=-1, structure_order="diagonal")
+    with pytest.raises(qcknot.QcknotError, match="single-GPU"):
+        qcknot.QuantumDynamics(integrators, traj, device=0, n_gpus=2, structure_order="row_major")
+
+
 def test_survey_size_table():
     # SURVEY.md section 8 size table (pade column): C1 104/58, C2 6674/1643 (zdim 175, dyn 170), C5 (S=256) 155,664/49,162
     for name, kw, want in (("hadamard", {}, (12, 104, 58, 15)), ("cz", {"T": 3}, (170, 6674, 1643, 175)),
