@@ -15,11 +15,38 @@ namespace {
 // straight from registers: no staging image.  Destinations per member come from the host's placement pass.
 // ------------------------------------------------------------------------------------------------------------
 // NC: columns of the state (N for unitaries, 1 for kets: QuantumStatePadeIntegrator = the same algebra on one column)
-template <int N, int ND, int NC>
-__global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
+//
+// ST (block-staged write-out; single-system problems: one member, no partial columns, this launch the only writer of the knot
+// blocks): a lane's run of 2N doubles is 32..64 bytes, so a warp-wide 16-byte store of 32 such runs touches 32 different lines and
+// the memory pipeline (ncu: L1/TEX the busiest unit, 2.9x the algorithmic L2 sectors), not HBM, bounds the direct-store kernel.
+// The IPW items of a warp are IPW CONSECUTIVE knots, i.e. one contiguous range of F, of the Jacobian values and of the Hessian
+// values.  With ST the lanes store to a shared-memory copy of those ranges at the very offsets they would use in global memory
+// (kron blocks N times) and the warp then copies each range out linearly, 512 contiguous bytes per store instruction.  Two phases
+// share the space: F + Jacobian, copied out, then the Hessian.  The derivative-integrator entries inside those ranges are
+// written by the stand-alone aux kernel right after this one (fused into the staged kernel they cost 60 us of dependent loads
+// on 8 warps per SM; the flat aux kernel takes 8 us).
+template <int N, int ND, int NC, bool ST>
+__global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, const int warp_doubles) {
     constexpr int n2 = 2 * N, blk = n2 * n2, IPW = 32 / NC, NPAIR = ND * (ND + 1) / 2;
     const QckClassDev& c = p.c;
     const int lane = threadIdx.x & 31;
+    extern __shared__ double2 col_smem[];
+    double* const wimg = ST ? reinterpret_cast<double*>(col_smem) + (size_t)(threadIdx.x >> 5) * warp_doubles : nullptr;
+    double* const wF = wimg;                                    // phase 1: [IPW][dyn] | [IPW][nnzJ]
+    double* const wJ = ST ? wimg + IPW * c.dyn : nullptr;
+    double* const wH = wimg;                                    // phase 2: [IPW][nnzH]
+    // linear copy of `count` doubles shared -> global (same parity of both addresses by construction: even knot, even offsets)
+    auto copy_out = [&](double* g, const double* s, long long count) {
+        __syncwarp();
+        if ((reinterpret_cast<uintptr_t>(g) & 8) == 0) {
+            const int pairs = (int)(count >> 1);
+            for (int k = lane; k < pairs; k += 32) reinterpret_cast<double2*>(g)[k] = reinterpret_cast<const double2*>(s)[k];
+            if ((count & 1) && lane == 0) g[count - 1] = s[count - 1];
+        } else {
+            for (int k = lane; k < (int)count; k += 32) g[k] = s[k];
+        }
+        __syncwarp();
+    };
     const int gi = lane / NC, col = lane - gi * NC;  // item slot inside the warp, column
     const bool needF = p.mask & QCK_EVAL_F, needJ = p.mask & QCK_EVAL_J, needH = p.mask & QCK_EVAL_H;
     const int nact = p.member_end - p.member_begin;
@@ -52,11 +79,14 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
         const long long it = on ? item : base;  // idle lanes shadow a valid item (no stores)
         const long long t = it / nact;
         const int mi = (int)(it - t * nact), m = p.member_begin + mi;
-        const int soff = p.moff_global[3 * mi], coff = p.moff_global[3 * mi + 1], roff = p.moff_global[3 * mi + 2];
+        const int soff = __ldg(p.moff_global + 3 * mi), coff = __ldg(p.moff_global + 3 * mi + 1), roff = __ldg(p.moff_global + 3 * mi + 2);
         const double* zt = p.Z + t * c.zdim;
         const int* qd = c.qdst + (size_t)m * QO_COUNT;
-        double* const oF = p.F + t * c.dyn;
-        double* const oJ = p.J + t * p.nnzJ;
+        const int gs = gi < IPW ? gi : 0;  // (idle lanes never store)
+        const int n_on = (int)((n_items - base) < (long long)IPW ? (n_items - base) : (long long)IPW);
+        double* const oF = ST ? wF + gs * c.dyn : p.F + t * c.dyn;
+        double* const oJ = ST ? wJ + gs * p.nnzJ : p.J + t * p.nnzJ;
+        double* const oH = ST ? wH + gs * p.nnzH : p.H + t * p.nnzH;
         // iso-vector quantity q: this lane's column (rows 0..N-1 real, then imaginary); arr0 = start of the knot block
         auto put_vec = [&](double* arr0, int d0, int q, const double2 (&x)[N]) {
             const int st = c.pl_stride[q];
@@ -80,30 +110,30 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
         auto put_H = [&](int q, const double2 (&x)[N]) {  // (>= nnzH: partial column of a shared position)
             const int d0 = qd[q];
             if (d0 < 0 || !on) return;
-            if (d0 < p.nnzH) put_vec(p.H + t * p.nnzH, d0, q, x);
+            if (ST || d0 < p.nnzH) put_vec(oH, d0, q, x);
             else put_vec(p.partial + t * p.npart, d0 - (int)p.nnzH, q, x);
         };
         auto put_scalar = [&](int q, double v) {
             const int d0 = qd[q];
             if (d0 < 0 || !on || col != 0) return;
-            if (d0 < p.nnzH) p.H[t * p.nnzH + d0] = v;
+            if (ST || d0 < p.nnzH) oH[d0] = v;
             else p.partial[t * p.npart + (d0 - p.nnzH)] = v;
         };
         // ---- inputs: this lane's column of U0, U1 and of the multipliers ------------------------------------------------------
         double2 d[N], s[N], mm[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-            const double u0r = zt[soff + col * n2 + r], u0i = zt[soff + col * n2 + N + r];
-            const double u1r = zt[c.zdim + soff + col * n2 + r], u1i = zt[c.zdim + soff + col * n2 + N + r];
+            const double u0r = __ldg(zt + soff + col * n2 + r), u0i = __ldg(zt + soff + col * n2 + N + r);
+            const double u1r = __ldg(zt + c.zdim + soff + col * n2 + r), u1i = __ldg(zt + c.zdim + soff + col * n2 + N + r);
             d[r] = make_double2(u1r - u0r, u1i - u0i);
             s[r] = make_double2(u1r + u0r, u1i + u0i);
-            mm[r] = needH ? make_double2(p.mu[t * c.dyn + roff + col * n2 + r], p.mu[t * c.dyn + roff + col * n2 + N + r]) : make_double2(0.0, 0.0);
+            mm[r] = needH ? make_double2(__ldg(p.mu + t * c.dyn + roff + col * n2 + r), __ldg(p.mu + t * c.dyn + roff + col * n2 + N + r)) : make_double2(0.0, 0.0);
         }
-        const double h = free_time ? zt[c.dt_off] : c.dt_fixed;
+        const double h = free_time ? __ldg(zt + c.dt_off) : c.dt_fixed;
         const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
         double a[ND];
 #pragma unroll
-        for (int j = 0; j < ND; ++j) a[j] = zt[coff + j];
+        for (int j = 0; j < ND; ++j) a[j] = __ldg(zt + coff + j);
         // ---- A = A0 + sum_j a_j A_j ---------------------------------------------------------------------------------------------
         const double2* const A0g = c.cmat + (size_t)m * c.cmat_stride;  // column-major
         const double2* const Ajg = c.dense_aj + (size_t)m * ND * N * N;  // [drive][row][column]
@@ -235,6 +265,10 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
                 }
             }
         }
+        if constexpr (ST) {  // phase 1 out: the warp's n_on knots of F and of the Jacobian values are one contiguous range each
+            if (needF) copy_out(p.F + base * c.dyn, wF, (long long)n_on * c.dyn);
+            if (needJ) copy_out(p.J + base * p.nnzJ, wJ, (long long)n_on * p.nnzJ);
+        }
         if (needH) {
             double2 w1[N];
             double s_ah[ND], pz[ND][ND];  // pz[i][j] = Re <A_i^H m, A_j d> (this lane's column)
@@ -293,7 +327,11 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p) {
 #pragma unroll
                 for (int i2 = 0; i2 <= j; ++i2, ++q) put_scalar(qo_haa(i2, j), c2h2 * gsum(s_aa[q]));
         }
-        if (mi == 0 && p.n_aux && on) do_aux(p, t, col, NC);  // derivative-integrator entries of this knot
+        if constexpr (ST) {
+            if (needH) copy_out(p.H + base * p.nnzH, wH, (long long)n_on * p.nnzH);
+        } else {
+            if (mi == 0 && p.n_aux && on) do_aux(p, t, col, NC);  // derivative-integrator entries of this knot
+        }
     }
 }
 
@@ -307,30 +345,58 @@ int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int
     static const int enabled = getenv("QCK_COLUMN") ? atoi(getenv("QCK_COLUMN")) : 1;
     const bool ket = c.kind == QCK_KET_PADE;
     if (!enabled || (c.kind != QCK_UNITARY_PADE && !ket) || c.order != 4 || c.N < 2 || c.N > 4 || c.nd < 1 || c.nd > 4 || !c.dense_aj || !c.qdst) return 0;
-    typedef void (*kern_t)(const QckLaunch);
+    typedef void (*kern_t)(const QckLaunch, const int);
     kern_t kern = nullptr;
-#define QCK_COL2(N_, NC_) (c.nd == 1 ? qck_column_kernel<N_, 1, NC_> : (c.nd == 2 ? qck_column_kernel<N_, 2, NC_> : (c.nd == 3 ? qck_column_kernel<N_, 3, NC_> : qck_column_kernel<N_, 4, NC_>)))
+    // block-staged write-out (unitaries of a single-system problem; QCK_COLUMN_STAGED=0: stores straight from registers as in
+    // round 1, which kets and ensembles keep)
+    static const int staged_knob = getenv("QCK_COLUMN_STAGED") ? atoi(getenv("QCK_COLUMN_STAGED")) : 1;
+    bool staged = staged_knob && !ket && L.sole_writer && L.member_end - L.member_begin == 1 && L.npart == 0;
+    const int ipw = 32 / (ket ? 1 : c.N);
+    int warp_doubles = 0, wpc = 8;
+    size_t smem = 0;
+    if (staged) {
+        const long long wd = (long long)ipw * std::max<long long>((long long)c.dyn + L.nnzJ, L.nnzH);
+        warp_doubles = (int)((wd + 1) & ~1LL);
+        static const int wpc_knob = getenv("QCK_COLUMN_WPC") ? atoi(getenv("QCK_COLUMN_WPC")) : 4;  // warps per CTA (1..8 measured: flat within 3 %)
+        wpc = (int)std::min<long long>(std::max(1, std::min(8, wpc_knob)), (220LL * 1024) / ((long long)warp_doubles * 8));
+        if ((220LL * 1024) / ((long long)warp_doubles * 8) < 4) { staged = false; wpc = 8; }  // (blocks too large to stage with enough warps per SM)
+        else smem = (size_t)wpc * warp_doubles * sizeof(double);
+    }
+#define QCK_COL3(N_, ND_, NC_) (staged && NC_ == N_ ? qck_column_kernel<N_, ND_, N_, true> : qck_column_kernel<N_, ND_, NC_, false>)
+#define QCK_COL2(N_, NC_) (c.nd == 1 ? QCK_COL3(N_, 1, NC_) : (c.nd == 2 ? QCK_COL3(N_, 2, NC_) : (c.nd == 3 ? QCK_COL3(N_, 3, NC_) : QCK_COL3(N_, 4, NC_))))
 #define QCK_COL(N_) (ket ? QCK_COL2(N_, 1) : QCK_COL2(N_, N_))
     kern = c.N == 2 ? QCK_COL(2) : (c.N == 3 ? QCK_COL(3) : QCK_COL(4));
 #undef QCK_COL
 #undef QCK_COL2
+#undef QCK_COL3
+    const int threads = 32 * wpc;
     int per_sm = 0;
-    if (L.plan && L.plan->kern == (const void*)kern) {
+    if (L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem) {
         per_sm = L.plan->per_sm;
     } else {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+        cudaError_t e = cudaSuccess;
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
         if (e != cudaSuccess) return (int)e;
-        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = 0; L.plan->per_sm = per_sm; }
+        if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = smem; L.plan->per_sm = per_sm; }
     }
     if (per_sm < 1) return 0;
     const long long n_items = L.n_knots * (long long)(L.member_end - L.member_begin);
-    const int ipw = 32 / (ket ? 1 : c.N);
     long long grid = (long long)sm_count * per_sm;
-    const long long need = (n_items + 8LL * ipw - 1) / (8LL * ipw);
+    const long long need = (n_items + (long long)wpc * ipw - 1) / ((long long)wpc * ipw);
     if (grid > need) grid = need;
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
-    if (dbg) fprintf(stderr, "[qcknot] column kernel: N=%d nd=%d CTAs/SM=%d grid=%lld items=%lld\n", c.N, c.nd, per_sm, grid, n_items);
-    kern<<<(unsigned)grid, 256, 0, stream>>>(L);
+    if (dbg) fprintf(stderr, "[qcknot] column kernel: N=%d nd=%d staged=%d (%d doubles/warp, %d warps/CTA) CTAs/SM=%d grid=%lld items=%lld\n", c.N, c.nd, (int)staged, warp_doubles, wpc, per_sm, grid, n_items);
+    if (staged && L.n_aux) {  // whole knot blocks are stored: the derivative-integrator entries follow in their own pass
+        QckLaunch Lq = L;
+        Lq.aux = nullptr; Lq.n_aux = 0;
+        kern<<<(unsigned)grid, threads, smem, stream>>>(Lq, warp_doubles);
+        if (launches) ++*launches;
+        *done = true;
+        const int e = (int)cudaGetLastError();
+        return e ? e : qck_launch_aux(L, stream, launches);
+    }
+    kern<<<(unsigned)grid, threads, smem, stream>>>(L, warp_doubles);
     if (launches) ++*launches;
     *done = true;
     return (int)cudaGetLastError();

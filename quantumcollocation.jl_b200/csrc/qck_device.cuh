@@ -80,29 +80,32 @@ __device__ __forceinline__ double warp_sum(double s) {
     return s;
 }
 
-__device__ __forceinline__ void do_aux(const QckLaunch& p, long long t, int tid, int nthreads) {
+// one derivative-integrator entry k of knot t (read-only loads, ld.global.nc: independent entries do not wait for each other's stores)
+__device__ __forceinline__ void aux_entry(const QckLaunch& p, long long t, int k, double dt) {
     const QckClassDev& c = p.c;
     const double* zt = p.Z + t * c.zdim;
-    const double dt = c.free_time ? __ldg(zt + c.dt_off) : c.dt_fixed;
-    // read-only loads (ld.global.nc): the entries of one thread do not wait for each other's stores
-#pragma unroll 4
-    for (int k = tid; k < p.n_aux; k += nthreads) {
-        const int4 a0 = __ldg(reinterpret_cast<const int4*>(p.aux + k));  // out, op, pos, i0
-        const int out = a0.x, op = a0.y, pos = a0.z, i0 = a0.w;
-        if (!((p.mask >> out) & 1u)) continue;
-        double v;
-        switch (op) {
-            case QAUX_CONST: v = __ldg(&p.aux[k].c); break;
-            case QAUX_NEG_DT: v = -dt; break;
-            case QAUX_NEG_Z: v = -__ldg(zt + i0); break;
-            case QAUX_NEG_MU: v = -__ldg(p.mu + t * c.dyn + i0); break;
-            default: v = __ldg(zt + c.zdim + i0) - __ldg(zt + i0) - dt * __ldg(zt + __ldg(&p.aux[k].i1)); break;
-        }
-        if (out == 0) p.F[t * c.dyn + pos] = v;
-        else if (out == 1) p.J[t * p.nnzJ + pos] = v;
-        else if (pos < p.nnzH) p.H[t * p.nnzH + pos] = v;
-        else p.partial[t * p.npart + (pos - p.nnzH)] = v;
+    const int4 a0 = __ldg(reinterpret_cast<const int4*>(p.aux + k));  // out, op, pos, i0
+    const int out = a0.x, op = a0.y, pos = a0.z, i0 = a0.w;
+    if (!((p.mask >> out) & 1u)) return;
+    double v;
+    switch (op) {
+        case QAUX_CONST: v = __ldg(&p.aux[k].c); break;
+        case QAUX_NEG_DT: v = -dt; break;
+        case QAUX_NEG_Z: v = -__ldg(zt + i0); break;
+        case QAUX_NEG_MU: v = -__ldg(p.mu + t * c.dyn + i0); break;
+        default: v = __ldg(zt + c.zdim + i0) - __ldg(zt + i0) - dt * __ldg(zt + __ldg(&p.aux[k].i1)); break;
     }
+    if (out == 0) p.F[t * c.dyn + pos] = v;
+    else if (out == 1) p.J[t * p.nnzJ + pos] = v;
+    else if (pos < p.nnzH) p.H[t * p.nnzH + pos] = v;
+    else p.partial[t * p.npart + (pos - p.nnzH)] = v;
+}
+
+__device__ __forceinline__ void do_aux(const QckLaunch& p, long long t, int tid, int nthreads) {
+    const QckClassDev& c = p.c;
+    const double dt = c.free_time ? __ldg(p.Z + t * c.zdim + c.dt_off) : c.dt_fixed;
+#pragma unroll 4
+    for (int k = tid; k < p.n_aux; k += nthreads) aux_entry(p, t, k, dt);
 }
 
 // same entries, operands already staged in shared memory by the prefetch (fused path: no global load latency)

@@ -795,6 +795,9 @@ int qck_run(qck_handle* h, uint32_t mask, long long k0, long long nk, const doub
         const bool take_aux = !aux_done && fuse_aux;
         L.aux = take_aux ? h->d_aux : nullptr; L.n_aux = take_aux ? (int)h->aux.size() : 0;
         if (take_aux) aux_done = true;
+        // one class with one member and no partial columns: whatever the launch does not write itself is written after it (the
+        // stand-alone aux kernel), so a kernel may store whole knot blocks (column kernel: block-staged write-out)
+        L.sole_writer = h->classes.size() == 1 && C.dev.n_members == 1 && h->npart == 0 && (take_aux || h->aux.empty() || !fuse_aux) ? 1 : 0;
         int rc = qck_launch_quantum(L, h->sm_count, st, &launches);
         if (rc) return fail(h, QCK_ECUDA, "quantum kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
     }

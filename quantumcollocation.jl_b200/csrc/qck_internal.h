@@ -161,6 +161,7 @@ struct QckLaunch {
     int db;                  // row-slice kernel: separate staging buffers for the F + J image and the Hessian image
     int spread;              // row-slice kernel: the kron block copies are issued right after A^2, ahead of the rest of phase 1
     int* status;             // device-side error word (QCK_ST_* bits)
+    int sole_writer;         // this launch (one class, one member, its fused aux entries) writes every position of the knot blocks
     QckPlanCache* plan;      // host-side: per-class launch plan cache (may be NULL)
 };
 

@@ -1403,8 +1403,15 @@ qck_quantum_kernel(const QckLaunch p) {
 #undef GSYNC
 }
 
-__global__ void qck_aux_kernel(const QckLaunch p) {
-    for (long long t = blockIdx.x; t < p.n_knots; t += gridDim.x) do_aux(p, t, threadIdx.x, blockDim.x);
+// stand-alone pass over the derivative-integrator entries: (knot, entry) pairs over the threads, consecutive threads on the
+// entries of one knot
+__global__ void __launch_bounds__(256) qck_aux_kernel(const QckLaunch p) {
+    const long long total = p.n_knots * p.n_aux;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / p.n_aux;
+        const int k = (int)(i - t * p.n_aux);
+        aux_entry(p, t, k, p.c.free_time ? __ldg(p.Z + t * p.c.zdim + p.c.dt_off) : p.c.dt_fixed);
+    }
 }
 
 // One warp per (knot, shared position): the lanes walk the contributors' partial columns in ascending order with stride 32,
@@ -1594,12 +1601,16 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
     return (int)cudaGetLastError();
 }
 
-int qck_fused_aux_limit(void) { return QCK_MAX_FUSED_AUX; }
+int qck_fused_aux_limit(void) {
+    static const int lim = getenv("QCK_FUSED_AUX_LIMIT") ? atoi(getenv("QCK_FUSED_AUX_LIMIT")) : QCK_MAX_FUSED_AUX;  // (-1: never fused)
+    return lim;
+}
 
 int qck_launch_aux(const QckLaunch& L, cudaStream_t stream, int* launches) {
     if (L.n_aux == 0 || L.n_knots <= 0) return 0;
-    long long grid = L.n_knots < 4096 ? L.n_knots : 4096;
-    qck_aux_kernel<<<(unsigned)grid, 64, 0, stream>>>(L);
+    const long long total = L.n_knots * L.n_aux;
+    const long long grid = std::min<long long>((total + 255) / 256, 148 * 8);
+    qck_aux_kernel<<<(unsigned)grid, 256, 0, stream>>>(L);
     if (launches) ++*launches;
     return (int)cudaGetLastError();
 }

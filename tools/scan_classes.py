@@ -42,20 +42,25 @@ def rnd(levels, nd, T, integrator="pade", order=4, ket=False, seed=1, n_states=1
     return [sys_], traj, wl.build_integrators([sys_], traj, integrator=integrator, order=order, ket=ket)
 
 
-for order in (6, 8, 12):
-    systems, traj, _ = wl.config("cz", T=4000)
-    run(f"cz N=9 pade order {order}", systems, traj, wl.build_integrators(systems, traj, order=order))
-    systems, traj, _ = wl.config("hadamard", T=50000)
-    run(f"hadamard N=2 pade order {order}", systems, traj, wl.build_integrators(systems, traj, order=order))
-for N in (5, 6, 7, 8):
-    run(f"dense N={N} nd=2 pade-4", *rnd(N, 2, 8000))
-    run(f"dense N={N} nd=2 exponential", *rnd(N, 2, 4000, integrator="exponential"))
-run("dense N=9 nd=2 ket pade-4 (2 kets)", *rnd(9, 2, 20000, ket=True, n_states=2))
-run("dense N=9 nd=2 ket exponential (2 kets)", *rnd(9, 2, 8000, integrator="exponential", ket=True, n_states=2))
-run("dense N=9 nd=5 pade-4 (tiled: > 4 drives)", *rnd(9, 5, 4000))
-run("dense N=12 nd=2 pade-4", *rnd(12, 2, 3000))
-run("dense N=12 nd=2 exponential", *rnd(12, 2, 1000, integrator="exponential"))
-sy = [wl.random_hermitian_system(9, 2, seed=s, scale=0.4) for s in range(4)]
-tr = wl.random_pulse_trajectory(sy, 2000, 0.2, seed=3)
-run("ensemble 4 x N=9 nd=2 pade-4 (shared controls)", sy, tr, wl.build_integrators(sy, tr))
-run("ensemble 4 x N=9 nd=2 exponential (shared controls)", sy, tr, wl.build_integrators(sy, tr, integrator="exponential"))
+def main():
+    for order in (6, 8, 12):
+        systems, traj, _ = wl.config("cz", T=4000)
+        run(f"cz N=9 pade order {order}", systems, traj, wl.build_integrators(systems, traj, order=order))
+        systems, traj, _ = wl.config("hadamard", T=50000)
+        run(f"hadamard N=2 pade order {order}", systems, traj, wl.build_integrators(systems, traj, order=order))
+    for N in (5, 6, 7, 8):
+        run(f"dense N={N} nd=2 pade-4", *rnd(N, 2, 8000))
+        run(f"dense N={N} nd=2 exponential", *rnd(N, 2, 4000, integrator="exponential"))
+    run("dense N=9 nd=2 ket pade-4 (2 kets)", *rnd(9, 2, 20000, ket=True, n_states=2))
+    run("dense N=9 nd=2 ket exponential (2 kets)", *rnd(9, 2, 8000, integrator="exponential", ket=True, n_states=2))
+    run("dense N=9 nd=5 pade-4 (tiled: > 4 drives)", *rnd(9, 5, 4000))
+    run("dense N=12 nd=2 pade-4", *rnd(12, 2, 3000))
+    run("dense N=12 nd=2 exponential", *rnd(12, 2, 1000, integrator="exponential"))
+    sy = [wl.random_hermitian_system(9, 2, seed=s, scale=0.4) for s in range(4)]
+    tr = wl.random_pulse_trajectory(sy, 2000, 0.2, seed=3)
+    run("ensemble 4 x N=9 nd=2 pade-4 (shared controls)", sy, tr, wl.build_integrators(sy, tr))
+    run("ensemble 4 x N=9 nd=2 exponential (shared controls)", sy, tr, wl.build_integrators(sy, tr, integrator="exponential"))
+
+
+if __name__ == "__main__":
+    main()
