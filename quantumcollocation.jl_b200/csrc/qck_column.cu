@@ -22,19 +22,32 @@ namespace {
 // The IPW items of a warp are IPW CONSECUTIVE knots, i.e. one contiguous range of F, of the Jacobian values and of the Hessian
 // values.  With ST the lanes store to a shared-memory copy of those ranges at the very offsets they would use in global memory
 // (kron blocks N times) and the warp then copies each range out linearly, 512 contiguous bytes per store instruction.  Two phases
-// share the space: F + Jacobian, copied out, then the Hessian.  The derivative-integrator entries inside those ranges are
-// written by the stand-alone aux kernel right after this one (fused into the staged kernel they cost 60 us of dependent loads
-// on 8 warps per SM; the flat aux kernel takes 8 us).
+// share the space: F + Jacobian, copied out, then the Hessian.  The member's constant matrices sit in shared memory for the whole
+// kernel.  The derivative-integrator entries inside those ranges are written by the flat stand-alone aux kernel right after this
+// one.  Measured and dropped (tools/column_bench.py, profiles/r02_column_staged.txt): the same entries filled in by the lanes
+// inside the staged kernel, in three forms (table walk from global memory, from shared memory, entry descriptions resident in
+// registers: +15..130 us -- with 8..12 warps per SM whatever a warp does serially adds to its critical path) and the inputs staged
+// through shared memory by 512-byte loads (+3..9 us: the copy-in serialises with the items' own latency instead of hiding behind it).
 template <int N, int ND, int NC, bool ST>
 __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, const int warp_doubles) {
     constexpr int n2 = 2 * N, blk = n2 * n2, IPW = 32 / NC, NPAIR = ND * (ND + 1) / 2;
     const QckClassDev& c = p.c;
     const int lane = threadIdx.x & 31;
     extern __shared__ double2 col_smem[];
+    // per warp: the staged output ranges;  after the warps: the member's constant matrices (one member: they never change)
     double* const wimg = ST ? reinterpret_cast<double*>(col_smem) + (size_t)(threadIdx.x >> 5) * warp_doubles : nullptr;
     double* const wF = wimg;                                    // phase 1: [IPW][dyn] | [IPW][nnzJ]
     double* const wJ = ST ? wimg + IPW * c.dyn : nullptr;
     double* const wH = wimg;                                    // phase 2: [IPW][nnzH]
+    double2* const sA0 = reinterpret_cast<double2*>(reinterpret_cast<double*>(col_smem) + (size_t)(blockDim.x >> 5) * warp_doubles);
+    double2* const sAj = sA0 + N * N;
+    if constexpr (ST) {
+        const double2* const A0m = c.cmat + (size_t)p.member_begin * c.cmat_stride;
+        const double2* const Ajm = c.dense_aj + (size_t)p.member_begin * ND * N * N;
+        for (int i = threadIdx.x; i < N * N; i += blockDim.x) sA0[i] = A0m[i];
+        for (int i = threadIdx.x; i < ND * N * N; i += blockDim.x) sAj[i] = Ajm[i];
+        __syncthreads();
+    }
     // linear copy of `count` doubles shared -> global (same parity of both addresses by construction: even knot, even offsets)
     auto copy_out = [&](double* g, const double* s, long long count) {
         __syncwarp();
@@ -80,10 +93,13 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
         const long long t = it / nact;
         const int mi = (int)(it - t * nact), m = p.member_begin + mi;
         const int soff = __ldg(p.moff_global + 3 * mi), coff = __ldg(p.moff_global + 3 * mi + 1), roff = __ldg(p.moff_global + 3 * mi + 2);
+        const int n_on = (int)((n_items - base) < (long long)IPW ? (n_items - base) : (long long)IPW);
         const double* zt = p.Z + t * c.zdim;
+        const double* mut = p.mu + t * c.dyn;
+        auto ldin = [](const double* q) { return __ldg(q); };
+        auto ldcm = [](const double2* q) { return ST ? *q : __ldg(q); };
         const int* qd = c.qdst + (size_t)m * QO_COUNT;
         const int gs = gi < IPW ? gi : 0;  // (idle lanes never store)
-        const int n_on = (int)((n_items - base) < (long long)IPW ? (n_items - base) : (long long)IPW);
         double* const oF = ST ? wF + gs * c.dyn : p.F + t * c.dyn;
         double* const oJ = ST ? wJ + gs * p.nnzJ : p.J + t * p.nnzJ;
         double* const oH = ST ? wH + gs * p.nnzH : p.H + t * p.nnzH;
@@ -123,29 +139,29 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
         double2 d[N], s[N], mm[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-            const double u0r = __ldg(zt + soff + col * n2 + r), u0i = __ldg(zt + soff + col * n2 + N + r);
-            const double u1r = __ldg(zt + c.zdim + soff + col * n2 + r), u1i = __ldg(zt + c.zdim + soff + col * n2 + N + r);
+            const double u0r = ldin(zt + soff + col * n2 + r), u0i = ldin(zt + soff + col * n2 + N + r);
+            const double u1r = ldin(zt + c.zdim + soff + col * n2 + r), u1i = ldin(zt + c.zdim + soff + col * n2 + N + r);
             d[r] = make_double2(u1r - u0r, u1i - u0i);
             s[r] = make_double2(u1r + u0r, u1i + u0i);
-            mm[r] = needH ? make_double2(__ldg(p.mu + t * c.dyn + roff + col * n2 + r), __ldg(p.mu + t * c.dyn + roff + col * n2 + N + r)) : make_double2(0.0, 0.0);
+            mm[r] = needH ? make_double2(ldin(mut + roff + col * n2 + r), ldin(mut + roff + col * n2 + N + r)) : make_double2(0.0, 0.0);
         }
-        const double h = free_time ? __ldg(zt + c.dt_off) : c.dt_fixed;
+        const double h = free_time ? ldin(zt + c.dt_off) : c.dt_fixed;
         const double c1h = 0.5 * h, c2h2 = h * h * (1.0 / 12.0), c2h = h * (1.0 / 6.0);
         double a[ND];
 #pragma unroll
-        for (int j = 0; j < ND; ++j) a[j] = __ldg(zt + coff + j);
+        for (int j = 0; j < ND; ++j) a[j] = ldin(zt + coff + j);
         // ---- A = A0 + sum_j a_j A_j ---------------------------------------------------------------------------------------------
-        const double2* const A0g = c.cmat + (size_t)m * c.cmat_stride;  // column-major
-        const double2* const Ajg = c.dense_aj + (size_t)m * ND * N * N;  // [drive][row][column]
+        const double2* const A0g = ST ? sA0 : c.cmat + (size_t)m * c.cmat_stride;  // column-major
+        const double2* const Ajg = ST ? sAj : c.dense_aj + (size_t)m * ND * N * N;  // [drive][row][column]
         double2 A[N][N];
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                double2 v = __ldg(A0g + r + N * k);
+                double2 v = ldcm(A0g + r + N * k);
 #pragma unroll
                 for (int j = 0; j < ND; ++j) {
-                    const double2 w = __ldg(Ajg + (j * N + r) * N + k);
+                    const double2 w = ldcm(Ajg + (j * N + r) * N + k);
                     v.x = fma(a[j], w.x, v.x);
                     v.y = fma(a[j], w.y, v.y);
                 }
@@ -221,10 +237,10 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
                 double2 acol[N];
 #pragma unroll
                 for (int k = 0; k < N; ++k) {  // column `col` of A (a lane-dependent column: rebuilt from the constants)
-                    double2 v = __ldg(A0g + k + N * col);
+                    double2 v = ldcm(A0g + k + N * col);
 #pragma unroll
                     for (int j = 0; j < ND; ++j) {
-                        const double2 w = __ldg(Ajg + (j * N + k) * N + col);
+                        const double2 w = ldcm(Ajg + (j * N + k) * N + col);
                         v.x = fma(a[j], w.x, v.x);
                         v.y = fma(a[j], w.y, v.y);
                     }
@@ -252,7 +268,7 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
                     y[r] = u[j][r] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
-                        const double2 w = __ldg(Ajg + (j * N + r) * N + k);
+                        const double2 w = ldcm(Ajg + (j * N + r) * N + k);
                         if (needJ) cfma(y[r], w, vv[k]);
                         cfma(u[j][r], w, d[k]);
                     }
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
                     z1[r] = z2[r] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int k = 0; k < N; ++k) {
-                        double2 w = __ldg(Ajg + (j * N + k) * N + r);  // conj(A_j[k][r])
+                        double2 w = ldcm(Ajg + (j * N + k) * N + r);  // conj(A_j[k][r])
                         w.y = -w.y;
                         cfma(z1[r], w, mm[k]);
                         cfma(z2[r], w, w1[k]);
@@ -347,22 +363,25 @@ int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int
     if (!enabled || (c.kind != QCK_UNITARY_PADE && !ket) || c.order != 4 || c.N < 2 || c.N > 4 || c.nd < 1 || c.nd > 4 || !c.dense_aj || !c.qdst) return 0;
     typedef void (*kern_t)(const QckLaunch, const int);
     kern_t kern = nullptr;
-    // block-staged write-out (unitaries of a single-system problem; QCK_COLUMN_STAGED=0: stores straight from registers as in
-    // round 1, which kets and ensembles keep)
+    // block-staged variant (single-system problems, unitaries and kets; QCK_COLUMN_STAGED=0: loads and stores straight from / to
+    // global memory as in round 1, which ensembles and several kets sharing their controls keep)
     static const int staged_knob = getenv("QCK_COLUMN_STAGED") ? atoi(getenv("QCK_COLUMN_STAGED")) : 1;
-    bool staged = staged_knob && !ket && L.sole_writer && L.member_end - L.member_begin == 1 && L.npart == 0;
+    // (short calls stay on the direct variant: one launch instead of two, and nothing to gain below a few waves of warps)
+    static const long long staged_min = getenv("QCK_COLUMN_STAGED_MIN") ? atoll(getenv("QCK_COLUMN_STAGED_MIN")) : 1024;
+    bool staged = staged_knob && L.sole_writer && L.member_end - L.member_begin == 1 && L.npart == 0 && L.n_knots >= staged_min;
     const int ipw = 32 / (ket ? 1 : c.N);
     int warp_doubles = 0, wpc = 8;
     size_t smem = 0;
     if (staged) {
-        const long long wd = (long long)ipw * std::max<long long>((long long)c.dyn + L.nnzJ, L.nnzH);
-        warp_doubles = (int)((wd + 1) & ~1LL);
+        const long long od = ((long long)ipw * std::max<long long>((long long)c.dyn + L.nnzJ, L.nnzH) + 1) & ~1LL;  // staged outputs
+        warp_doubles = (int)od;
+        const size_t tab = (size_t)(1 + c.nd) * c.N * c.N * sizeof(double2);
         static const int wpc_knob = getenv("QCK_COLUMN_WPC") ? atoi(getenv("QCK_COLUMN_WPC")) : 4;  // warps per CTA (1..8 measured: flat within 3 %)
-        wpc = (int)std::min<long long>(std::max(1, std::min(8, wpc_knob)), (220LL * 1024) / ((long long)warp_doubles * 8));
-        if ((220LL * 1024) / ((long long)warp_doubles * 8) < 4) { staged = false; wpc = 8; }  // (blocks too large to stage with enough warps per SM)
-        else smem = (size_t)wpc * warp_doubles * sizeof(double);
+        wpc = (int)std::min<long long>(std::max(1, std::min(8, wpc_knob)), (200LL * 1024) / ((long long)warp_doubles * 8));
+        if ((200LL * 1024) / ((long long)warp_doubles * 8) < 4) { staged = false; wpc = 8; }  // (blocks too large to stage with enough warps per SM)
+        else smem = (size_t)wpc * warp_doubles * sizeof(double) + tab;
     }
-#define QCK_COL3(N_, ND_, NC_) (staged && NC_ == N_ ? qck_column_kernel<N_, ND_, N_, true> : qck_column_kernel<N_, ND_, NC_, false>)
+#define QCK_COL3(N_, ND_, NC_) (staged ? qck_column_kernel<N_, ND_, NC_, true> : qck_column_kernel<N_, ND_, NC_, false>)
 #define QCK_COL2(N_, NC_) (c.nd == 1 ? QCK_COL3(N_, 1, NC_) : (c.nd == 2 ? QCK_COL3(N_, 2, NC_) : (c.nd == 3 ? QCK_COL3(N_, 3, NC_) : QCK_COL3(N_, 4, NC_))))
 #define QCK_COL(N_) (ket ? QCK_COL2(N_, 1) : QCK_COL2(N_, N_))
     kern = c.N == 2 ? QCK_COL(2) : (c.N == 3 ? QCK_COL(3) : QCK_COL(4));
@@ -388,9 +407,7 @@ int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int
     static const bool dbg = getenv("QCK_DEBUG") != nullptr;
     if (dbg) fprintf(stderr, "[qcknot] column kernel: N=%d nd=%d staged=%d (%d doubles/warp, %d warps/CTA) CTAs/SM=%d grid=%lld items=%lld\n", c.N, c.nd, (int)staged, warp_doubles, wpc, per_sm, grid, n_items);
     if (staged && L.n_aux) {  // whole knot blocks are stored: the derivative-integrator entries follow in their own pass
-        QckLaunch Lq = L;
-        Lq.aux = nullptr; Lq.n_aux = 0;
-        kern<<<(unsigned)grid, threads, smem, stream>>>(Lq, warp_doubles);
+        kern<<<(unsigned)grid, threads, smem, stream>>>(L, warp_doubles);
         if (launches) ++*launches;
         *done = true;
         const int e = (int)cudaGetLastError();

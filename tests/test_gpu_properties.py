@@ -85,6 +85,40 @@ def test_full_size_properties_cz():
         assert rel_err(H1[t * D.nnzH:(t + 1) * D.nnzH], O.mu_d2F(zz, mm)) < TOL
 
 
+def test_config4_upper_end_T100000_device_resident():
+    """BASELINE config 4 at its upper end (T = 100,000, N = 9; 7.2 GB of values): device-resident pass, a sample of 24 knot blocks
+    spread over the whole range (first, last, chunk borders of the persistent loop) against the oracle, the kron(I_N, B)
+    replicas bit-identical over the whole Jacobian, run-to-run bitwise reproducible (checked on the device)."""
+    import torch
+    systems, traj, integrators = wl.config("cz", T=100000)
+    D = qcknot.QuantumDynamics(integrators, traj)
+    nb = D.n_blocks
+    dev = torch.device("cuda:0")
+    Z = traj.datavec
+    mu = wl.random_multipliers(nb * D.dyn)
+    dZ, dmu = torch.from_numpy(Z).to(dev), torch.from_numpy(mu).to(dev)
+    out = [[torch.empty(nb * n, dtype=torch.float64, device=dev) for n in (D.dyn, D.nnzJ, D.nnzH)] for _ in range(2)]
+    torch.cuda.synchronize()
+    for F, J, H in out:
+        D.eval_device(7, dZ.data_ptr(), dmu.data_ptr(), F.data_ptr(), J.data_ptr(), H.data_ptr(), 0)
+    D.synchronize()
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    F, J, H = out[0]
+    N = 9
+    blk = J.view(nb, D.nnzJ)[:, : 4 * N**3].view(nb, N, 4 * N * N)
+    assert bool((blk == blk[:, :1]).all())
+    idx = sorted(set(np.linspace(0, nb - 1, 20).astype(int).tolist() + [1, 147, 148, nb - 2]))
+    for t in idx:
+        sub = qcknot.NamedTrajectory({n: traj[n][:, t:t + 2] for n in traj.names}, controls=("dda", "Δt"), timestep="Δt")
+        O = oracle_dynamics(wl.build_integrators(systems, sub), sub)
+        zz, mm = sub.datavec, mu[t * D.dyn:(t + 1) * D.dyn]
+        assert rel_err(F[t * D.dyn:(t + 1) * D.dyn].cpu().numpy(), O.F(zz)) < TOL
+        assert rel_err(J[t * D.nnzJ:(t + 1) * D.nnzJ].cpu().numpy(), O.dF(zz)) < TOL
+        assert rel_err(H[t * D.nnzH:(t + 1) * D.nnzH].cpu().numpy(), O.mu_d2F(zz, mm)) < TOL
+    D.close()
+
+
 def test_exponential_residual_vanishes_on_exact_propagation():
     """U_{t+1} = exp(-i H(a_t) dt_t) U_t  =>  the exponential residual is zero to rounding, at T = 2,000."""
     import scipy.linalg as sla
@@ -261,6 +295,37 @@ def test_large_level_kernel_on_small_problems():
     e.update({"QCK_BIG": "1", "QCK_RS3": "0"})
     out = subprocess.run([sys.executable, "-c", _BIG_SCRIPT.format(root=root)], env=e, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "big ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("levels,nd,ket,T", [(2, 1, False, 4999), (3, 2, False, 3001), (3, 4, False, 1203), (4, 2, False, 2502), (4, 4, False, 1300),
+                                             (2, 2, True, 5003), (3, 3, True, 4001), (4, 2, True, 3333)])
+def test_column_kernel_every_block_single_systems(levels, nd, ket, T):
+    """Block-staged column kernel (single-system problems, 2..4 levels, unitaries and kets): more knots than resident warps, knot
+    counts that leave a partial last group; every block against the C port of the oracle, staged = direct variant bit for bit."""
+    import subprocess, sys, tempfile
+    from oracle.c_port import CPort
+    root = os.path.dirname(HERE)
+    sys_ = wl.random_hermitian_system(levels, nd, seed=levels * 10 + nd, scale=0.4)
+    traj = wl.random_pulse_trajectory([sys_], T, 0.2, seed=3, ket=ket)
+    integrators = wl.build_integrators([sys_], traj, ket=ket)
+    D = qcknot.QuantumDynamics(integrators, traj)
+    Z, mu = traj.datavec, wl.random_multipliers(D.n_blocks * D.dyn)
+    F, J, H = D.eval_all(Z, mu)
+    Fo, Jo, Ho = CPort(oracle_dynamics(integrators, traj)).eval(Z, mu)
+    assert rel_err(F, Fo) < TOL and rel_err(J, Jo) < TOL and rel_err(H, Ho) < TOL
+    assert np.array_equal(J, D.dF(Z)) and np.array_equal(H, D.mu_d2F(Z, mu)) and np.array_equal(F, D.F(Z))
+    D.close()
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import qcknot; from qcknot import workloads as wl\n"
+            "s = wl.random_hermitian_system(%d, %d, seed=%d, scale=0.4); tr = wl.random_pulse_trajectory([s], %d, 0.2, seed=3, ket=%r)\n"
+            "D = qcknot.QuantumDynamics(wl.build_integrators([s], tr, ket=%r), tr)\n"
+            "F, J, H = D.eval_all(tr.datavec, wl.random_multipliers(D.n_blocks * D.dyn)); np.savez(sys.argv[1], F=F, J=J, H=H)\n"
+            % (root, levels, nd, levels * 10 + nd, T, ket, ket))
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "direct.npz")
+        out = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, QCK_COLUMN_STAGED="0"), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        ref = np.load(f)
+        assert np.array_equal(F, ref["F"]) and np.array_equal(J, ref["J"]) and np.array_equal(H, ref["H"])
 
 
 @pytest.mark.parametrize("name,T,integ", [("cz", 2500, "pade"), ("hadamard", 5000, "pade"), ("ket", 3000, "pade"), ("cz", 1300, "exponential"),

@@ -10,3 +10,6 @@ systems, traj, integ = wl.config("hadamard", T=T)
 run("hadamard N=2 nd=2", systems, traj, integ)
 for N, nd, t in ((2, 1, T), (3, 2, T // 2), (4, 2, T // 4), (4, 4, T // 4)):
     run(f"random N={N} nd={nd}", *rnd(N, nd, t))
+systems, traj, integ = wl.config("ket", T=T)
+run("two kets N=2 nd=2 (shared controls: direct variant)", systems, traj, integ)
+run("random ket N=3 nd=2", *rnd(3, 2, T, ket=True))
