@@ -1404,7 +1404,10 @@ qck_quantum_kernel(const QckLaunch p) {
 }
 
 // stand-alone pass over the derivative-integrator entries: (knot, entry) pairs over the threads, consecutive threads on the
-// entries of one knot
+// entries of one knot.  26 us for the 2.4 M entries of the Hadamard problem at T = 100,000 (ncu), and the form does not matter:
+// one entry per lane with a warp per knot 37 us, a thread per knot over a shared-memory table 38 us (with a switch, branch-free, or
+// with the operand loads of 8 entries batched: 38..42 us) -- the cost is the 8-byte stores themselves, partial writes of sectors
+// the previous kernel has just streamed out (profiles/r02_column_staged.txt)
 __global__ void __launch_bounds__(256) qck_aux_kernel(const QckLaunch p) {
     const long long total = p.n_knots * p.n_aux;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
