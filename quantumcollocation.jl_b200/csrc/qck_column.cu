@@ -53,7 +53,11 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
         __syncwarp();
         if ((reinterpret_cast<uintptr_t>(g) & 8) == 0) {
             const int pairs = (int)(count >> 1);
+#if QCK_STORE_HINT
+            for (int k = lane; k < pairs; k += 32) __stcs(reinterpret_cast<double2*>(g) + k, reinterpret_cast<const double2*>(s)[k]);
+#else
             for (int k = lane; k < pairs; k += 32) reinterpret_cast<double2*>(g)[k] = reinterpret_cast<const double2*>(s)[k];
+#endif
             if ((count & 1) && lane == 0) g[count - 1] = s[count - 1];
         } else {
             for (int k = lane; k < (int)count; k += 32) g[k] = s[k];

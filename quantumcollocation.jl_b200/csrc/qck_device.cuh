@@ -145,9 +145,29 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 // TMA bulk copy shared -> global (one thread issues; the copy engine drains the image while the CTA computes on)
+// QCK_STORE_HINT (compile-time A/B knob): L2 eviction policy of the value-array stores; 0 = none, 1 = evict-first (default),
+// 2 = evict-last, 3 = evict-unchanged.  The value arrays are written once and never read back by the kernels, and at T = 10,000 a
+// pass writes 5x the L2: with evict-first the written lines leave L2 in the order they arrive instead of competing with the inputs
+// and the staging traffic.  Measured on the CZ problem (row-slice kernel, profiles/r02_store_hint.txt): 199.2 -> 188.3 us at
+// T = 10,000, 1,892 -> 1,778 us at T = 100,000; evict-last 202.8 us, evict-unchanged 199.4 us.
+#ifndef QCK_STORE_HINT
+#define QCK_STORE_HINT 1
+#endif
 __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+#if QCK_STORE_HINT
+    unsigned long long pol;
+#if QCK_STORE_HINT == 1
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+#elif QCK_STORE_HINT == 2
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;\n" : "=l"(pol));
+#endif
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(s), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
