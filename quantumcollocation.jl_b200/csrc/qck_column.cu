@@ -71,15 +71,22 @@ __global__ void __launch_bounds__(256) qck_column_kernel(const QckLaunch p, cons
     const long long nslots = (long long)gridDim.x * (blockDim.x >> 5) * IPW;
     const bool free_time = c.free_time;
 
-    auto store_run = [](double* dst, const double (&v)[n2]) {  // 2N consecutive doubles, 16-byte stores where aligned
+#ifndef QCK_DIRECT_STCS
+#define QCK_DIRECT_STCS 0  // (A/B knob) direct variant: st.global.cs (L2 evict-first) for the value-array stores
+#endif
+    auto st2 = [](double* dst, double2 v) {
+        if constexpr (!ST && QCK_DIRECT_STCS) __stcs(reinterpret_cast<double2*>(dst), v);
+        else *reinterpret_cast<double2*>(dst) = v;
+    };
+    auto store_run = [&](double* dst, const double (&v)[n2]) {  // 2N consecutive doubles, 16-byte stores where aligned
         if (reinterpret_cast<uintptr_t>(dst) & 8) {
             dst[0] = v[0];
 #pragma unroll
-            for (int i = 0; i < N - 1; ++i) *reinterpret_cast<double2*>(dst + 1 + 2 * i) = make_double2(v[1 + 2 * i], v[2 + 2 * i]);
+            for (int i = 0; i < N - 1; ++i) st2(dst + 1 + 2 * i, make_double2(v[1 + 2 * i], v[2 + 2 * i]));
             dst[n2 - 1] = v[n2 - 1];
         } else {
 #pragma unroll
-            for (int i = 0; i < N; ++i) *reinterpret_cast<double2*>(dst + 2 * i) = make_double2(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < N; ++i) st2(dst + 2 * i, make_double2(v[2 * i], v[2 * i + 1]));
         }
     };
     auto rdot = [](double2 x, double2 y) { return x.x * y.x + x.y * y.y; };  // Re <x, y>
