@@ -354,7 +354,7 @@ int qck_launch_big(const QckLaunch& L, int sm_count, cudaStream_t stream, int* l
     if (L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem) {
         per_sm = L.plan->per_sm;
     } else {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, QCK_MAX_DYN_SMEM);
         if (e != cudaSuccess) return (int)e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
         if (e != cudaSuccess) return (int)e;

@@ -405,7 +405,7 @@ int qck_launch_column(const QckLaunch& L, int sm_count, cudaStream_t stream, int
         per_sm = L.plan->per_sm;
     } else {
         cudaError_t e = cudaSuccess;
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, QCK_MAX_DYN_SMEM);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
         if (e != cudaSuccess) return (int)e;
         if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = smem; L.plan->per_sm = per_sm; }

@@ -461,7 +461,7 @@ int qck_launch_genexp(const QckLaunch& L, int sm_count, cudaStream_t stream, int
     if (L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem) {
         per_sm = L.plan->per_sm;
     } else {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, QCK_MAX_DYN_SMEM);
         if (e != cudaSuccess) return (int)e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem);
         if (e != cudaSuccess) return (int)e;

@@ -125,6 +125,10 @@ struct QckClassDev {
     double pade_r[8];
 };
 
+// Opt-in cap on dynamic shared memory, always the device maximum: the attribute belongs to the kernel FUNCTION, so a launcher that set
+// it to its own class's size would lower it under another live handle that runs the same instantiation with a larger size.
+#define QCK_MAX_DYN_SMEM (227 * 1024)
+
 // Launch geometry of one class, filled by the launcher at the first launch on a device (attribute + occupancy calls
 // happen once per handle, not on every callback).
 struct QckPlanCache {

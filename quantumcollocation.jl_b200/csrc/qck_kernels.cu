@@ -1564,7 +1564,7 @@ int qck_launch_quantum(const QckLaunch& L0, int sm_count, cudaStream_t stream, i
         if (L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem) {
             per_sm = L.plan->per_sm;  // found at an earlier launch of this class on this device
         } else {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, QCK_MAX_DYN_SMEM);
             if (e != cudaSuccess) return (int)e;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
             if (e != cudaSuccess) return (int)e;

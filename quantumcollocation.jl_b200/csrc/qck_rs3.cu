@@ -401,7 +401,7 @@ int qck_launch_rs3(const QckLaunch& L, int sm_count, cudaStream_t stream, int* l
     const size_t smem = qck_rs3_smem(c, hoff, kpc);
     if (smem > 227 * 1024) return (int)cudaErrorInvalidConfiguration;
     if (!(L.plan && L.plan->kern == (const void*)kern && L.plan->smem == smem)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, QCK_MAX_DYN_SMEM);
         if (e != cudaSuccess) return (int)e;
         if (L.plan) { L.plan->kern = (const void*)kern; L.plan->smem = smem; L.plan->per_sm = 1; }
     }

@@ -119,6 +119,27 @@ def test_config4_upper_end_T100000_device_resident():
     D.close()
 
 
+def test_two_live_handles_share_a_kernel_with_different_shared_memory():
+    """Two problems alive at once that run the SAME kernel instantiation with different dynamic shared-memory sizes (the generic
+    spectral kernel takes the level count at run time): the opt-in cap is a property of the function, so the small problem's
+    launcher must not lower it under the large one."""
+    def problem(levels, seed):
+        sys_ = wl.random_hermitian_system(levels, 2, seed=seed, scale=0.3)
+        traj = wl.random_pulse_trajectory([sys_], 6, 0.2, seed=seed)
+        return traj, wl.build_integrators([sys_], traj, integrator="exponential")
+    (trA, iA), (trB, iB) = problem(12, 3), problem(6, 4)
+    A, B = qcknot.QuantumDynamics(iA, trA), qcknot.QuantumDynamics(iB, trB)
+    muA, muB = wl.random_multipliers(A.n_blocks * A.dyn), wl.random_multipliers(B.n_blocks * B.dyn)
+    first = A.eval_all(trA.datavec, muA)
+    B.eval_all(trB.datavec, muB)
+    again = A.eval_all(trA.datavec + 0.0, muA)
+    for x, y in zip(first, again):
+        assert np.array_equal(x, y)
+    OB = oracle_dynamics(iB, trB)
+    assert rel_err(B.dF(trB.datavec), OB.dF(trB.datavec)) < TOL
+    A.close(); B.close()
+
+
 def test_exponential_residual_vanishes_on_exact_propagation():
     """U_{t+1} = exp(-i H(a_t) dt_t) U_t  =>  the exponential residual is zero to rounding, at T = 2,000."""
     import scipy.linalg as sla
