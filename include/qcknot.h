@@ -152,12 +152,13 @@ int qck_eval_all(qck_handle* h, const double* Z, const double* mu, double* F, do
  * cudaStream_t (NULL = the handle's own stream).  Asynchronous: returns after the launches are enqueued. */
 int qck_eval_device(qck_handle* h, uint32_t mask, const double* dZ, const double* dmu, double* dF, double* dJ,
                     double* dH, void* stream);
-/* the handle's own device buffers (what the host-buffer entry points stage through) */
+/* the handle's own device buffers (what the host-buffer entry points stage through); under a structure_order other than CSC
+ * dJ / dH are the caller-order arrays that qck_eval_resident fills (the canonical arrays stay internal) */
 int qck_device_buffers(qck_handle* h, double** dZ, double** dmu, double** dF, double** dJ, double** dH);
 int qck_synchronize(qck_handle* h);
 
-/* Hessian positions (0-based, within one knot block) that receive contributions from more than one integrator
- * (shared controls in the sampling problem).  With ensemble sharding each handle leaves its local partial sum
+/* Hessian positions (0-based, within one knot block, in the handle's structure order) that receive contributions from more than one
+ * integrator (shared controls in the sampling problem; none under QCK_ORDER_PER_INTEGRATOR, where every contribution has its own entry).  With ensemble sharding each handle leaves its local partial sum
  * there and the caller all-reduces exactly these positions.  pos may be NULL to query the count. */
 int qck_shared_hessian_positions(const qck_handle* h, int64_t* count, int64_t* pos);
 
