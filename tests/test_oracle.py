@@ -196,6 +196,32 @@ def test_dense_contract_sums_duplicates_and_symmetrises():
     assert M[0, 2] == 3
 
 
+@pytest.mark.parametrize("name,kw", [("hadamard", {"T": 5}), ("sampling", {"T": 3, "n_systems": 4}), ("ket", {"T": 4, "free_time": False}),
+                                     ("hadamard", {"T": 4, "integrator": "exponential"})])
+def test_structure_order_policies_describe_the_same_matrices(name, kw):
+    """The three intra-knot orders (csc | row_major | per_integrator with duplicates) are different listings of the same sparse
+    Jacobian and Hessian of the Lagrangian: rebuilt with the reference's dense() (duplicates sum, test/test_utils.jl:14-27) they
+    agree, and per_integrator has duplicates exactly where integrators share a Hessian position."""
+    import qcknot  # host objects only (no device needed)
+    from oracle.bridge import oracle_dynamics
+    from qcknot import workloads as wl
+    systems, traj, integrators = wl.config(name, **kw)
+    Z = traj.datavec
+    O = {o: oracle_dynamics(integrators, traj, structure_order=o) for o in ("csc", "row_major", "per_integrator")}
+    mu = wl.random_multipliers((traj.T - 1) * O["csc"].dyn)
+    nZ, nF = traj.T * traj.dim, (traj.T - 1) * O["csc"].dyn
+    Jd = {o: ko.dense(D.dF(Z), D.dF_structure, (nF, nZ)) for o, D in O.items()}
+    Hd = {o: ko.dense(D.mu_d2F(Z, mu), D.mu_d2F_structure, (nZ, nZ)) for o, D in O.items()}
+    for o in ("row_major", "per_integrator"):
+        assert np.array_equal(Jd[o], Jd["csc"])
+        assert np.abs(Hd[o] - Hd["csc"]).max() <= 1e-14 * max(1.0, np.abs(Hd["csc"]).max())
+        assert sorted(O[o].dF_structure) == sorted(O["csc"].dF_structure)
+    assert sorted(O["row_major"].mu_d2F_structure) == sorted(O["csc"].mu_d2F_structure)
+    dup = len(O["per_integrator"].mu_d2F_structure) - len(set(O["per_integrator"].mu_d2F_structure))
+    assert dup == len(O["per_integrator"].mu_d2F_structure) - len(O["csc"].mu_d2F_structure)
+    assert (dup > 0) == (sum(1 for I in integrators if type(I).__name__ != "DerivativeIntegrator") > 1)  # shared controls / timestep
+
+
 @pytest.mark.parametrize("case", ["unitary", "ket", "sampling", "fixed"])
 def test_c_port_matches_numpy_oracle(case):
     import qcknot  # host objects only (no device needed)
